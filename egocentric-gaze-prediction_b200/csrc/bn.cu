@@ -1,0 +1,209 @@
+// BatchNorm2d (reference utils.py:72, models/model_SP.py:12, models/late_fusion.py:10-12) split into the
+// pieces that fuse around the tcgen05 conv:
+//   conv epilogue      -> per-tile (mean, M2) partials            (conv3x3_tc.cu, phase 2)
+//   egaze_col_stats    -> the same partials for a plain [rows][C] fp32 matrix (fusion layer after pair-max)
+//   egaze_bn_finalize  -> Chan-combine partials in fp64 -> batch mean / biased var, running-stat update
+//                         (momentum, unbiased var, exactly nn.BatchNorm2d), folded scale/shift
+//   egaze_bn_apply     -> y = relu(x*scale+shift) [-> 2x2 max-pool] -> NHWC split-bf16 (and/or fp32)
+//   egaze_pairmax      -> max over the two streams of the fusion layer (MaxPool3d((2,1,1)), model_SP.py:11)
+// All HBM-bound: float4 (4 channels) per thread, grid sized in multiples of the SM count.
+#include "common.cuh"
+
+namespace {
+
+// partial: [T][2][C] (mean, M2), cnt: [T].  One thread column per channel, 32 slices of tiles per block.
+__global__ void __launch_bounds__(1024)
+bn_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ cnt, int T, int C, float eps,
+                   float momentum, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ mean_out,
+                   float* __restrict__ invstd_out, float* __restrict__ scale_out, float* __restrict__ shift_out) {
+  __shared__ double s_n[32][33], s_mean[32][33], s_m2[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int sl = threadIdx.y;
+  double n = 0.0, mean = 0.0, m2 = 0.0;
+  if (c < C) {
+    for (int t = sl; t < T; t += 32) {
+      const double nb = (double)cnt[t];
+      if (nb <= 0.0) continue;
+      const double mb = (double)partial[((size_t)t * 2 + 0) * C + c];
+      const double m2b = (double)partial[((size_t)t * 2 + 1) * C + c];
+      const double nn = n + nb;
+      const double d = mb - mean;
+      mean += d * nb / nn;
+      m2 += m2b + d * d * n * nb / nn;
+      n = nn;
+    }
+  }
+  s_n[sl][threadIdx.x] = n;
+  s_mean[sl][threadIdx.x] = mean;
+  s_m2[sl][threadIdx.x] = m2;
+  __syncthreads();
+  if (sl == 0 && c < C) {
+    n = 0.0; mean = 0.0; m2 = 0.0;
+    for (int i = 0; i < 32; ++i) {
+      const double nb = s_n[i][threadIdx.x];
+      if (nb <= 0.0) continue;
+      const double mb = s_mean[i][threadIdx.x], m2b = s_m2[i][threadIdx.x];
+      const double nn = n + nb;
+      const double d = mb - mean;
+      mean += d * nb / nn;
+      m2 += m2b + d * d * n * nb / nn;
+      n = nn;
+    }
+    const double var_b = m2 / n;                       // biased: used to normalise
+    const double var_u = n > 1.0 ? m2 / (n - 1.0) : var_b;  // unbiased: goes into running_var
+    const float invstd = (float)(1.0 / sqrt(var_b + (double)eps));
+    if (mean_out) mean_out[c] = (float)mean;
+    if (invstd_out) invstd_out[c] = invstd;
+    if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+    if (running_var) running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)var_u;
+    const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+    const float sc = g * invstd;
+    if (scale_out) scale_out[c] = sc;
+    if (shift_out) shift_out[c] = b - (float)mean * sc;
+  }
+}
+
+// eval-mode fold: scale = gamma / sqrt(running_var + eps), shift = beta - running_mean * scale (+ conv bias * scale)
+__global__ void bn_fold_kernel(const float* gamma, const float* beta, const float* rm, const float* rv,
+                               const float* conv_bias, float eps, int C, float* scale, float* shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float sc = (gamma ? gamma[c] : 1.f) / sqrtf(rv[c] + eps);
+  float sh = (beta ? beta[c] : 0.f) - rm[c] * sc;
+  if (conv_bias) sh += conv_bias[c] * sc;
+  scale[c] = sc;
+  shift[c] = sh;
+}
+
+// x: [rows][C] fp32 -> partial (mean, M2) per block of `rows_per_blk` rows.  blockDim = (32 ch-quads? no: 128 ch)
+__global__ void col_stats_kernel(const float* __restrict__ x, int rows, int C, int rows_per_blk,
+                                 float* __restrict__ partial, float* __restrict__ cnt) {
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;
+  const int r0 = blockIdx.x * rows_per_blk;
+  const int r1 = min(rows, r0 + rows_per_blk);
+  if (c >= C) return;
+  float sum = 0.f;
+  for (int r = r0; r < r1; ++r) sum += x[(size_t)r * C + c];
+  const float mean = sum / (float)(r1 - r0);
+  float m2 = 0.f;
+  for (int r = r0; r < r1; ++r) {
+    const float d = x[(size_t)r * C + c] - mean;
+    m2 = fmaf(d, d, m2);
+  }
+  partial[((size_t)blockIdx.x * 2 + 0) * C + c] = mean;
+  partial[((size_t)blockIdx.x * 2 + 1) * C + c] = m2;
+  if (c == 0) cnt[blockIdx.x] = (float)(r1 - r0);
+}
+
+// y = relu?(x*scale+shift), optional 2x2 max pool; x NHWC fp32 [N,H,W,C]; outputs NHWC [N,Ho,Wo,C].
+__global__ void bn_apply_kernel(const float* __restrict__ x, int N, int H, int W, int C, const float* __restrict__ scale,
+                                const float* __restrict__ shift, int relu, int pool, float* __restrict__ out_f32,
+                                __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
+  const int Ho = pool ? H / 2 : H, Wo = pool ? W / 2 : W;
+  const int C4 = C / 4;
+  const size_t total = (size_t)N * Ho * Wo * C4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % C4);
+    size_t pix = i / C4;
+    const int ow = (int)(pix % Wo);
+    pix /= Wo;
+    const int oh = (int)(pix % Ho);
+    const int n = (int)(pix / Ho);
+    const float4 sc = *reinterpret_cast<const float4*>(scale + c4 * 4);
+    const float4 sh = *reinterpret_cast<const float4*>(shift + c4 * 4);
+    float4 v;
+    if (!pool) {
+      const float4 a = *reinterpret_cast<const float4*>(x + (((size_t)n * H + oh) * W + ow) * C + c4 * 4);
+      v.x = fmaf(a.x, sc.x, sh.x); v.y = fmaf(a.y, sc.y, sh.y); v.z = fmaf(a.z, sc.z, sh.z); v.w = fmaf(a.w, sc.w, sh.w);
+    } else {
+      v = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const float4 a =
+              *reinterpret_cast<const float4*>(x + (((size_t)n * H + 2 * oh + dy) * W + 2 * ow + dx) * C + c4 * 4);
+          v.x = fmaxf(v.x, fmaf(a.x, sc.x, sh.x));
+          v.y = fmaxf(v.y, fmaf(a.y, sc.y, sh.y));
+          v.z = fmaxf(v.z, fmaf(a.z, sc.z, sh.z));
+          v.w = fmaxf(v.w, fmaf(a.w, sc.w, sh.w));
+        }
+    }
+    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    const size_t o = i * 4;
+    if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = v;
+    if (out_hi) {
+      __nv_bfloat16 h[4], l[4];
+      split_bf16(v.x, h[0], l[0]); split_bf16(v.y, h[1], l[1]); split_bf16(v.z, h[2], l[2]); split_bf16(v.w, h[3], l[3]);
+      *reinterpret_cast<uint2*>(out_hi + o) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
+      if (out_lo) *reinterpret_cast<uint2*>(out_lo + o) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+    }
+  }
+}
+
+// out[b] = max(x[b], x[b+B]) elementwise over [B][M] fp32 (M = H*W*C); optional folded affine + relu + split
+__global__ void pairmax_kernel(const float* __restrict__ x, size_t per_stream, float* __restrict__ out) {
+  const size_t n4 = per_stream / 4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 a = reinterpret_cast<const float4*>(x)[i];
+    const float4 b = reinterpret_cast<const float4*>(x + per_stream)[i];
+    reinterpret_cast<float4*>(out)[i] = make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
+  }
+}
+
+}  // namespace
+
+extern "C" int egaze_bn_finalize(const float* partial, const float* cnt, int T, int C, float eps, float momentum,
+                                 const float* gamma, const float* beta, float* running_mean, float* running_var,
+                                 float* mean_out, float* invstd_out, float* scale_out, float* shift_out, void* stream) {
+  EGAZE_CHECK_ARG(partial && cnt && T > 0 && C > 0, "bn_finalize: bad args");
+  dim3 block(32, 32), grid(ceil_div(C, 32));
+  bn_finalize_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(partial, cnt, T, C, eps, momentum, gamma, beta,
+                                                               running_mean, running_var, mean_out, invstd_out,
+                                                               scale_out, shift_out);
+  EGAZE_LAUNCH_CHECK();
+  return EGAZE_OK;
+}
+
+extern "C" int egaze_bn_fold(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                             const float* conv_bias, float eps, int C, float* scale, float* shift, void* stream) {
+  EGAZE_CHECK_ARG(running_mean && running_var && scale && shift && C > 0, "bn_fold: bad args");
+  bn_fold_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(gamma, beta, running_mean, running_var, conv_bias,
+                                                                     eps, C, scale, shift);
+  EGAZE_LAUNCH_CHECK();
+  return EGAZE_OK;
+}
+
+// rows_per_blk is fixed at 128 so the caller can size partial as [ceil(rows/128)][2][C].
+extern "C" int egaze_col_stats(const float* x, long long rows, int C, float* partial, float* cnt, void* stream) {
+  EGAZE_CHECK_ARG(x && partial && cnt && rows > 0 && C > 0, "col_stats: bad args");
+  dim3 grid((unsigned)((rows + 127) / 128), ceil_div(C, 128)), block(128);
+  col_stats_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, (int)rows, C, 128, partial, cnt);
+  EGAZE_LAUNCH_CHECK();
+  return EGAZE_OK;
+}
+
+extern "C" int egaze_bn_apply(const float* x, int N, int H, int W, int C, const float* scale, const float* shift,
+                              int relu, int pool, float* out_f32, void* out_hi, void* out_lo, void* stream) {
+  EGAZE_CHECK_ARG(x && scale && shift && (out_f32 || out_hi), "bn_apply: bad args");
+  EGAZE_CHECK_ARG(C % 4 == 0, "bn_apply: C %% 4 != 0");
+  EGAZE_CHECK_ARG(!pool || ((H | W) & 1) == 0, "bn_apply: pool needs even H, W");
+  const int Ho = pool ? H / 2 : H, Wo = pool ? W / 2 : W;
+  const size_t total = (size_t)N * Ho * Wo * (C / 4);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  bn_apply_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, N, H, W, C, scale, shift, relu, pool, out_f32,
+                                                           (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo);
+  EGAZE_LAUNCH_CHECK();
+  return EGAZE_OK;
+}
+
+extern "C" int egaze_pairmax(const float* x, long long per_stream, float* out, void* stream) {
+  EGAZE_CHECK_ARG(x && out && per_stream > 0 && per_stream % 4 == 0, "pairmax: bad args");
+  int blocks = (int)((per_stream / 4 + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  pairmax_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, (size_t)per_stream, out);
+  EGAZE_LAUNCH_CHECK();
+  return EGAZE_OK;
+}

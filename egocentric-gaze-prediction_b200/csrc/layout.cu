@@ -1,0 +1,188 @@
+// Layout kernels: the reference API is NCHW fp32 (SURVEY 8b "Tensor conventions"); internally the
+// conv kernels consume NHWC split-bf16 activations and [tap][Cout][Cin_p] split-bf16 weights.
+// All of these are HBM-bound element shuffles: 32x32 smem-tile transposes so both sides are coalesced.
+#include "common.cuh"
+
+namespace {
+
+// x: [N][C][HW] fp32  ->  hi/lo: [N][HW][Cp] bf16 (channels >= C zero-filled)
+__global__ void nchw_to_nhwc_split_kernel(const float* __restrict__ x, int C, int HW, int Cp,
+                                          __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const float* xn = x + (size_t)n * C * HW;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && p < HW) ? xn[(size_t)c * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + i, c = c0 + threadIdx.x;
+    if (p < HW && c < Cp) {
+      const float v = tile[threadIdx.x][i];
+      __nv_bfloat16 h, l;
+      split_bf16(v, h, l);
+      const size_t o = ((size_t)n * HW + p) * Cp + c;
+      hi[o] = h;
+      if (lo) lo[o] = l;
+    }
+  }
+}
+
+// hi/lo (or f32): [N][HW][Cs] (channel stride Cs >= C)  ->  out: [N][C][HW] fp32
+__global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                                    const float* __restrict__ f32, int C, int HW, int Cs, float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + i, c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (p < HW && c < C) {
+      const size_t o = ((size_t)n * HW + p) * Cs + c;
+      if (f32) v = f32[o];
+      else {
+        v = __bfloat162float(hi[o]);
+        if (lo) v += __bfloat162float(lo[o]);
+      }
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    if (c < C && p < HW) out[((size_t)n * C + c) * HW + p] = tile[threadIdx.x][i];
+  }
+}
+
+// x: [N][C][HW] fp32 -> out: [N][HW][C] fp32
+__global__ void nchw_to_nhwc_f32_kernel(const float* __restrict__ x, int C, int HW, float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && p < HW) ? x[((size_t)n * C + c) * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + i, c = c0 + threadIdx.x;
+    if (p < HW && c < C) out[((size_t)n * HW + p) * C + c] = tile[threadIdx.x][i];
+  }
+}
+
+// fp32 NHWC -> split planes (same shape), elementwise
+__global__ void f32_to_split_kernel(const float* __restrict__ x, size_t n, __nv_bfloat16* __restrict__ hi,
+                                    __nv_bfloat16* __restrict__ lo) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    __nv_bfloat16 h, l;
+    split_bf16(x[i], h, l);
+    hi[i] = h;
+    if (lo) lo[i] = l;
+  }
+}
+
+// w: OIHW fp32 [Co][Ci][3][3].
+//  mode 0 (fprop) : out[(r*3+s)][co][ci]            rows = Co, cols = Ci_p  (ci >= Ci zero)
+//  mode 1 (dgrad) : out[((2-r)*3+(2-s))][ci][co]    rows = Ci, cols = Co_p  (co >= Co zero)
+__global__ void pack_w3x3_kernel(const float* __restrict__ w, int Co, int Ci, int rows, int cols_p, int mode,
+                                 __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  const size_t total = (size_t)9 * rows * cols_p;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int col = (int)(i % cols_p);
+    const int row = (int)((i / cols_p) % rows);
+    const int tap = (int)(i / ((size_t)cols_p * rows));
+    float v = 0.f;
+    if (mode == 0) {
+      if (col < Ci) v = w[((size_t)row * Ci + col) * 9 + tap];
+    } else {
+      if (col < Co) v = w[((size_t)col * Ci + row) * 9 + (8 - tap)];
+    }
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    hi[i] = h;
+    if (lo) lo[i] = l;
+  }
+}
+
+// dwp: [9][Co][Ci_p] fp32 (wgrad accumulator)  ->  gw: OIHW [Co][Ci][3][3]  (gw = beta*gw + dwp)
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, int Co, int Ci, int Ci_p, float beta,
+                                    float* __restrict__ gw) {
+  const size_t total = (size_t)Co * Ci * 9;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int tap = (int)(i % 9);
+    const int ci = (int)((i / 9) % Ci);
+    const int co = (int)(i / ((size_t)9 * Ci));
+    const float v = dwp[((size_t)tap * Co + co) * Ci_p + ci];
+    gw[i] = beta == 0.f ? v : fmaf(beta, gw[i], v);
+  }
+}
+
+}  // namespace
+
+extern "C" int egaze_nchw_to_nhwc_split(const float* x, int N, int C, int H, int W, int Cp, void* hi, void* lo,
+                                        void* stream) {
+  EGAZE_CHECK_ARG(x && hi && Cp >= C, "nchw_to_nhwc_split: bad args");
+  const int HW = H * W;
+  dim3 grid(ceil_div(HW, 32), ceil_div(Cp, 32), N), block(32, 8);
+  nchw_to_nhwc_split_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, C, HW, Cp, (__nv_bfloat16*)hi,
+                                                                      (__nv_bfloat16*)lo);
+  EGAZE_LAUNCH_CHECK();
+  return EGAZE_OK;
+}
+
+extern "C" int egaze_nhwc_to_nchw(const void* hi, const void* lo, const float* f32, int N, int C, int H, int W, int Cs,
+                                  float* out, void* stream) {
+  EGAZE_CHECK_ARG((hi || f32) && out && Cs >= C, "nhwc_to_nchw: bad args");
+  const int HW = H * W;
+  dim3 grid(ceil_div(HW, 32), ceil_div(C, 32), N), block(32, 8);
+  nhwc_to_nchw_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)hi, (const __nv_bfloat16*)lo, f32,
+                                                                C, HW, Cs, out);
+  EGAZE_LAUNCH_CHECK();
+  return EGAZE_OK;
+}
+
+extern "C" int egaze_nchw_to_nhwc_f32(const float* x, int N, int C, int H, int W, float* out, void* stream) {
+  EGAZE_CHECK_ARG(x && out, "nchw_to_nhwc_f32: bad args");
+  const int HW = H * W;
+  dim3 grid(ceil_div(HW, 32), ceil_div(C, 32), N), block(32, 8);
+  nchw_to_nhwc_f32_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, C, HW, out);
+  EGAZE_LAUNCH_CHECK();
+  return EGAZE_OK;
+}
+
+extern "C" int egaze_f32_to_split(const float* x, long long n, void* hi, void* lo, void* stream) {
+  EGAZE_CHECK_ARG(x && hi && n >= 0, "f32_to_split: bad args");
+  if (n == 0) return EGAZE_OK;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  f32_to_split_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, (size_t)n, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+  EGAZE_LAUNCH_CHECK();
+  return EGAZE_OK;
+}
+
+extern "C" int egaze_pack_w3x3(const float* w_oihw, int Cout, int Cin, int cols_p, int mode, void* hi, void* lo,
+                               void* stream) {
+  EGAZE_CHECK_ARG(w_oihw && hi, "pack_w3x3: bad args");
+  const int rows = mode == 0 ? Cout : Cin;
+  EGAZE_CHECK_ARG(cols_p >= (mode == 0 ? Cin : Cout), "pack_w3x3: cols_p too small");
+  const size_t total = (size_t)9 * rows * cols_p;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  pack_w3x3_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w_oihw, Cout, Cin, rows, cols_p, mode, (__nv_bfloat16*)hi,
+                                                             (__nv_bfloat16*)lo);
+  EGAZE_LAUNCH_CHECK();
+  return EGAZE_OK;
+}
+
+extern "C" int egaze_unpack_wgrad(const float* dwp, int Cout, int Cin, int Cin_p, float beta, float* gw_oihw,
+                                  void* stream) {
+  EGAZE_CHECK_ARG(dwp && gw_oihw, "unpack_wgrad: bad args");
+  const size_t total = (size_t)Cout * Cin * 9;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  unpack_wgrad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dwp, Cout, Cin, Cin_p, beta, gw_oihw);
+  EGAZE_LAUNCH_CHECK();
+  return EGAZE_OK;
+}

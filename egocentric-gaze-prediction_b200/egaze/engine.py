@@ -1,0 +1,171 @@
+"""Forward (and, via egaze.autograd, backward) schedules of the hot-path networks on top of egaze.ops.
+
+The nn.Module containers (utils.make_layers trunk, model_SP, late_fusion) keep the reference's parameter
+layout (SURVEY 8b "State layout"); this module reads their parameters and drives the fused sm_100a kernels:
+
+  trunk layer, eval BN : conv3x3_tc [BN folded into scale/shift + ReLU (+2x2 max-pool) in the epilogue] -> split act
+  trunk layer, train BN: conv3x3_tc [+bias, raw fp32 out, per-tile (mean, M2)] -> bn_finalize (running stats)
+                         -> bn_apply [normalise + ReLU (+pool)] -> split act
+  decoder layer        : conv3x3_tc [+bias, ReLU (, 2x nearest replicate for the following nn.Upsample)] -> split act
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+class ConvSpec(object):
+    """One fused step of a Sequential: conv [+ bn] [+ relu] [+ pool | + upsample]."""
+    __slots__ = ("conv", "bn", "relu", "pool", "ups")
+
+    def __init__(self, conv):
+        self.conv, self.bn, self.relu, self.pool, self.ups = conv, None, False, False, False
+
+
+def parse_sequential(seq):
+    """Group the children of a reference-style nn.Sequential into fused ConvSpecs (+ trailing 1x1 conv if any)."""
+    specs, tail = [], None
+    for m in seq.children():
+        if isinstance(m, nn.Conv2d):
+            if m.kernel_size == (3, 3):
+                if m.padding != (1, 1) or m.stride != (1, 1) or m.dilation != (1, 1) or m.groups != 1:
+                    raise RuntimeError("egaze: only 3x3/pad1/stride1 convs are on the hot path, got %r" % (m,))
+                specs.append(ConvSpec(m))
+            elif m.kernel_size == (1, 1) and m.out_channels == 1:
+                tail = m
+            else:
+                raise RuntimeError("egaze: unsupported conv on the hot path: %r" % (m,))
+        elif isinstance(m, nn.BatchNorm2d):
+            specs[-1].bn = m
+        elif isinstance(m, nn.ReLU):
+            specs[-1].relu = True
+        elif isinstance(m, nn.MaxPool2d):
+            if m.kernel_size not in (2, (2, 2)) or m.stride not in (2, (2, 2)):
+                raise RuntimeError("egaze: only MaxPool2d(2,2) is on the hot path")
+            specs[-1].pool = True
+        elif isinstance(m, nn.Upsample):
+            if m.scale_factor not in (2, 2.0) or m.mode != "nearest":
+                raise RuntimeError("egaze: only nearest Upsample(scale_factor=2) is on the hot path")
+            specs[-1].ups = True
+        else:
+            raise RuntimeError("egaze: unsupported module on the hot path: %r" % (m,))
+    return specs, tail
+
+
+def _bn_uses_batch_stats(bn):
+    return bn.training or (bn.running_mean is None and bn.running_var is None)
+
+
+def run_conv_spec(act, spec, saved=None):
+    """Execute one ConvSpec on a split activation.  `saved` (list) collects what backward needs."""
+    conv, bn = spec.conv, spec.bn
+    cout_p = ops.pad_channels(conv.out_channels) if conv.out_channels % 16 else conv.out_channels
+    wpack = ops.pack_cache.get(conv.weight, 0, rows_p=cout_p, cols_p=act.Cp)
+    bias = conv.bias.detach() if conv.bias is not None else None
+    if bias is not None and cout_p != conv.out_channels:
+        bias = torch.cat([bias, bias.new_zeros(cout_p - conv.out_channels)])
+    if bn is None:
+        out, _, _ = ops.conv3x3(act, wpack, bias=bias, relu=spec.relu, reduce=1 if spec.pool else 0, ups=spec.ups)
+        if saved is not None:
+            saved.append({"x": act, "y": out})
+        out.C = conv.out_channels
+        return out
+    C = conv.out_channels
+    gamma = bn.weight.detach() if bn.weight is not None else None
+    beta = bn.bias.detach() if bn.bias is not None else None
+    if cout_p != C:
+        gamma = torch.cat([gamma, gamma.new_ones(cout_p - C)]) if gamma is not None else None
+        beta = torch.cat([beta, beta.new_zeros(cout_p - C)]) if beta is not None else None
+    if not _bn_uses_batch_stats(bn):
+        rm, rv = bn.running_mean, bn.running_var
+        if cout_p != C:
+            rm = torch.cat([rm, rm.new_zeros(cout_p - C)])
+            rv = torch.cat([rv, rv.new_ones(cout_p - C)])
+        scale, shift = ops.bn_fold(gamma, beta, rm, rv, bias, bn.eps)
+        out, _, _ = ops.conv3x3(act, wpack, scale=scale, shift=shift, relu=spec.relu, reduce=1 if spec.pool else 0,
+                                ups=spec.ups)
+        if saved is not None:
+            saved.append({"x": act, "y": out, "scale": scale})
+        out.C = C
+        return out
+    # training-mode BatchNorm: batch statistics are needed before normalising
+    if spec.ups:
+        raise RuntimeError("egaze: conv+BN followed by Upsample is not on the hot path")
+    _, raw, st = ops.conv3x3(act, wpack, bias=bias, want_f32=True, want_split=False, stats=True)
+    if bn.momentum is None:
+        raise RuntimeError("egaze: BatchNorm2d(momentum=None) (cumulative average) is not supported")
+    rm = bn.running_mean if bn.track_running_stats else None
+    rv = bn.running_var if bn.track_running_stats else None
+    if cout_p != C and rm is not None:
+        rm_p = torch.cat([rm, rm.new_zeros(cout_p - C)])
+        rv_p = torch.cat([rv, rv.new_ones(cout_p - C)])
+        mean, invstd, scale, shift = ops.bn_finalize(st, cout_p, bn.eps, bn.momentum, gamma, beta, rm_p, rv_p)
+        rm.copy_(rm_p[:C])
+        rv.copy_(rv_p[:C])
+    else:
+        mean, invstd, scale, shift = ops.bn_finalize(st, cout_p, bn.eps, bn.momentum, gamma, beta, rm, rv)
+    if bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    out, _ = ops.bn_apply(raw, scale, shift, relu=spec.relu, pool=spec.pool)
+    if saved is not None:
+        saved.append({"x": act, "raw": raw, "mean": mean, "invstd": invstd, "scale": scale, "shift": shift, "y": out})
+    out.C = C
+    return out
+
+
+def run_sequential(seq, act, saved=None):
+    """Run a reference-style Sequential of 3x3 convs.  Returns (act, tail_1x1_conv | None)."""
+    specs, tail = parse_sequential(seq)
+    for spec in specs:
+        act = run_conv_spec(act, spec, saved)
+    return act, tail
+
+
+def attach_act(t, act):
+    """Side channel: keep the internal split-NHWC activation next to the NCHW fp32 tensor the API returns."""
+    t._egaze_act = act
+    return t
+
+
+def get_act(t, Cp=None):
+    act = getattr(t, "_egaze_act", None)
+    if act is not None and act.N == t.shape[0] and act.C == t.shape[1] and (Cp is None or act.Cp == Cp):
+        return act
+    return ops.to_split(t, Cp)
+
+
+# ---- model_SP tail: fusion (shared conv on both streams + max) -> bn -> relu -> decoder -> sigmoid ----------------
+def run_sp_tail(model, a_s, a_t, saved=None):
+    """models/model_SP.py:38-49.  a_s / a_t: split conv5_3 activations of the spatial / temporal trunks."""
+    B = a_s.N
+    fusion, bn = model.fusion, model.bn
+    cat = ops.Act(torch.cat([a_s.hi, a_t.hi], 0), torch.cat([a_s.lo, a_t.lo], 0), a_s.C)  # depth order (s, t): model_SP.py:40
+    wpack = ops.pack_cache.get(fusion.weight, 0, cols_p=cat.Cp)
+    bias = fusion.bias.detach() if fusion.bias is not None else None
+    _, raw2, _ = ops.conv3x3(cat, wpack, bias=bias, want_f32=True, want_split=False)
+    mx = ops.pairmax(raw2)  # [B,14,14,512] fp32
+    C = mx.shape[-1]
+    gamma = bn.weight.detach() if bn.weight is not None else None
+    beta = bn.bias.detach() if bn.bias is not None else None
+    rec = {"cat": cat, "raw2": raw2, "mx": mx}
+    if _bn_uses_batch_stats(bn):
+        st = ops.col_stats(mx.view(-1, C))
+        rm = bn.running_mean if bn.track_running_stats else None
+        rv = bn.running_var if bn.track_running_stats else None
+        mean, invstd, scale, shift = ops.bn_finalize(st, C, bn.eps, bn.momentum, gamma, beta, rm, rv)
+        if bn.track_running_stats and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+        rec.update(mean=mean, invstd=invstd)
+    else:
+        scale, shift = ops.bn_fold(gamma, beta, bn.running_mean, bn.running_var, None, bn.eps)
+    act, _ = ops.bn_apply(mx, scale, shift, relu=True, pool=False)
+    rec.update(scale=scale, shift=shift, y=act)
+    dec_saved = [] if saved is not None else None
+    act, tail = run_sequential(model.decoder, act, dec_saved)
+    if tail is None:
+        raise RuntimeError("egaze: decoder must end with the 1x1 conv (model_SP.py:30)")
+    out = ops.head_fwd(act, tail.weight, tail.bias)
+    if saved is not None:
+        rec.update(decoder=dec_saved, head_in=act, out=out)
+        saved.append(rec)
+    return out

@@ -1,0 +1,328 @@
+"""Thin tensor-level wrappers over the C-ABI (include/egaze.h).  PyTorch is used for device memory and streams
+only; all arithmetic happens in libegaze.so."""
+import ctypes
+import os
+import weakref
+
+import torch
+
+from . import _lib
+from ._lib import call, stream_ptr
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+def precision():
+    """'precise' (default): split-bf16 operands, 3 MMAs per product -- meets the 1e-3 parity gate.
+    'fast': single bf16 pass -- reported, never gated."""
+    p = os.environ.get("EGAZE_PRECISION", "precise")
+    if p not in ("precise", "fast"):
+        raise RuntimeError("EGAZE_PRECISION must be 'precise' or 'fast', got %r" % p)
+    return p
+
+
+def is_precise():
+    return precision() == "precise"
+
+
+def pad_channels(c):
+    """Channel padding of the K dimension: multiples of 64 when >= 64, else 16/32/48."""
+    if c % 64 == 0:
+        return c
+    if c > 64:
+        return (c + 63) // 64 * 64
+    return (c + 15) // 16 * 16
+
+
+class Act(object):
+    """NHWC split-bf16 activation: x ~= hi + lo.  `C` = logical channels, hi.shape[-1] = padded channels."""
+    __slots__ = ("hi", "lo", "C")
+
+    def __init__(self, hi, lo, C):
+        self.hi, self.lo, self.C = hi, lo, C
+
+    @property
+    def N(self):
+        return self.hi.shape[0]
+
+    @property
+    def H(self):
+        return self.hi.shape[1]
+
+    @property
+    def W(self):
+        return self.hi.shape[2]
+
+    @property
+    def Cp(self):
+        return self.hi.shape[3]
+
+
+def empty_act(N, H, W, Cp, C, device, lo=True):
+    hi = torch.empty((N, H, W, Cp), dtype=BF16, device=device)
+    lo_t = torch.empty((N, H, W, Cp), dtype=BF16, device=device) if lo else None
+    return Act(hi, lo_t, C)
+
+
+def to_split(x, Cp=None):
+    """NCHW fp32 -> Act (channels zero-padded to Cp)."""
+    _lib.check_device(x.device)
+    x = x.contiguous().float()
+    N, C, H, W = x.shape
+    Cp = pad_channels(C) if Cp is None else Cp
+    act = empty_act(N, H, W, Cp, C, x.device, lo=True)
+    call("egaze_nchw_to_nhwc_split", x, N, C, H, W, Cp, act.hi, act.lo, stream_ptr())
+    return act
+
+
+def from_split(act, C=None):
+    """Act -> NCHW fp32 [N, C, H, W]."""
+    C = act.C if C is None else C
+    out = torch.empty((act.N, C, act.H, act.W), dtype=F32, device=act.hi.device)
+    call("egaze_nhwc_to_nchw", act.hi, act.lo, None, act.N, C, act.H, act.W, act.Cp, out, stream_ptr())
+    return out
+
+
+def nhwc_f32_to_nchw(x, C=None):
+    N, H, W, Cs = x.shape
+    C = Cs if C is None else C
+    out = torch.empty((N, C, H, W), dtype=F32, device=x.device)
+    call("egaze_nhwc_to_nchw", None, None, x, N, C, H, W, Cs, out, stream_ptr())
+    return out
+
+
+def nchw_to_nhwc_f32(x):
+    x = x.contiguous().float()
+    N, C, H, W = x.shape
+    out = torch.empty((N, H, W, C), dtype=F32, device=x.device)
+    call("egaze_nchw_to_nhwc_f32", x, N, C, H, W, out, stream_ptr())
+    return out
+
+
+def f32_to_split(x_nhwc, C=None):
+    x_nhwc = x_nhwc.contiguous()
+    N, H, W, Cs = x_nhwc.shape
+    act = empty_act(N, H, W, Cs, Cs if C is None else C, x_nhwc.device, lo=True)
+    call("egaze_f32_to_split", x_nhwc, x_nhwc.numel(), act.hi, act.lo, stream_ptr())
+    return act
+
+
+# ---- packed-weight cache: derived copies keyed on (parameter identity, version) ---------------------------------
+class _PackCache(object):
+    def __init__(self):
+        self._d = {}
+
+    def get(self, w, mode, rows_p=None, cols_p=None):
+        """w: nn.Conv2d weight [Co, Ci, 3, 3] (or Conv3d [Co, Ci, 1, 3, 3]).  Returns (hi, lo, rows, cols_p)."""
+        key = (id(w), mode, rows_p, cols_p)
+        ent = self._d.get(key)
+        ver = w._version
+        if ent is not None and ent[0]() is w and ent[1] == ver and ent[2] == w.data_ptr():
+            return ent[3]
+        Co, Ci = int(w.shape[0]), int(w.shape[1])
+        w4 = w.detach().reshape(Co, Ci, 3, 3).contiguous().float()
+        rows = Co if mode == 0 else Ci
+        cols = Ci if mode == 0 else Co
+        cp = pad_channels(cols) if cols_p is None else cols_p
+        rp = rows if rows_p is None else rows_p
+        hi = torch.zeros((9, rp, cp), dtype=BF16, device=w.device)
+        lo = torch.zeros((9, rp, cp), dtype=BF16, device=w.device)
+        if rp == rows:
+            call("egaze_pack_w3x3", w4, Co, Ci, cp, mode, hi, lo, stream_ptr())
+        else:
+            # padded rows (tiny layers only, e.g. LF 32->8): pack densely then copy into the padded buffer
+            thi = torch.empty((9, rows, cp), dtype=BF16, device=w.device)
+            tlo = torch.empty((9, rows, cp), dtype=BF16, device=w.device)
+            call("egaze_pack_w3x3", w4, Co, Ci, cp, mode, thi, tlo, stream_ptr())
+            hi[:, :rows].copy_(thi)
+            lo[:, :rows].copy_(tlo)
+        val = (hi, lo, rp, cp)
+        self._d[key] = (weakref.ref(w), ver, w.data_ptr(), val)
+        return val
+
+
+pack_cache = _PackCache()
+
+
+def conv_tiles(N, H, W, need_even=False):
+    nt = ctypes.c_int(0)
+    bh = ctypes.c_int(0)
+    bw = ctypes.c_int(0)
+    call("egaze_conv3x3_tiles", N, H, W, int(need_even), ctypes.addressof(nt), ctypes.addressof(bh), ctypes.addressof(bw))
+    return nt.value, bh.value, bw.value
+
+
+def conv3x3(act, wpack, bias=None, scale=None, shift=None, relu=False, reduce=0, ups=False, mask=None,
+            want_f32=False, want_split=True, stats=False, precise=None):
+    """3x3/pad-1 conv on the tcgen05 path.  wpack = (w_hi, w_lo, Cout_p, Cin_p) from pack_cache.
+    Returns (out_act | None, out_f32 | None, (stats_partial, stats_cnt) | None)."""
+    w_hi, w_lo, Cout, Cin_p = wpack
+    if Cin_p != act.Cp:
+        raise RuntimeError("egaze: conv3x3 channel mismatch: activation Cp=%d, weight Cin_p=%d" % (act.Cp, Cin_p))
+    precise = is_precise() if precise is None else precise
+    N, H, W = act.N, act.H, act.W
+    dev = act.hi.device
+    Ho, Wo = (H // 2, W // 2) if reduce else (H, W)
+    if ups:
+        Ho, Wo = Ho * 2, Wo * 2
+    out_act = empty_act(N, Ho, Wo, Cout, Cout, dev, lo=True) if want_split else None
+    out_f32 = torch.empty((N, Ho, Wo, Cout), dtype=F32, device=dev) if want_f32 else None
+    st = None
+    if stats:
+        nt, _, _ = conv_tiles(N, H, W, bool(reduce))
+        st = (torch.empty((nt, 2, Cout), dtype=F32, device=dev), torch.empty((nt,), dtype=F32, device=dev))
+    call("egaze_conv3x3_tc", act.hi, act.lo if precise else None, w_hi, w_lo if precise else None, N, H, W, Cin_p, Cout,
+         bias, scale, shift, int(relu), int(reduce), int(ups), mask, out_f32,
+         out_act.hi if out_act is not None else None, out_act.lo if out_act is not None else None,
+         st[0] if st else None, st[1] if st else None, int(precise), stream_ptr())
+    return out_act, out_f32, st
+
+
+def bn_finalize(st, C, eps, momentum, gamma, beta, running_mean, running_var):
+    """-> (mean, invstd, scale, shift); updates running stats in place when given."""
+    partial, cnt = st
+    dev = partial.device
+    mean = torch.empty((C,), dtype=F32, device=dev)
+    invstd = torch.empty((C,), dtype=F32, device=dev)
+    scale = torch.empty((C,), dtype=F32, device=dev)
+    shift = torch.empty((C,), dtype=F32, device=dev)
+    call("egaze_bn_finalize", partial, cnt, partial.shape[0], C, float(eps), float(momentum), gamma, beta, running_mean,
+         running_var, mean, invstd, scale, shift, stream_ptr())
+    return mean, invstd, scale, shift
+
+
+def bn_fold(gamma, beta, running_mean, running_var, conv_bias, eps):
+    C = running_mean.numel()
+    scale = torch.empty((C,), dtype=F32, device=running_mean.device)
+    shift = torch.empty((C,), dtype=F32, device=running_mean.device)
+    call("egaze_bn_fold", gamma, beta, running_mean, running_var, conv_bias, float(eps), C, scale, shift, stream_ptr())
+    return scale, shift
+
+
+def col_stats(x2d):
+    rows, C = x2d.shape
+    nb = (rows + 127) // 128
+    partial = torch.empty((nb, 2, C), dtype=F32, device=x2d.device)
+    cnt = torch.empty((nb,), dtype=F32, device=x2d.device)
+    call("egaze_col_stats", x2d, rows, C, partial, cnt, stream_ptr())
+    return partial, cnt
+
+
+def bn_apply(x_nhwc, scale, shift, relu=True, pool=False, want_f32=False, want_split=True):
+    N, H, W, C = x_nhwc.shape
+    Ho, Wo = (H // 2, W // 2) if pool else (H, W)
+    dev = x_nhwc.device
+    out_act = empty_act(N, Ho, Wo, C, C, dev, lo=True) if want_split else None
+    out_f32 = torch.empty((N, Ho, Wo, C), dtype=F32, device=dev) if want_f32 else None
+    call("egaze_bn_apply", x_nhwc, N, H, W, C, scale, shift, int(relu), int(pool), out_f32,
+         out_act.hi if out_act is not None else None, out_act.lo if out_act is not None else None, stream_ptr())
+    return out_act, out_f32
+
+
+def pairmax(x_2b):
+    """x [2B, H, W, C] fp32 -> [B, H, W, C] elementwise max of the two halves."""
+    B2 = x_2b.shape[0]
+    out = torch.empty((B2 // 2,) + tuple(x_2b.shape[1:]), dtype=F32, device=x_2b.device)
+    call("egaze_pairmax", x_2b, out.numel(), out, stream_ptr())
+    return out
+
+
+def head_fwd(act, w, b, want_logit=False):
+    """1x1 conv (C -> 1) + sigmoid.  -> [N, 1, H, W] fp32."""
+    N, H, W = act.N, act.H, act.W
+    out = torch.empty((N, 1, H, W), dtype=F32, device=act.hi.device)
+    logit = torch.empty((N, 1, H, W), dtype=F32, device=act.hi.device) if want_logit else None
+    wf = w.detach().reshape(-1).contiguous().float()
+    call("egaze_head_fwd", act.hi, act.lo, wf, b.detach() if b is not None else None, wf.numel(), act.Cp, N * H * W, out,
+         logit, stream_ptr())
+    return (out, logit) if want_logit else out
+
+
+# ---- floss -------------------------------------------------------------------------------------------------------
+def floss_centroid(target):
+    B, H, W = target.shape[0], target.shape[-2], target.shape[-1]
+    cen = torch.empty((B, 2), dtype=torch.float64, device=target.device)
+    call("egaze_floss_centroid", target, B, H, W, cen, stream_ptr())
+    return cen
+
+
+def floss_weight(target):
+    target = target.contiguous().float()
+    B, H, W = target.shape[0], target.shape[-2], target.shape[-1]
+    cen = floss_centroid(target)
+    w = torch.empty_like(target)
+    call("egaze_floss_weight", cen, B, H, W, w, stream_ptr())
+    return w
+
+
+def floss_fwd(inp, target, cen):
+    B, H, W = target.shape[0], target.shape[-2], target.shape[-1]
+    acc = torch.empty((1,), dtype=torch.float64, device=inp.device)
+    loss = torch.empty((), dtype=F32, device=inp.device)
+    call("egaze_floss_fwd", inp, target, cen, B, H, W, acc, loss, stream_ptr())
+    return loss
+
+
+def floss_bwd(inp, target, cen, grad_loss):
+    B, H, W = target.shape[0], target.shape[-2], target.shape[-1]
+    g = torch.empty_like(inp)
+    call("egaze_floss_bwd", inp, target, cen, B, H, W, grad_loss.contiguous().float(), g, stream_ptr())
+    return g
+
+
+# ---- AT glue -----------------------------------------------------------------------------------------------------
+def crop_mean(feat, gaze, size=3, down=16):
+    feat = feat.contiguous().float()
+    B, C, H, W = feat.shape
+    g = torch.as_tensor(gaze, dtype=torch.int32, device=feat.device).reshape(B, 2).contiguous()
+    out = torch.empty((B, C), dtype=F32, device=feat.device)
+    call("egaze_crop_mean", feat, g, B, C, H, W, int(size), int(down), out, stream_ptr())
+    return out
+
+
+def weighted_map(chn_weight, feat):
+    feat = feat.contiguous().float()
+    B, C, H, W = feat.shape
+    w = chn_weight.reshape(B, C).contiguous().float()
+    out = torch.empty((B, H, W), dtype=F32, device=feat.device)
+    call("egaze_weighted_map", feat, w, B, C, H * W, out, stream_ptr())
+    return out
+
+
+def bilinear_up(x, scale=16, align_corners=False):
+    shp = x.shape
+    h, w = shp[-2], shp[-1]
+    xb = x.contiguous().float().reshape(-1, h, w)
+    out = torch.empty((xb.shape[0], h * scale, w * scale), dtype=F32, device=x.device)
+    call("egaze_bilinear_up", xb, xb.shape[0], h, w, int(scale), int(align_corners), out, stream_ptr())
+    return out.reshape(tuple(shp[:-2]) + (h * scale, w * scale))
+
+
+# ---- LSTM ----------------------------------------------------------------------------------------------------------
+def lstm_seq_fwd(x, h0, c0, lstm, lin, save_gates=False):
+    """x [T,B,512] raw input (tanh applied inside).  lstm: nn.LSTM(512,512,2) parameter container, lin: nn.Linear."""
+    x = x.contiguous().float()
+    T, B, Hd = x.shape
+    dev = x.device
+    out = torch.empty((T, B, Hd), dtype=F32, device=dev)
+    hn = torch.empty((2, B, Hd), dtype=F32, device=dev)
+    cn = torch.empty((2, B, Hd), dtype=F32, device=dev)
+    ws_h = torch.empty((T, 2, B, Hd), dtype=F32, device=dev)
+    ws_c = torch.empty((T, 2, B, Hd), dtype=F32, device=dev)
+    ws_g = torch.empty((T, 2, B, 4, Hd), dtype=F32, device=dev) if save_gates else None
+
+    def ptrs(fmt):
+        ts = [getattr(lstm, fmt % l).detach().contiguous() for l in range(2)]
+        arr = (ctypes.c_void_p * 2)(*[t.data_ptr() for t in ts])
+        return ts, arr
+
+    k1, w_ih = ptrs("weight_ih_l%d")
+    k2, w_hh = ptrs("weight_hh_l%d")
+    k3, b_ih = ptrs("bias_ih_l%d")
+    k4, b_hh = ptrs("bias_hh_l%d")
+    call("egaze_lstm_seq_fwd", x, h0.contiguous().float(), c0.contiguous().float(), w_ih, w_hh, b_ih, b_hh,
+         lin.weight.detach().contiguous(), lin.bias.detach().contiguous(), T, B, out, hn, cn, ws_h, ws_c, ws_g,
+         stream_ptr())
+    del k1, k2, k3, k4
+    return out, hn, cn, (ws_h, ws_c, ws_g)

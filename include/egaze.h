@@ -1,0 +1,101 @@
+/* egaze.h -- C-ABI of libegaze.so: the B200-native (sm_100a) replacement for what PyTorch->cuDNN/oneDNN
+ * executes underneath the reference's hot-path modules.  The reference (hyf015/egocentric-gaze-prediction) is pure
+ * Python; its "FFI for this path" is the nn.Module surface.  The Python host mirror in
+ * egocentric-gaze-prediction_b200/{models,floss.py,utils.py} keeps that surface and calls ONLY these entry points
+ * through ctypes (egocentric-gaze-prediction_b200/egaze/_lib.py); INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - every function returns int: 0 = ok, < 0 = invalid argument / unsupported, > 0 = cudaError_t;
+ *     egaze_last_error() returns the message of the calling thread's last failure.
+ *   - all data pointers are DEVICE pointers owned by the caller (PyTorch caching allocator); the library never
+ *     allocates or frees caller-visible memory.  `stream` is a cudaStream_t passed as void*.
+ *   - launches are asynchronous and stream-ordered; no host synchronisation inside any entry point.
+ *   - there is NO CPU fallback: a non-sm_100 device is an error (egaze_check_device).
+ *   - "split" activations: NHWC bf16 planes hi and lo with x ~= hi + lo (16 mantissa bits).  lo may be NULL
+ *     where documented ("fast" single-pass mode).
+ */
+#ifndef EGAZE_H_
+#define EGAZE_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- runtime ------------------------------------------------------------------------------------------------ */
+int egaze_version(void);
+int egaze_last_error(char* buf, int n);
+int egaze_check_device(void);
+int egaze_sm_count(int* out);
+
+/* ---- layout (API tensors are NCHW fp32: reference SURVEY 8b "Tensor conventions") ---------------------------- */
+/* x [N][C][H][W] fp32 -> hi/lo [N][H][W][Cp] bf16, channels C..Cp-1 zero.  (input side of utils.py:70 / model_SP.py:36-37) */
+int egaze_nchw_to_nhwc_split(const float* x, int N, int C, int H, int W, int Cp, void* hi, void* lo, void* stream);
+/* (hi[,lo]) or f32, NHWC with channel stride Cs -> out [N][C][H][W] fp32 (what forward hooks / callers see: AT.py:22,226) */
+int egaze_nhwc_to_nchw(const void* hi, const void* lo, const float* f32, int N, int C, int H, int W, int Cs, float* out,
+                       void* stream);
+int egaze_nchw_to_nhwc_f32(const float* x, int N, int C, int H, int W, float* out, void* stream);
+int egaze_f32_to_split(const float* x, long long n, void* hi, void* lo, void* stream);
+/* nn.Conv2d weight OIHW fp32 -> packed split bf16.  mode 0 (fprop): [9][Cout][cols_p>=Cin];
+ * mode 1 (dgrad): taps flipped, [9][Cin][cols_p>=Cout].  (weights of utils.py:70, model_SP.py:10,13-30, late_fusion.py:10-12) */
+int egaze_pack_w3x3(const float* w_oihw, int Cout, int Cin, int cols_p, int mode, void* hi, void* lo, void* stream);
+/* wgrad accumulator [9][Cout][Cin_p] fp32 -> OIHW grad, gw = beta*gw + dw */
+int egaze_unpack_wgrad(const float* dwp, int Cout, int Cin, int Cin_p, float beta, float* gw_oihw, void* stream);
+
+/* ---- 3x3 convolution, tcgen05 implicit GEMM (replaces nn.Conv2d(k=3,p=1): utils.py:70, model_SP.py:10,13-30) - */
+/* Tile geometry the kernel will use for an (N,H,W) map; num_tiles sizes the BN-statistics workspace. */
+int egaze_conv3x3_tiles(int N, int H, int W, int need_even, int* num_tiles, int* BH, int* BW);
+/* y = epilogue(conv3x3(x, w)):  v = acc + bias; v = v*scale + shift; relu; 2x2 reduce (1 max = MaxPool2d utils.py:68,
+ * 2 sum = grad of nn.Upsample); mask (zero where mask <= 0: ReLU backward); 2x nearest replicate (ups: model_SP.py:16,20,24,27).
+ *   x_hi/x_lo : [N][H][W][Cin_p] bf16        w_hi/w_lo : [9][Cout][Cin_p] bf16 (egaze_pack_w3x3)
+ *   out_f32 / out_hi / out_lo : NHWC [N][Ho][Wo][Cout] (any non-NULL subset is written)
+ *   stats [num_tiles][2][Cout], stats_cnt [num_tiles] : per-tile (mean, M2) of v BEFORE relu, for BatchNorm batch statistics
+ *   precise != 0 : hi*hi + hi*lo + lo*hi (3 MMAs), needs x_lo and w_lo;  0 : single bf16 pass. */
+int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, int N, int H, int W,
+                     int Cin_p, int Cout, const float* bias, const float* scale, const float* shift, int relu,
+                     int reduce, int ups, const void* mask, float* out_f32, void* out_hi, void* out_lo, float* stats,
+                     float* stats_cnt, int precise, void* stream);
+
+/* ---- BatchNorm2d pieces (utils.py:72, model_SP.py:12, late_fusion.py:10-12) ---------------------------------- */
+int egaze_bn_finalize(const float* partial, const float* cnt, int T, int C, float eps, float momentum,
+                      const float* gamma, const float* beta, float* running_mean, float* running_var, float* mean_out,
+                      float* invstd_out, float* scale_out, float* shift_out, void* stream);
+int egaze_bn_fold(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                  const float* conv_bias, float eps, int C, float* scale, float* shift, void* stream);
+/* x [rows][C] fp32 -> partial [ceil(rows/128)][2][C], cnt [ceil(rows/128)] */
+int egaze_col_stats(const float* x, long long rows, int C, float* partial, float* cnt, void* stream);
+/* y = relu?(x*scale+shift) [-> MaxPool2d(2,2)] ; x NHWC fp32, outputs NHWC */
+int egaze_bn_apply(const float* x, int N, int H, int W, int C, const float* scale, const float* shift, int relu,
+                   int pool, float* out_f32, void* out_hi, void* out_lo, void* stream);
+/* out[b] = max(x[b], x[b+B]) : Conv3d(1,3,3)+MaxPool3d((2,1,1)) second half (model_SP.py:11,43) */
+int egaze_pairmax(const float* x, long long per_stream, float* out, void* stream);
+
+/* ---- 1x1 conv to one channel + sigmoid (model_SP.py:30,32 ; late_fusion.py:13,15) ---------------------------- */
+int egaze_head_fwd(const void* x_hi, const void* x_lo, const float* w, const float* b, int C, int Cs, long long P,
+                   float* out, float* logit_out, void* stream);
+int egaze_head_bwd(const void* x_hi, const void* x_lo, const float* w, int C, int Cs, long long P, const float* y,
+                   const float* gy, int relu_mask, void* dx_hi, void* dx_lo, float* dw, float* db, void* stream);
+
+/* ---- floss (floss.py:9-41) ----------------------------------------------------------------------------------- */
+int egaze_floss_centroid(const float* target, int B, int H, int W, double* centroid, void* stream);
+int egaze_floss_weight(const double* centroid, int B, int H, int W, float* weights, void* stream);
+int egaze_floss_fwd(const float* input, const float* target, const double* centroid, int B, int H, int W,
+                    double* loss_acc, float* loss, void* stream);
+int egaze_floss_bwd(const float* input, const float* target, const double* centroid, int B, int H, int W,
+                    const float* grad_loss, float* grad_input, void* stream);
+
+/* ---- AT glue (AT.py:25-39,58-66,236-241 ; run_spatialstream.py:85-104,136) ------------------------------------ */
+int egaze_crop_mean(const float* feat_nchw, const int* gaze, int B, int C, int H, int W, int size, int down, float* out,
+                    void* stream);
+int egaze_weighted_map(const float* feat_nchw, const float* chn_weight, int B, int C, int HW, float* out, void* stream);
+int egaze_bilinear_up(const float* x, int B, int h, int w, int scale, int align_corners, float* out, void* stream);
+
+/* ---- lstmnet (models/LSTMnet.py:15-37) ------------------------------------------------------------------------ */
+int egaze_lstm_seq_fwd(const float* x, const float* h0, const float* c0, const float* const* w_ih,
+                       const float* const* w_hh, const float* const* b_ih, const float* const* b_hh, const float* lin_w,
+                       const float* lin_b, int T, int B, float* out, float* hn, float* cn, float* ws_h, float* ws_c,
+                       float* ws_gates, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EGAZE_H_ */

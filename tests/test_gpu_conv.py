@@ -1,0 +1,131 @@
+"""GPU parity of the tcgen05 3x3 conv (through the C-ABI) against a plain PyTorch fp32 conv2d of the same operands.
+
+Tolerances: `precise` (split-bf16, 3 MMAs) must agree with fp32 to ~2^-16 relative per product -> we gate at
+max-abs <= 2e-4 * scale; `fast` (single bf16 pass) is gated loosely at 2e-2 * scale (reported mode).
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(N, H, W, Cin, Cout, dev, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    x = torch.randn(N, Cin, H, W, generator=g).to(dev)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) * (2.0 / (9 * Cin)) ** 0.5).to(dev)
+    b = (torch.randn(Cout, generator=g) * 0.1).to(dev)
+    return x, w, b
+
+
+def _run(x, w, b, precise, **kw):
+    from egaze import ops
+    Cout, Cin = w.shape[0], w.shape[1]
+    act = ops.to_split(x)
+    cout_p = ops.pad_channels(Cout) if Cout % 16 else Cout
+    wp = ops.pack_cache.get(w, 0, rows_p=cout_p, cols_p=act.Cp)
+    bias = b
+    if bias is not None and cout_p != Cout:
+        bias = torch.cat([b, b.new_zeros(cout_p - Cout)])
+    return ops.conv3x3(act, wp, bias=bias, precise=precise, **kw)
+
+
+SHAPES = [
+    # N, H, W, Cin, Cout
+    (2, 16, 16, 64, 64),
+    (1, 14, 14, 512, 512),
+    (2, 28, 28, 256, 512),
+    (1, 56, 56, 128, 256),
+    (1, 112, 112, 64, 128),
+    (1, 224, 224, 64, 64),
+    (2, 32, 32, 3, 64),      # KC=16 / SWIZZLE_32B path (RGB conv1_1)
+    (2, 32, 32, 20, 64),     # KC=32 / SWIZZLE_64B path (flow conv1_1)
+    (2, 32, 32, 32, 8),      # LF conv3: Cout padded to 16
+    (2, 18, 18, 128, 128),   # 288-input conv5 size (partial tiles)
+    (1, 36, 36, 64, 192),    # BN tile = 64, 3 n-tiles
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("precise", [True, False])
+def test_conv3x3_plain(cuda_dev, shape, precise):
+    from egaze import ops
+    N, H, W, Cin, Cout = shape
+    x, w, b = _mk(N, H, W, Cin, Cout, cuda_dev)
+    act_out, f32_out, _ = _run(x, w, b, precise, want_f32=True, want_split=True)
+    torch.cuda.synchronize()
+    if precise:
+        # the kernel sees x, w rounded to 16 mantissa bits (hi+lo); compare against fp32 conv of the same rounded operands
+        xr = ops.from_split(ops.to_split(x))
+        ref = F.conv2d(xr.double(), w.double(), b.double(), padding=1).float()
+        tol = 3e-4
+    else:
+        ref = F.conv2d(x.double(), w.double(), b.double(), padding=1).float()
+        tol = 3e-2
+    got = ops.nhwc_f32_to_nchw(f32_out, Cout)
+    scale = ref.abs().max().item()
+    err = (got - ref).abs().max().item()
+    assert err <= tol * scale, "f32 out: max-abs err %.3e (scale %.3e)" % (err, scale)
+    got2 = ops.from_split(act_out, Cout)
+    err2 = (got2 - ref).abs().max().item()
+    assert err2 <= (tol + 2e-5) * scale, "split out: max-abs err %.3e (scale %.3e)" % (err2, scale)
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 32, 64, 128), (1, 56, 56, 64, 64), (2, 28, 28, 128, 256)])
+def test_conv3x3_epilogues(cuda_dev, shape):
+    """bias + folded scale/shift + relu + 2x2 max-pool; relu + nearest-2x replicate; 2x2 sum + mask."""
+    from egaze import ops
+    N, H, W, Cin, Cout = shape
+    x, w, b = _mk(N, H, W, Cin, Cout, cuda_dev, seed=1)
+    g = torch.Generator().manual_seed(5)
+    scale = (torch.rand(Cout, generator=g) + 0.5).to(cuda_dev)
+    shift = (torch.randn(Cout, generator=g) * 0.2).to(cuda_dev)
+    xr = ops.from_split(ops.to_split(x))
+    conv = F.conv2d(xr.double(), w.double(), b.double(), padding=1).float()
+    sc = conv.abs().max().item()
+    # (a) eval-BN fold + relu + pool
+    a, _, _ = _run(x, w, b, True, scale=scale, shift=shift, relu=True, reduce=1)
+    ref = F.max_pool2d(F.relu(conv * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)), 2, 2)
+    assert (ops.from_split(a) - ref).abs().max().item() <= 4e-4 * sc
+    # (b) relu + upsample
+    a, _, _ = _run(x, w, b, True, relu=True, ups=True)
+    ref = F.interpolate(F.relu(conv), scale_factor=2, mode="nearest")
+    assert (ops.from_split(a) - ref).abs().max().item() <= 4e-4 * sc
+    # (c) 2x2 sum + mask (dgrad-of-upsample epilogue)
+    mask_src = torch.randn(N, Cout, H // 2, W // 2, generator=g).to(cuda_dev)
+    mact = ops.to_split(mask_src, Cout)
+    a, f, _ = _run(x, w, None, True, reduce=2, mask=mact.hi, want_f32=True)
+    conv_nb = F.conv2d(xr.double(), w.double(), None, padding=1).float()
+    ref = F.avg_pool2d(conv_nb, 2, 2) * 4 * (ops.from_split(ops.Act(mact.hi, None, Cout)) > 0).float()
+    assert (ops.nhwc_f32_to_nchw(f) - ref).abs().max().item() <= 4e-4 * 4 * sc
+    assert (ops.from_split(a) - ref).abs().max().item() <= 5e-4 * 4 * sc
+
+
+@pytest.mark.parametrize("shape", [(4, 32, 32, 64, 64), (2, 14, 14, 128, 512), (3, 28, 28, 64, 128), (2, 36, 36, 32, 32)])
+def test_conv3x3_bn_stats(cuda_dev, shape):
+    """Per-tile (mean, M2) partials + finalize == torch batch statistics; running stats follow nn.BatchNorm2d."""
+    from egaze import ops
+    N, H, W, Cin, Cout = shape
+    x, w, b = _mk(N, H, W, Cin, Cout, cuda_dev, seed=2)
+    _, raw, st = _run(x, w, b, True, want_f32=True, want_split=False, stats=True)
+    bn = torch.nn.BatchNorm2d(Cout).to(cuda_dev).train()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.normal_(0, 0.1)
+    rm, rv = bn.running_mean.clone(), bn.running_var.clone()
+    mean, invstd, scale, shift = ops.bn_finalize(st, Cout, bn.eps, bn.momentum, bn.weight.detach(), bn.bias.detach(), rm, rv)
+    raw_nchw = ops.nhwc_f32_to_nchw(raw)
+    ref_y = bn(raw_nchw)
+    ref_mean = raw_nchw.double().mean((0, 2, 3))
+    ref_var = raw_nchw.double().var((0, 2, 3), unbiased=False)
+    assert (mean.double() - ref_mean).abs().max().item() <= 1e-5
+    assert (invstd.double() - 1.0 / torch.sqrt(ref_var + bn.eps)).abs().max().item() <= 1e-4
+    assert (rm - bn.running_mean).abs().max().item() <= 1e-5
+    assert (rv - bn.running_var).abs().max().item() <= 1e-5
+    for pool in (False, True):
+        a, f = ops.bn_apply(raw, scale, shift, relu=True, pool=pool, want_f32=True)
+        ref = F.relu(ref_y)
+        if pool:
+            ref = F.max_pool2d(ref, 2, 2)
+        assert (ops.nhwc_f32_to_nchw(f) - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
+        assert (ops.from_split(a) - ref).abs().max().item() <= 5e-5 * max(1.0, ref.abs().max().item())
