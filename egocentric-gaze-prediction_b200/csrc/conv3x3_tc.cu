@@ -199,6 +199,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
       float* dst = stage + (size_t)m * ldst + c0;
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
+        if (c0 + j >= p.BN) break;  // BN == 16: only half of the 32-column TMEM load is live
         float4 o;
         float* po = reinterpret_cast<float*>(&o);
 #pragma unroll
@@ -397,7 +398,7 @@ extern "C" int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* 
   }
   static bool attr_set = false;
   if (!attr_set) {
-    EGAZE_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    EGAZE_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     attr_set = true;
   }
   dim3 grid((unsigned)(p.tiles_n * p.tiles_w * p.tiles_h * N));
