@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py -- the driver's benchmark contract for the egaze-b200 hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload sp_train|sp_fwd|pipeline_fwd] [--impl reference]
+
+Metric (BASELINE.json): SP(+AT+LF) gaze-map frames/s at 224x224, batch 32 per GPU.  One "step" = one pass of the hot
+path over one synthetic batch: `sp_train` = model_SP two-stream forward + floss + backward +
+Adam step (BASELINE configs[1]); `sp_fwd` = eval-mode two-stream forward; `pipeline_fwd` = SP forward -> AT step ->
+LF forward (gaze-map inference).  N > 1 ranks (torchrun) shard frames: weak scaling, B=32 per rank, one NCCL
+allreduce of the weight gradients per training step and no collective for inference.
+
+Prints ONE JSON line (rank 0).  `value` = device-resident throughput; `e2e` = same metric through the public module
+API with HOST (pinned) inputs and a host read of the result inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "egocentric-gaze-prediction_b200")
+for _p in (PKG, ROOT):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "SP+AT+LF gaze-map frames/sec at 224x224 b32"
+UNIT = "frames/s"
+# algorithmic FLOPs per frame (SURVEY 8d / BASELINE.md 4): 2 FLOP per MAC of the reference's direct convolutions
+FLOP_SP_FWD = 114.167e9
+FLOP_SP_TRAIN = 341.171e9
+FLOP_LF_FWD = 1.2147e9
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            d = json.load(fh)
+        return d, "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._halt = index, [], threading.Event()
+
+    def run(self):
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def finish(self):
+        self._halt.set()
+        self.join(timeout=3)
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        # the busiest half of the samples == "under load"
+        sm_sorted = sorted(sm)
+        load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else [0.0]
+        return {"sm_mhz": float(np.median(load)), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# workloads
+# --------------------------------------------------------------------------------------------------------------------
+class Workload(object):
+    def __init__(self, name, B, S, rank, world, device):
+        from oracle import egaze_oracle as orc  # synthetic-input generator only (no oracle compute on this path)
+        from utils import make_layers, cfg
+        from models.model_SP import model_SP
+        from models.late_fusion import late_fusion
+        from models.LSTMnet import lstmnet
+        import floss as floss_mod
+        self.name, self.B, self.S, self.device, self.world = name, B, S, device, world
+        torch.manual_seed(0)  # identical replicas on every rank
+        self.model = model_SP(make_layers(cfg['D'], 3), make_layers(cfg['D'], 20)).to(device)
+        self.crit = floss_mod.floss()
+        x_s, x_t, gt = orc.synth_sp_inputs(B, S, 1234 + rank)
+        self.host = [torch.from_numpy(a).pin_memory() for a in (x_s, x_t, gt)]
+        self.dev = [t.to(device) for t in self.host]
+        self.h2d_bytes = sum(t.numel() * 4 for t in self.host[:2]) + (self.host[2].numel() * 4 if name == "sp_train" else 0)
+        self.flat = None
+        if name == "sp_train":
+            self.model.train()
+            self.opt = torch.optim.Adam(self.model.parameters(), lr=1e-7)  # gaze_full.py:11 default lr, SP.py:113
+            self.flop = FLOP_SP_TRAIN
+            self.d2h_bytes = 4
+            if world > 1:
+                self._make_flat_grads()
+        elif name == "sp_fwd":
+            self.model.eval()
+            self.flop = FLOP_SP_FWD
+            self.d2h_bytes = B * S * S * 4
+        elif name == "pipeline_fwd":
+            self.model.eval()
+            self.lstm = lstmnet().to(device).eval()
+            self.lf = late_fusion().to(device).eval()
+            self.feats = []
+            self.model._modules.get('features_s').register_forward_hook(lambda m, i, o: self.feats.append(o))  # AT.py:105
+            self.hidden = (torch.zeros(2, B, 512, device=device), torch.zeros(2, B, 512, device=device))
+            self.gaze = torch.randint(0, S, (B, 2), generator=torch.Generator().manual_seed(5 + rank)).int().to(device)
+            self.flop = FLOP_SP_FWD + FLOP_LF_FWD
+            self.d2h_bytes = B * S * S * 4
+        else:
+            raise SystemExit("unknown workload %r" % name)
+
+    def _make_flat_grads(self):
+        """All weight grads live in ONE flat fp32 buffer so the per-step NCCL allreduce needs no pack/copy."""
+        ps = [p for p in self.model.parameters() if p.requires_grad]
+        self.flat = torch.zeros(sum(p.numel() for p in ps), device=self.device)
+        off = 0
+        for p in ps:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def step(self, x_s, x_t, gt):
+        """One pass of the hot path; returns the tensor a user would read back."""
+        from egaze import ops
+        if self.name == "sp_train":
+            if self.flat is not None:
+                self.flat.zero_()
+            else:
+                self.opt.zero_grad(set_to_none=False)
+            out = self.model(x_s, x_t)
+            loss = self.crit(out, gt.view(out.size()))
+            loss.backward()
+            if self.flat is not None:
+                torch.distributed.all_reduce(self.flat, op=torch.distributed.ReduceOp.AVG)
+            self.opt.step()
+            return loss
+        with torch.no_grad():
+            if self.name == "sp_fwd":
+                return self.model(x_s, x_t)
+            self.feats.clear()
+            out = self.model(x_s, x_t)
+            feat = self.feats[0]
+            vec = ops.crop_mean(feat, self.gaze, 3)                        # AT.py:236-241
+            w, self.hidden = self.lstm(vec.unsqueeze(0), self.hidden)      # AT.py:245-246 (saccade branch)
+            amap = ops.weighted_map(w.squeeze(0), feat)                    # AT.py:248
+            up = ops.bilinear_up(amap.unsqueeze(1), 16, False)             # run_spatialstream.py:136
+            return self.lf(up, out)                                        # LF.py:90 argument order (AT map, SP map)
+
+
+def count_launches(fn):
+    from egaze import _lib
+    n0 = _lib.launch_counter()
+    fn()
+    return _lib.launch_counter() - n0
+
+
+def cpu_reference_fps(workload, B, S, steps, warmup, threads):
+    """The reference's CPU path (stock torch.nn modules + oneDNN, oracle/torch_cpu_ref.py) on this box's host cores."""
+    from oracle import torch_cpu_ref as ref
+    from oracle import egaze_oracle as orc
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    m = ref.ModelSP()
+    x_s, x_t, gt = [torch.from_numpy(a) for a in orc.synth_sp_inputs(B, S, 1234)]
+    if workload == "sp_train":
+        m.train()
+        opt = torch.optim.Adam(m.parameters(), lr=1e-7)
+
+        def step():
+            opt.zero_grad()
+            loss = ref.floss(m(x_s, x_t), gt)
+            loss.backward()
+            opt.step()
+    else:
+        m.eval()
+        lf = ref.LateFusion().eval() if workload == "pipeline_fwd" else None
+        lstm = ref.LSTMNet().eval() if workload == "pipeline_fwd" else None
+
+        def step():
+            with torch.no_grad():
+                if lf is None:
+                    return m(x_s, x_t)
+                blobs = []
+                h = m.features_s.register_forward_hook(lambda mod, i, o: blobs.append(o))
+                out = m(x_s, x_t)
+                h.remove()
+                feat = blobs[0]
+                gaze = [[S // 2, S // 2]] * B
+                vec = torch.from_numpy(orc.crop_mean(feat.numpy(), gaze, 3))
+                w, _ = lstm(vec.unsqueeze(0), (torch.zeros(2, B, 512), torch.zeros(2, B, 512)))
+                amap = torch.from_numpy(orc.get_weighted(w.squeeze(0).numpy(), feat.numpy()))
+                up = torch.nn.functional.interpolate(amap.unsqueeze(1), scale_factor=16, mode="bilinear", align_corners=False)
+                return lf(up, out)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return B / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    B = args.ref_batch
+    steps = max(1, min(args.steps, 3))
+    fps, dt = cpu_reference_fps(args.workload, B, args.size, steps, 1, threads)
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "batch_per_gpu": 32, "size": args.size,
+                       "note": "reference CPU path timed on a bounded sample (batch %d) of the same workload" % B},
+            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": "%s, batch %d x %dx%d, %d step(s), torch %s CPU (oneDNN), %d threads" % (
+                                 args.workload, B, args.size, args.size, steps, torch.__version__, threads)},
+            "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default=os.environ.get("EGAZE_BENCH_WORKLOAD", "sp_fwd"))
+    ap.add_argument("--impl", default="egaze")
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--size", type=int, default=224)
+    ap.add_argument("--ref-batch", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the egaze path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=device)
+    from egaze import _lib, ops
+    W = max(args.warmup, 3)
+    K = args.steps
+    wl = Workload(args.workload, args.batch, args.size, rank, world, device)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ------------------------------------------------------------------------------------
+    for _ in range(W):
+        wl.step(*wl.dev)
+    launches = count_launches(lambda: wl.step(*wl.dev))
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ops.conv_timer_reset(True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        wl.step(*wl.dev)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / K
+    conv_ms, conv_launches = ops.conv_timer_read()   # summed over the K timed steps, CUDA events on the launch stream
+    ops.conv_timer_reset(False)
+    clocks = sampler.finish() if sampler else None
+
+    # ---- end to end: host (pinned) inputs in, result read back, every step -----------------------------------------------
+    def e2e_step():
+        xs = [t.to(device, non_blocking=True) for t in wl.host]
+        res = wl.step(*xs)
+        return res.detach().to("cpu", non_blocking=False)
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(K):
+        e2e_step()
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1) / K
+
+    t = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+
+    peaks, peak_src = load_peaks()
+    frames = args.batch * world
+    value = frames / ms * 1e3
+    conv_flop_step = (wl.flop - (FLOP_LF_FWD if args.workload == "pipeline_fwd" else 0.0)) * args.batch
+    conv_tflops = conv_flop_step * K / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    peak_tf = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16x3-split (fp32 accumulate)" if ops.is_precise() else "bf16 (fp32 accumulate)", "data": "synthetic",
+        "config": {"workload": args.workload, "batch_per_gpu": args.batch, "size": args.size, "global_batch": frames,
+                   "precision_mode": ops.precision(), "parallelism": "dp%d" % world,
+                   "l2": "per-step inputs+activations (>1 GB) exceed the 126 MB L2; no explicit flush"},
+        "clocks": clocks,
+        "e2e": {"value": frames / ms_e2e * 1e3, "unit": UNIT, "h2d_bytes_per_step": wl.h2d_bytes,
+                "d2h_bytes_per_step": wl.d2h_bytes},
+        "gpu_launches": launches * K,
+        "roofline": {"bound": "tensor", "kernel": "conv3x3_tc_kernel (all 3x3 conv launches of the step)",
+                     "achieved": conv_tflops, "peak": peak_tf, "unit": "TFLOP/s", "frac": conv_tflops / peak_tf,
+                     "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step)" % peak_src,
+                     "launches_per_step": conv_launches / max(K, 1), "kernel_ms_per_step": conv_ms / max(K, 1),
+                     "step_tflops": wl.flop * args.batch / (ms * 1e-3) / 1e12, "traffic": None},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        threads = os.cpu_count() or 1
+        fps, dt = cpu_reference_fps(args.workload, args.ref_batch, args.size, 1, 1, threads)
+        line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": "%s, batch %d x %dx%d, 1 warm-up + 1 timed step, torch %s CPU (oneDNN), %d threads"
+                                          % (args.workload, args.ref_batch, args.size, args.size, torch.__version__, threads)}
+    print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

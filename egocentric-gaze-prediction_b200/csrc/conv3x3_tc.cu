@@ -58,7 +58,7 @@ __device__ __forceinline__ bool row_valid(const ConvTcParams& p, int m, int h0, 
   return (h0 + th < p.H) && (w0 + tw < p.W);
 }
 
-template <int kDummy>
+template <int NSPLIT, int KSTEPS>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                   const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -115,26 +115,25 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (lane == 0) {
-      int a_it = 0, b_it = 0;
+      int sa = 0, sb = 0;
+      uint32_t a_par = 1, b_par = 1;  // a fresh mbarrier passes a parity-1 wait: the first lap never blocks
       for (int kc = 0; kc < chunks; ++kc) {
         for (int s = 0; s < 3; ++s) {
-          const int sa = a_it % p.SA;
-          ptx::mbar_wait(&a_empty[sa], ((a_it / p.SA) & 1) ^ 1);
-          ptx::mbar_arrive_expect_tx(&a_full[sa], a_box_bytes * p.nsplit);
-          uint8_t* a_dst = a_ring + (size_t)sa * p.nsplit * p.a_slot_bytes;
+          ptx::mbar_wait(&a_empty[sa], a_par);
+          ptx::mbar_arrive_expect_tx(&a_full[sa], a_box_bytes * NSPLIT);
+          uint8_t* a_dst = a_ring + (size_t)sa * NSPLIT * p.a_slot_bytes;
           ptx::tma_load_4d(a_dst, &tmA_hi, &a_full[sa], kc * p.KC, w0 - 1 + s, h0 - 1, img);
-          if (p.nsplit == 2)
+          if (NSPLIT == 2)
             ptx::tma_load_4d(a_dst + p.a_slot_bytes, &tmA_lo, &a_full[sa], kc * p.KC, w0 - 1 + s, h0 - 1, img);
-          ++a_it;
+          if (++sa == p.SA) { sa = 0; a_par ^= 1; }
           for (int r = 0; r < 3; ++r) {
-            const int sb = b_it % p.SB;
-            ptx::mbar_wait(&b_empty[sb], ((b_it / p.SB) & 1) ^ 1);
-            ptx::mbar_arrive_expect_tx(&b_full[sb], b_box_bytes * p.nsplit);
-            uint8_t* b_dst = b_ring + (size_t)sb * p.nsplit * p.b_slot_bytes;
+            ptx::mbar_wait(&b_empty[sb], b_par);
+            ptx::mbar_arrive_expect_tx(&b_full[sb], b_box_bytes * NSPLIT);
+            uint8_t* b_dst = b_ring + (size_t)sb * NSPLIT * p.b_slot_bytes;
             const int brow = (r * 3 + s) * p.Cout + n0;
             ptx::tma_load_2d(b_dst, &tmB_hi, &b_full[sb], kc * p.KC, brow);
-            if (p.nsplit == 2) ptx::tma_load_2d(b_dst + p.b_slot_bytes, &tmB_lo, &b_full[sb], kc * p.KC, brow);
-            ++b_it;
+            if (NSPLIT == 2) ptx::tma_load_2d(b_dst + p.b_slot_bytes, &tmB_lo, &b_full[sb], kc * p.KC, brow);
+            if (++sb == p.SB) { sb = 0; b_par ^= 1; }
           }
         }
       }
@@ -144,37 +143,46 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     if (lane == 0) {
       const uint32_t idesc = ptx::make_idesc_bf16(128, p.BN, 0, 0);
       const uint32_t sbo = 8u * (uint32_t)row_bytes;
-      const int ksteps = p.KC / 16;
-      int a_it = 0, b_it = 0;
+      // Descriptors differ only in their 14-bit start-address field (smem address >> 4; smem < 256 KB so the
+      // field never carries): build the static part once, then a descriptor is one 64-bit add.
+      const uint64_t desc_static = ptx::make_smem_desc(0, 16, sbo, (uint32_t)row_bytes);
+      const uint64_t a_ring_desc = desc_static + (uint64_t)(ptx::smem_u32(a_ring) >> 4);
+      const uint64_t b_ring_desc = desc_static + (uint64_t)(ptx::smem_u32(b_ring) >> 4);
+      const uint32_t a_slot16 = (uint32_t)(p.nsplit * p.a_slot_bytes) >> 4, a_plane16 = (uint32_t)p.a_slot_bytes >> 4;
+      const uint32_t b_slot16 = (uint32_t)(p.nsplit * p.b_slot_bytes) >> 4, b_plane16 = (uint32_t)p.b_slot_bytes >> 4;
+      const uint32_t r_step16 = (uint32_t)(p.BW * row_bytes) >> 4;
+      int a_it = 0, b_it = 0, sa = 0, sb = 0;
+      uint32_t a_par = 0, b_par = 0;
       uint32_t accumulate = 0;
       for (int kc = 0; kc < chunks; ++kc) {
         for (int s = 0; s < 3; ++s) {
-          const int sa = a_it % p.SA;
-          ptx::mbar_wait(&a_full[sa], (a_it / p.SA) & 1);
+          ptx::mbar_wait(&a_full[sa], a_par);
           ptx::tc_fence_after();
-          const uint32_t a_base = ptx::smem_u32(a_ring + (size_t)sa * p.nsplit * p.a_slot_bytes);
+          const uint64_t a_desc0 = a_ring_desc + (uint64_t)((uint32_t)sa * a_slot16);
+#pragma unroll 1
           for (int r = 0; r < 3; ++r) {
-            const int sb = b_it % p.SB;
-            ptx::mbar_wait(&b_full[sb], (b_it / p.SB) & 1);
+            ptx::mbar_wait(&b_full[sb], b_par);
             ptx::tc_fence_after();
-            const uint32_t b_base = ptx::smem_u32(b_ring + (size_t)sb * p.nsplit * p.b_slot_bytes);
-            const uint32_t a_row0 = a_base + (uint32_t)(r * p.BW * row_bytes);
+            const uint64_t ad = a_desc0 + (uint64_t)((uint32_t)r * r_step16);
+            const uint64_t bd = b_ring_desc + (uint64_t)((uint32_t)sb * b_slot16);
             // products: (hi,hi) [, (hi,lo), (lo,hi)]
-            const int nprod = p.nsplit == 2 ? 3 : 1;
-            for (int pr = 0; pr < nprod; ++pr) {
-              const uint32_t a_addr = a_row0 + (pr == 2 ? (uint32_t)p.a_slot_bytes : 0u);
-              const uint32_t b_addr = b_base + (pr == 1 ? (uint32_t)p.b_slot_bytes : 0u);
-              for (int k = 0; k < ksteps; ++k) {
-                const uint64_t ad = ptx::make_smem_desc(a_addr + k * 32, 16, sbo, (uint32_t)row_bytes);
-                const uint64_t bd = ptx::make_smem_desc(b_addr + k * 32, 16, sbo, (uint32_t)row_bytes);
-                ptx::umma_bf16(tmem_base, ad, bd, idesc, accumulate);
-                accumulate = 1;
-              }
+#pragma unroll
+            for (int k = 0; k < KSTEPS; ++k) {
+              ptx::umma_bf16(tmem_base, ad + 2 * k, bd + 2 * k, idesc, accumulate);
+              accumulate = 1;
+            }
+            if (NSPLIT == 2) {
+#pragma unroll
+              for (int k = 0; k < KSTEPS; ++k) ptx::umma_bf16(tmem_base, ad + 2 * k, bd + b_plane16 + 2 * k, idesc, 1);
+#pragma unroll
+              for (int k = 0; k < KSTEPS; ++k) ptx::umma_bf16(tmem_base, ad + a_plane16 + 2 * k, bd + 2 * k, idesc, 1);
             }
             ptx::umma_commit(&b_empty[sb]);
+            if (++sb == p.SB) { sb = 0; b_par ^= 1; }
             ++b_it;
           }
           ptx::umma_commit(&a_empty[sa]);
+          if (++sa == p.SA) { sa = 0; a_par ^= 1; }
           ++a_it;
         }
       }
@@ -396,13 +404,28 @@ extern "C" int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* 
     rc = egaze_encode_tmap(&tmB_lo, precise ? w_lo : w_hi, 2, dims, str, box, row_bytes, 2);
     if (rc) return rc;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    EGAZE_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-    attr_set = true;
-  }
   dim3 grid((unsigned)(p.tiles_n * p.tiles_w * p.tiles_h * N));
-  conv3x3_tc_kernel<0><<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
+  const int ksteps = p.KC / 16;
+#define EGAZE_CONV_LAUNCH(NS, KS)                                                                                     \
+  do {                                                                                                                \
+    static bool attr_set = false;                                                                                     \
+    if (!attr_set) {                                                                                                  \
+      EGAZE_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<NS, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+                                      224 * 1024));                                                                   \
+      attr_set = true;                                                                                                \
+    }                                                                                                                 \
+    conv3x3_tc_kernel<NS, KS><<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);     \
+  } while (0)
+  if (p.nsplit == 2) {
+    if (ksteps == 4) EGAZE_CONV_LAUNCH(2, 4);
+    else if (ksteps == 2) EGAZE_CONV_LAUNCH(2, 2);
+    else EGAZE_CONV_LAUNCH(2, 1);
+  } else {
+    if (ksteps == 4) EGAZE_CONV_LAUNCH(1, 4);
+    else if (ksteps == 2) EGAZE_CONV_LAUNCH(1, 2);
+    else EGAZE_CONV_LAUNCH(1, 1);
+  }
+#undef EGAZE_CONV_LAUNCH
   EGAZE_LAUNCH_CHECK();
   return EGAZE_OK;
 }

@@ -82,9 +82,23 @@ def _arg(a):
     return a
 
 
+# kernels launched per C-ABI call (bench.py's `gpu_launches` claim); entries not listed launch nothing
+_LAUNCHES = {"egaze_floss_fwd": 2, "egaze_conv3x3_tiles": 0, "egaze_check_device": 0, "egaze_sm_count": 0}
+_launch_count = 0
+
+
+def launch_counter():
+    return _launch_count
+
+
 def call(name, *args):
+    global _launch_count
     fn = getattr(lib(), name)
     rc = fn(*[_arg(a) for a in args])
+    if name == "egaze_lstm_seq_fwd":
+        _launch_count += 3 * int(args[9])  # 2 cell kernels + 1 linear per time step
+    else:
+        _launch_count += _LAUNCHES.get(name, 1)
     if rc != 0:
         raise RuntimeError("egaze: %s failed (rc=%d): %s" % (name, rc, last_error()))
 

@@ -145,6 +145,22 @@ class _PackCache(object):
 pack_cache = _PackCache()
 
 
+# optional per-launch timing of the tensor-core conv (bench.py roofline): CUDA events on the launching stream
+_conv_timer = {"on": False, "events": []}
+
+
+def conv_timer_reset(enable):
+    _conv_timer["on"] = bool(enable)
+    _conv_timer["events"] = []
+
+
+def conv_timer_read():
+    """-> (total ms, number of launches) since the last reset."""
+    torch.cuda.synchronize()
+    ev = _conv_timer["events"]
+    return sum(a.elapsed_time(b) for a, b in ev), len(ev)
+
+
 def conv_tiles(N, H, W, need_even=False):
     nt = ctypes.c_int(0)
     bh = ctypes.c_int(0)
@@ -172,10 +188,16 @@ def conv3x3(act, wpack, bias=None, scale=None, shift=None, relu=False, reduce=0,
     if stats:
         nt, _, _ = conv_tiles(N, H, W, bool(reduce))
         st = (torch.empty((nt, 2, Cout), dtype=F32, device=dev), torch.empty((nt,), dtype=F32, device=dev))
+    if _conv_timer["on"]:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     call("egaze_conv3x3_tc", act.hi, act.lo if precise else None, w_hi, w_lo if precise else None, N, H, W, Cin_p, Cout,
          bias, scale, shift, int(relu), int(reduce), int(ups), mask, out_f32,
          out_act.hi if out_act is not None else None, out_act.lo if out_act is not None else None,
          st[0] if st else None, st[1] if st else None, int(precise), stream_ptr())
+    if _conv_timer["on"]:
+        ev1.record()
+        _conv_timer["events"].append((ev0, ev1))
     return out_act, out_f32, st
 
 

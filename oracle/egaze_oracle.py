@@ -225,7 +225,7 @@ def crop_feature(feature, maxind, size=3):
     res = []
     for b in range(feature.shape[0]):
         fmax = np.array(maxind[b]) // 16
-        fmax = np.clip(fmax, size // 2, H - int(math.ceil(size / 2.0)))
+        fmax = np.clip(fmax, size // 2, H - int(math.ceil(size / 2.0))).astype(np.int64)  # run_spatialstream.py:93 int()
         lo, hi = size // 2, int(math.ceil(size / 2.0))
         res.append(feature[b, :, fmax[0] - lo:fmax[0] + hi, fmax[1] - lo:fmax[1] + hi])
     return np.stack(res)
