@@ -152,6 +152,195 @@ __global__ void pairmax_kernel(const float* __restrict__ x, size_t per_stream, f
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------------------------
+// Recompute z = raw*scale+shift for the 1 (no pool) or 4 (pool) source pixels of one output pixel and route the
+// incoming gradient g: ReLU mask (z > 0) and, for MaxPool2d, to the FIRST maximum in scan order (PyTorch tie rule,
+// SURVEY App. D).  gz[q] is the gradient w.r.t. z at source pixel q, xh[q] the normalised activation.
+struct BnSrc {
+  float gz[4][4];   // [pixel q][channel lane]
+  float xh[4][4];
+};
+
+__device__ __forceinline__ void bn_route(const float* __restrict__ raw, int H, int W, int C, int n, int oh, int ow,
+                                         int c4, int pool, int relu, const float4& g, const float4& sc,
+                                         const float4& sh, const float4& mean, const float4& invstd, BnSrc& o) {
+  const int np = pool ? 4 : 1;
+  float z[4][4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (q < np) {
+      const int h = pool ? 2 * oh + (q >> 1) : oh, w = pool ? 2 * ow + (q & 1) : ow;
+      const float4 a = *reinterpret_cast<const float4*>(raw + (((size_t)n * H + h) * W + w) * C + c4 * 4);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+      const float mv[4] = {mean.x, mean.y, mean.z, mean.w}, iv[4] = {invstd.x, invstd.y, invstd.z, invstd.w};
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {
+        z[q][l] = fmaf(av[l], scv[l], shv[l]);
+        o.xh[q][l] = (av[l] - mv[l]) * iv[l];
+      }
+    }
+  }
+  const float gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+  for (int l = 0; l < 4; ++l) {
+    int best = 0;
+    if (pool) {
+      float bz = z[0][l];
+#pragma unroll
+      for (int q = 1; q < 4; ++q)
+        if (z[q][l] > bz) { bz = z[q][l]; best = q; }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (q < np) o.gz[q][l] = (q == best && (!relu || z[q][l] > 0.f)) ? gv[l] : 0.f;
+  }
+}
+
+// partial[blk][0][c] = sum gz ; partial[blk][1][c] = sum gz*xhat     blockDim = (C/4, rows)
+__global__ void bn_bwd_reduce_kernel(const float* __restrict__ raw, const float* __restrict__ g, int N, int H, int W,
+                                     int C, const float* __restrict__ scale, const float* __restrict__ shift,
+                                     const float* __restrict__ mean, const float* __restrict__ invstd, int pool, int relu,
+                                     float* __restrict__ partial) {
+  extern __shared__ float red[];  // [rows][2][C]
+  const int Ho = pool ? H / 2 : H, Wo = pool ? W / 2 : W;
+  const int c4 = threadIdx.x;
+  const float4 sc = *reinterpret_cast<const float4*>(scale + c4 * 4), sh = *reinterpret_cast<const float4*>(shift + c4 * 4);
+  const float4 mn = *reinterpret_cast<const float4*>(mean + c4 * 4), iv = *reinterpret_cast<const float4*>(invstd + c4 * 4);
+  float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+  const size_t npix = (size_t)N * Ho * Wo;
+  for (size_t pix = (size_t)blockIdx.x * blockDim.y + threadIdx.y; pix < npix; pix += (size_t)gridDim.x * blockDim.y) {
+    const int ow = (int)(pix % Wo);
+    const int oh = (int)((pix / Wo) % Ho);
+    const int n = (int)(pix / ((size_t)Wo * Ho));
+    const float4 gg = *reinterpret_cast<const float4*>(g + pix * C + c4 * 4);
+    BnSrc o;
+    bn_route(raw, H, W, C, n, oh, ow, c4, pool, relu, gg, sc, sh, mn, iv, o);
+    const int np = pool ? 4 : 1;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (q < np) {
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+          s1[l] += o.gz[q][l];
+          s2[l] = fmaf(o.gz[q][l], o.xh[q][l], s2[l]);
+        }
+      }
+  }
+  float* my = red + (size_t)threadIdx.y * 2 * C;
+#pragma unroll
+  for (int l = 0; l < 4; ++l) { my[c4 * 4 + l] = s1[l]; my[C + c4 * 4 + l] = s2[l]; }
+  __syncthreads();
+  for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < 2 * C; i += blockDim.x * blockDim.y) {
+    float v = 0.f;
+    for (int r = 0; r < (int)blockDim.y; ++r) v += red[(size_t)r * 2 * C + i];
+    partial[(size_t)blockIdx.x * 2 * C + i] = v;
+  }
+}
+
+// dgamma[c] = sum_blk partial[blk][1][c]; dbeta[c] = sum_blk partial[blk][0][c]   (fp64 accumulation)
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double a = 0.0, b = 0.0;
+  for (int i = 0; i < nblk; ++i) {
+    b += (double)partial[(size_t)i * 2 * C + c];
+    a += (double)partial[(size_t)i * 2 * C + C + c];
+  }
+  dgamma[c] = (float)a;
+  dbeta[c] = (float)b;
+}
+
+// draw = gamma*invstd * (gz - dbeta/n - xhat*dgamma/n)  -> NHWC split-bf16 (and/or fp32) at the conv-output resolution
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ raw, const float* __restrict__ g, int N, int H, int W, int C,
+                                    const float* __restrict__ scale, const float* __restrict__ shift,
+                                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                                    const float* __restrict__ dgamma, const float* __restrict__ dbeta, int pool, int relu,
+                                    float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_hi,
+                                    __nv_bfloat16* __restrict__ out_lo) {
+  const int Ho = pool ? H / 2 : H, Wo = pool ? W / 2 : W;
+  const int C4 = C / 4;
+  const float inv_n = 1.f / (float)((size_t)N * H * W);
+  const size_t total = (size_t)N * Ho * Wo * C4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % C4);
+    const size_t pix = i / C4;
+    const int ow = (int)(pix % Wo);
+    const int oh = (int)((pix / Wo) % Ho);
+    const int n = (int)(pix / ((size_t)Wo * Ho));
+    const float4 sc = *reinterpret_cast<const float4*>(scale + c4 * 4), sh = *reinterpret_cast<const float4*>(shift + c4 * 4);
+    const float4 mn = *reinterpret_cast<const float4*>(mean + c4 * 4), iv = *reinterpret_cast<const float4*>(invstd + c4 * 4);
+    const float4 dg = *reinterpret_cast<const float4*>(dgamma + c4 * 4), db = *reinterpret_cast<const float4*>(dbeta + c4 * 4);
+    const float4 gg = *reinterpret_cast<const float4*>(g + pix * C + c4 * 4);
+    BnSrc o;
+    bn_route(raw, H, W, C, n, oh, ow, c4, pool, relu, gg, sc, sh, mn, iv, o);
+    const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, dgv[4] = {dg.x, dg.y, dg.z, dg.w}, dbv[4] = {db.x, db.y, db.z, db.w};
+    const int np = pool ? 4 : 1;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (q < np) {
+        const int h = pool ? 2 * oh + (q >> 1) : oh, w = pool ? 2 * ow + (q & 1) : ow;
+        float v[4];
+#pragma unroll
+        for (int l = 0; l < 4; ++l) v[l] = scv[l] * (o.gz[q][l] - dbv[l] * inv_n - o.xh[q][l] * dgv[l] * inv_n);
+        const size_t off = (((size_t)n * H + h) * W + w) * C + c4 * 4;
+        if (out_f32) *reinterpret_cast<float4*>(out_f32 + off) = make_float4(v[0], v[1], v[2], v[3]);
+        if (out_hi) {
+          __nv_bfloat16 hh[4], ll[4];
+#pragma unroll
+          for (int l = 0; l < 4; ++l) split_bf16(v[l], hh[l], ll[l]);
+          *reinterpret_cast<uint2*>(out_hi + off) = make_uint2(pack_bf16x2(hh[0], hh[1]), pack_bf16x2(hh[2], hh[3]));
+          if (out_lo) *reinterpret_cast<uint2*>(out_lo + off) = make_uint2(pack_bf16x2(ll[0], ll[1]), pack_bf16x2(ll[2], ll[3]));
+        }
+      }
+  }
+}
+
+// Backward of out = max(x[b], x[b+B]): gradient goes to the first stream on ties (MaxPool3d((2,1,1))).
+__global__ void pairmax_bwd_kernel(const float* __restrict__ x, const float* __restrict__ g, size_t per_stream,
+                                   __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_stream; i += (size_t)gridDim.x * blockDim.x) {
+    const float a = x[i], b = x[per_stream + i], gg = g[i];
+    const bool first = !(b > a);
+    __nv_bfloat16 h, l;
+    split_bf16(first ? gg : 0.f, h, l);
+    hi[i] = h; lo[i] = l;
+    split_bf16(first ? 0.f : gg, h, l);
+    hi[per_stream + i] = h; lo[per_stream + i] = l;
+  }
+}
+
+// out[c] += sum_rows (hi+lo)[row][c]   (conv bias gradients).  blockDim = (C/4 capped at 128, rows)
+__global__ void col_sum_split_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                                     size_t rows, int C, float* __restrict__ out) {
+  extern __shared__ float red[];  // [blockDim.y][C]
+  const int C4 = C / 4;
+  for (int c4 = threadIdx.x; c4 < C4; c4 += blockDim.x) {
+    float s[4] = {0, 0, 0, 0};
+    for (size_t r = (size_t)blockIdx.x * blockDim.y + threadIdx.y; r < rows; r += (size_t)gridDim.x * blockDim.y) {
+      const uint2 h = *reinterpret_cast<const uint2*>(hi + r * C + c4 * 4);
+      uint2 l = make_uint2(0, 0);
+      if (lo) l = *reinterpret_cast<const uint2*>(lo + r * C + c4 * 4);
+      s[0] += bf16_bits_to_float(h.x & 0xffffu) + bf16_bits_to_float(l.x & 0xffffu);
+      s[1] += bf16_bits_to_float(h.x >> 16) + bf16_bits_to_float(l.x >> 16);
+      s[2] += bf16_bits_to_float(h.y & 0xffffu) + bf16_bits_to_float(l.y & 0xffffu);
+      s[3] += bf16_bits_to_float(h.y >> 16) + bf16_bits_to_float(l.y >> 16);
+    }
+#pragma unroll
+    for (int l2 = 0; l2 < 4; ++l2) red[(size_t)threadIdx.y * C + c4 * 4 + l2] = s[l2];
+  }
+  __syncthreads();
+  for (int c = threadIdx.y * blockDim.x + threadIdx.x; c < C; c += blockDim.x * blockDim.y) {
+    float v = 0.f;
+    for (int r = 0; r < (int)blockDim.y; ++r) v += red[(size_t)r * C + c];
+    atomicAdd(out + c, v);
+  }
+}
+
 }  // namespace
 
 extern "C" int egaze_bn_finalize(const float* partial, const float* cnt, int T, int C, float eps, float momentum,
@@ -204,6 +393,80 @@ extern "C" int egaze_pairmax(const float* x, long long per_stream, float* out, v
   int blocks = (int)((per_stream / 4 + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   pairmax_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, (size_t)per_stream, out);
+  EGAZE_LAUNCH_CHECK();
+  return EGAZE_OK;
+}
+
+// ---- backward entry points ---------------------------------------------------------------------------------------
+static void bn_bwd_block(int C, dim3* block) {
+  int rows = 256 / (C / 4);
+  if (rows < 1) rows = 1;
+  if (rows > 32) rows = 32;
+  *block = dim3(C / 4, rows);
+}
+
+// partial: [nblk][2][C] with nblk = egaze_bn_bwd_blocks(); dgamma/dbeta: [C]
+extern "C" int egaze_bn_bwd_blocks(int* nblk) {
+  *nblk = 148 * 4;
+  return EGAZE_OK;
+}
+
+extern "C" int egaze_bn_bwd_reduce(const float* raw, const float* g, int N, int H, int W, int C, const float* scale,
+                                   const float* shift, const float* mean, const float* invstd, int pool, int relu,
+                                   float* partial, float* dgamma, float* dbeta, void* stream) {
+  EGAZE_CHECK_ARG(raw && g && scale && shift && mean && invstd && partial && dgamma && dbeta, "bn_bwd_reduce: null");
+  EGAZE_CHECK_ARG(C % 4 == 0 && C <= 4096, "bn_bwd_reduce: unsupported C=%d", C);
+  dim3 block;
+  bn_bwd_block(C, &block);
+  const int nblk = 148 * 4;
+  const size_t smem = (size_t)block.y * 2 * C * sizeof(float);
+  bn_bwd_reduce_kernel<<<nblk, block, smem, (cudaStream_t)stream>>>(raw, g, N, H, W, C, scale, shift, mean, invstd, pool,
+                                                                    relu, partial);
+  EGAZE_LAUNCH_CHECK();
+  bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(partial, nblk, C, dgamma, dbeta);
+  EGAZE_LAUNCH_CHECK();
+  return EGAZE_OK;
+}
+
+extern "C" int egaze_bn_bwd_apply(const float* raw, const float* g, int N, int H, int W, int C, const float* scale,
+                                  const float* shift, const float* mean, const float* invstd, const float* dgamma,
+                                  const float* dbeta, int pool, int relu, float* out_f32, void* out_hi, void* out_lo,
+                                  void* stream) {
+  EGAZE_CHECK_ARG(raw && g && dgamma && dbeta && (out_f32 || out_hi), "bn_bwd_apply: null");
+  const int Ho = pool ? H / 2 : H, Wo = pool ? W / 2 : W;
+  const size_t total = (size_t)N * Ho * Wo * (C / 4);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  bn_bwd_apply_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(raw, g, N, H, W, C, scale, shift, mean, invstd, dgamma,
+                                                               dbeta, pool, relu, out_f32, (__nv_bfloat16*)out_hi,
+                                                               (__nv_bfloat16*)out_lo);
+  EGAZE_LAUNCH_CHECK();
+  return EGAZE_OK;
+}
+
+extern "C" int egaze_pairmax_bwd(const float* x, const float* g, long long per_stream, void* hi, void* lo, void* stream) {
+  EGAZE_CHECK_ARG(x && g && hi && lo && per_stream > 0, "pairmax_bwd: bad args");
+  int blocks = (int)((per_stream + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  pairmax_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, g, (size_t)per_stream, (__nv_bfloat16*)hi,
+                                                               (__nv_bfloat16*)lo);
+  EGAZE_LAUNCH_CHECK();
+  return EGAZE_OK;
+}
+
+// out ([C] fp32) is ACCUMULATED into.
+extern "C" int egaze_col_sum_split(const void* hi, const void* lo, long long rows, int C, float* out, void* stream) {
+  EGAZE_CHECK_ARG(hi && out && rows > 0 && C % 4 == 0, "col_sum_split: bad args");
+  int bx = C / 4;
+  if (bx > 128) bx = 128;
+  int by = 256 / bx;
+  if (by < 1) by = 1;
+  dim3 block(bx, by);
+  int blocks = (int)((rows + by - 1) / by);
+  if (blocks > 148 * 2) blocks = 148 * 2;
+  const size_t smem = (size_t)by * C * sizeof(float);
+  col_sum_split_kernel<<<blocks, block, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)hi, (const __nv_bfloat16*)lo,
+                                                                      (size_t)rows, C, out);
   EGAZE_LAUNCH_CHECK();
   return EGAZE_OK;
 }

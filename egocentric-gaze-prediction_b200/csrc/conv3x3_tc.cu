@@ -45,6 +45,7 @@ struct ConvTcParams {
   int reduce;          // 0 none, 1 = 2x2 max (MaxPool2d), 2 = 2x2 sum (grad of nearest upsample)
   int ups;             // replicate every output pixel 2x2 (nn.Upsample(scale_factor=2))
   const __nv_bfloat16* mask;  // optional NHWC [N,Ho,Wo,Cout]: zero the output where mask <= 0 (ReLU backward)
+  int mask_ups;               // mask is stored 2x nearest-upsampled ([N,2Ho,2Wo,Cout]); read its (2oh,2ow) sample
   float* out_f32;             // optional NHWC fp32 [N,Ho*,Wo*,Cout]
   __nv_bfloat16* out_hi;      // optional NHWC bf16
   __nv_bfloat16* out_lo;      // optional (precise) NHWC bf16
@@ -283,7 +284,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
       }
       const int ch = n0 + g * 4;
       if (p.mask) {
-        const uint2 mk = __ldg(reinterpret_cast<const uint2*>(p.mask + ((size_t)(img * Ho + oh) * Wo + ow) * p.Cout + ch));
+        const size_t mpix = p.mask_ups ? ((size_t)(img * 2 * Ho + 2 * oh) * (2 * Wo) + 2 * ow) : ((size_t)(img * Ho + oh) * Wo + ow);
+        const uint2 mk = __ldg(reinterpret_cast<const uint2*>(p.mask + mpix * p.Cout + ch));
         if (!(bf16_bits_to_float(mk.x & 0xffffu) > 0.f)) v.x = 0.f;
         if (!(bf16_bits_to_float(mk.x >> 16) > 0.f)) v.y = 0.f;
         if (!(bf16_bits_to_float(mk.y & 0xffffu) > 0.f)) v.z = 0.f;
@@ -344,8 +346,8 @@ extern "C" int egaze_conv3x3_tiles(int N, int H, int W, int need_even, int* num_
 // See include/egaze.h for the contract.
 extern "C" int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, int N, int H, int W,
                                 int Cin_p, int Cout, const float* bias, const float* scale, const float* shift, int relu,
-                                int reduce, int ups, const void* mask, float* out_f32, void* out_hi, void* out_lo,
-                                float* stats, float* stats_cnt, int precise, void* stream) {
+                                int reduce, int ups, const void* mask, int mask_ups, float* out_f32, void* out_hi,
+                                void* out_lo, float* stats, float* stats_cnt, int precise, void* stream) {
   EGAZE_CHECK_ARG(x_hi && w_hi, "conv3x3_tc: null operand");
   EGAZE_CHECK_ARG(!precise || (x_lo && w_lo), "conv3x3_tc: precise mode needs lo planes");
   EGAZE_CHECK_ARG(N > 0 && H > 0 && W > 0, "conv3x3_tc: bad shape %d %d %d", N, H, W);
@@ -382,6 +384,7 @@ extern "C" int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* 
   smem += 1024;  // alignment slack
   p.bias = bias; p.scale = scale; p.shift = shift; p.relu = relu; p.reduce = reduce; p.ups = ups;
   p.mask = (const __nv_bfloat16*)mask;
+  p.mask_ups = mask_ups;
   p.out_f32 = out_f32; p.out_hi = (__nv_bfloat16*)out_hi; p.out_lo = (__nv_bfloat16*)out_lo;
   p.stats = stats; p.stats_cnt = stats_cnt;
 

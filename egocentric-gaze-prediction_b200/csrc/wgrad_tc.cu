@@ -1,0 +1,248 @@
+// Weight gradient of the 3x3 / pad 1 conv as a tcgen05 GEMM with the PIXEL axis as K (sm_100a).
+//
+//   dW[tap=(r,s)][co][ci] = sum_{n,h,w} dY[n,h,w,co] * X[n,h+r-1,w+s-1,ci]
+//
+// (autograd of nn.Conv2d on the reference hot path: loss.backward() in SP.py:136, spatialstream.py:140.)
+//
+// GEMM view per CTA: M = 128 output channels, N = 64 input channels, K = pixels of the spatial tiles this CTA owns
+// (split-K over tiles), one fp32 TMEM accumulator per vertical tap r (3 x 64 columns).  Both operands are
+// "MN-major" for the tensor core: dY^T tile [K px][64 co] and X window [K px][64 ci] are exactly what TMA delivers
+// from NHWC (pixel rows of 128 B, SWIZZLE_128B), so no transposes are materialised.  Like the forward kernel, the
+// X window for horizontal tap s is fetched once with a (BH+2)-row halo and the three vertical taps read it at a row
+// offset of r*BW rows.  precise mode: dYhi*Xhi + dYhi*Xlo + dYlo*Xhi.
+//
+// Grid: x = split-K slice, y = (co-tile, ci-tile, s).  Epilogue: TMEM -> registers -> vector fp32 atomics into the
+// packed [9][Cout][Cin_p] accumulator (zeroed by the caller), which egaze_unpack_wgrad turns into the OIHW .grad.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 192;
+
+struct WgradParams {
+  int N, H, W, Cin_p, Cout;
+  int BH, BW;
+  int tiles_h, tiles_w, total_tiles;
+  int co_tiles, ci_tiles;
+  int m_chunks;        // 64-channel chunks of dY actually present (1 when Cout == 64, else 2)
+  int nsplit;
+  int stage_bytes, dy_plane_bytes, x_plane_bytes;
+  float* dwp;          // [9][Cout][Cin_p]
+};
+
+template <int NSPLIT>
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid_constant__ CUtensorMap tmY_lo,
+                const __grid_constant__ CUtensorMap tmX_hi, const __grid_constant__ CUtensorMap tmX_lo,
+                const WgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  int job = blockIdx.y;
+  const int s = job % 3;
+  job /= 3;
+  const int ci_t = job % p.ci_tiles;
+  const int co_t = job / p.ci_tiles;
+  const int co0 = co_t * 128, ci0 = ci_t * 64;
+
+  __shared__ uint64_t full[2], empty[2], acc_full;
+  __shared__ uint32_t tmem_base_smem;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 1); }
+    ptx::mbar_init(&acc_full, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmY_hi);
+    ptx::prefetch_tmap(&tmX_hi);
+  }
+  constexpr uint32_t kTmemCols = 256;  // 3 accumulators x 64 columns, rounded to a power of two
+  if (warp == 1) {
+    ptx::tmem_alloc(&tmem_base_smem, kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  const int KP = p.BH * p.BW;                       // pixels (K) per tile, multiple of 16
+  const uint32_t dy_box_bytes = (uint32_t)KP * 128u;
+  const uint32_t x_box_bytes = (uint32_t)(p.BH + 2) * p.BW * 128u;
+  const uint32_t tx_bytes = NSPLIT * (p.m_chunks * dy_box_bytes + x_box_bytes);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int st = 0;
+      uint32_t par = 1;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const int tw_i = t % p.tiles_w;
+        const int th_i = (t / p.tiles_w) % p.tiles_h;
+        const int img = t / (p.tiles_w * p.tiles_h);
+        const int h0 = th_i * p.BH, w0 = tw_i * p.BW;
+        ptx::mbar_wait(&empty[st], par);
+        ptx::mbar_arrive_expect_tx(&full[st], tx_bytes);
+        uint8_t* base = smem + (size_t)st * p.stage_bytes;
+        for (int c = 0; c < p.m_chunks; ++c) {
+          ptx::tma_load_4d(base + c * dy_box_bytes, &tmY_hi, &full[st], co0 + 64 * c, w0, h0, img);
+          if (NSPLIT == 2)
+            ptx::tma_load_4d(base + p.dy_plane_bytes + c * dy_box_bytes, &tmY_lo, &full[st], co0 + 64 * c, w0, h0, img);
+        }
+        uint8_t* xb = base + (size_t)NSPLIT * p.dy_plane_bytes;
+        ptx::tma_load_4d(xb, &tmX_hi, &full[st], ci0, w0 - 1 + s, h0 - 1, img);
+        if (NSPLIT == 2) ptx::tma_load_4d(xb + p.x_plane_bytes, &tmX_lo, &full[st], ci0, w0 - 1 + s, h0 - 1, img);
+        if (++st == 2) { st = 0; par ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = ptx::make_idesc_bf16(128, 64, 1, 1);  // both operands MN-major
+      // MN-major SWIZZLE_128B canonical layout: 64 channels (128 B) contiguous, 8 pixel rows per 1024 B atom (SBO),
+      // next 64-channel chunk LBO bytes away.
+      const uint64_t a_static = ptx::make_smem_desc(0, dy_box_bytes, 1024, 128);
+      const uint64_t b_static = ptx::make_smem_desc(0, x_box_bytes, 1024, 128);
+      const int ksteps = KP / 16;
+      int st = 0;
+      uint32_t par = 0;
+      uint32_t acc[3] = {0, 0, 0};
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        ptx::mbar_wait(&full[st], par);
+        ptx::tc_fence_after();
+        const uint32_t base = ptx::smem_u32(smem + (size_t)st * p.stage_bytes);
+        const uint64_t a_hi = a_static + (uint64_t)(base >> 4);
+        const uint64_t a_lo = a_hi + (uint64_t)((uint32_t)p.dy_plane_bytes >> 4);
+        const uint64_t b_hi = b_static + (uint64_t)((base + (uint32_t)NSPLIT * p.dy_plane_bytes) >> 4);
+        const uint64_t b_lo = b_hi + (uint64_t)((uint32_t)p.x_plane_bytes >> 4);
+        const uint32_t r_step16 = (uint32_t)(p.BW * 128) >> 4;
+#pragma unroll 1
+        for (int r = 0; r < 3; ++r) {
+          const uint32_t d = tmem_base + (uint32_t)(r * 64);
+          const uint64_t br_hi = b_hi + (uint64_t)(r * r_step16), br_lo = b_lo + (uint64_t)(r * r_step16);
+          for (int k = 0; k < ksteps; ++k) {  // 16 pixel rows = 2048 B per K step
+            const uint64_t ko = (uint64_t)(k * 128);
+            ptx::umma_bf16(d, a_hi + ko, br_hi + ko, idesc, acc[r]);
+            acc[r] = 1;
+            if (NSPLIT == 2) {
+              ptx::umma_bf16(d, a_hi + ko, br_lo + ko, idesc, 1);
+              ptx::umma_bf16(d, a_lo + ko, br_hi + ko, idesc, 1);
+            }
+          }
+        }
+        ptx::umma_commit(&empty[st]);
+        if (++st == 2) { st = 0; par ^= 1; }
+      }
+      ptx::umma_commit(&acc_full);
+    }
+  } else {
+    // epilogue: thread = output-channel row; 64 consecutive ci per tap -> float4 atomics
+    const int ew = warp & 3;
+    const int m = ew * 32 + lane;
+    ptx::mbar_wait(&acc_full, 0);
+    ptx::tc_fence_after();
+    const bool any_tile = (int)blockIdx.x < p.total_tiles;
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(r * 64 + c0), v);
+        ptx::tmem_ld_wait();
+        if (any_tile && co0 + m < p.Cout) {
+          float* dst = p.dwp + ((size_t)(r * 3 + s) * p.Cout + co0 + m) * p.Cin_p + ci0 + c0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 val = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                     __uint_as_float(v[j + 3]));
+            atomicAdd(reinterpret_cast<float4*>(dst + j), val);
+          }
+        }
+      }
+    }
+    ptx::tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, kTmemCols);
+}
+
+void pick_wgrad_tile(int H, int W, int* BH, int* BW) {
+  // K per tile = BH*BW must be a multiple of 16 and <= 128; BW % 8 == 0
+  const int cand[][2] = {{8, 16}, {4, 32}, {16, 8}, {14, 8}, {6, 16}, {12, 8}, {2, 64}, {10, 8}, {4, 16}, {8, 8}, {2, 32}, {4, 8}, {2, 8}};
+  double best = -1.0;
+  for (auto& c : cand) {
+    const int bh = c[0], bw = c[1];
+    if ((bh * bw) % 16) continue;
+    const double eff = (double)H * W / ((double)ceil_div(H, bh) * ceil_div(W, bw) * bh * bw);  // useful K fraction
+    const double halo = (double)(bh + 2) / bh;
+    const double score = eff / (0.6 + 0.4 * halo) * (0.75 + 0.25 * (bh * bw) / 128.0);
+    if (score > best) { best = score; *BH = bh; *BW = bw; }
+  }
+}
+
+}  // namespace
+
+// dwp ([9][Cout][Cin_p] fp32) is ACCUMULATED into: zero it first.  Cin_p % 64 == 0, Cout % 64 == 0.
+extern "C" int egaze_wgrad3x3_tc(const void* x_hi, const void* x_lo, const void* dy_hi, const void* dy_lo, int N, int H,
+                                 int W, int Cin_p, int Cout, float* dwp, int precise, void* stream) {
+  EGAZE_CHECK_ARG(x_hi && dy_hi && dwp, "wgrad3x3_tc: null operand");
+  EGAZE_CHECK_ARG(!precise || (x_lo && dy_lo), "wgrad3x3_tc: precise mode needs lo planes");
+  EGAZE_CHECK_ARG(Cin_p % 64 == 0 && Cout % 64 == 0, "wgrad3x3_tc: Cin_p=%d, Cout=%d must be multiples of 64", Cin_p, Cout);
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = N; p.H = H; p.W = W; p.Cin_p = Cin_p; p.Cout = Cout;
+  pick_wgrad_tile(H, W, &p.BH, &p.BW);
+  p.tiles_h = ceil_div(H, p.BH); p.tiles_w = ceil_div(W, p.BW);
+  p.total_tiles = N * p.tiles_h * p.tiles_w;
+  p.co_tiles = ceil_div(Cout, 128); p.ci_tiles = Cin_p / 64;
+  p.m_chunks = Cout >= 128 ? 2 : 1;
+  p.nsplit = precise ? 2 : 1;
+  const int KP = p.BH * p.BW;
+  p.dy_plane_bytes = 2 * KP * 128;                                  // room for both 64-channel chunks
+  p.x_plane_bytes = ((p.BH + 2) * p.BW * 128 + 1023) / 1024 * 1024;
+  // the MMA for tap r reads K rows [r*BW, r*BW + KP): always inside the (BH+2)*BW window
+  p.stage_bytes = p.nsplit * (p.dy_plane_bytes + p.x_plane_bytes);
+  p.dwp = dwp;
+  const size_t smem = (size_t)2 * p.stage_bytes + 1024;
+  EGAZE_CHECK_ARG(smem <= 224 * 1024, "wgrad3x3_tc: tile does not fit shared memory");
+
+  CUtensorMap tmY_hi, tmY_lo, tmX_hi, tmX_lo;
+  {
+    uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    uint64_t str[3] = {(uint64_t)Cout * 2, (uint64_t)W * Cout * 2, (uint64_t)H * W * Cout * 2};
+    uint32_t box[4] = {64, (uint32_t)p.BW, (uint32_t)p.BH, 1};
+    int rc = egaze_encode_tmap(&tmY_hi, dy_hi, 4, dims, str, box, 128, 2);
+    if (rc) return rc;
+    rc = egaze_encode_tmap(&tmY_lo, precise ? dy_lo : dy_hi, 4, dims, str, box, 128, 2);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)Cin_p, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    uint64_t str[3] = {(uint64_t)Cin_p * 2, (uint64_t)W * Cin_p * 2, (uint64_t)H * W * Cin_p * 2};
+    uint32_t box[4] = {64, (uint32_t)p.BW, (uint32_t)(p.BH + 2), 1};
+    int rc = egaze_encode_tmap(&tmX_hi, x_hi, 4, dims, str, box, 128, 2);
+    if (rc) return rc;
+    rc = egaze_encode_tmap(&tmX_lo, precise ? x_lo : x_hi, 4, dims, str, box, 128, 2);
+    if (rc) return rc;
+  }
+  const int jobs = p.co_tiles * p.ci_tiles * 3;
+  int ksplit = (148 * 2 + jobs - 1) / jobs;
+  if (ksplit > p.total_tiles) ksplit = p.total_tiles;
+  if (ksplit < 1) ksplit = 1;
+  dim3 grid((unsigned)ksplit, (unsigned)jobs);
+  if (precise) {
+    static bool attr = false;
+    if (!attr) {
+      EGAZE_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+      attr = true;
+    }
+    wgrad_tc_kernel<2><<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmY_hi, tmY_lo, tmX_hi, tmX_lo, p);
+  } else {
+    static bool attr = false;
+    if (!attr) {
+      EGAZE_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+      attr = true;
+    }
+    wgrad_tc_kernel<1><<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmY_hi, tmY_lo, tmX_hi, tmX_lo, p);
+  }
+  EGAZE_LAUNCH_CHECK();
+  return EGAZE_OK;
+}

@@ -1,22 +1,304 @@
-"""Autograd bridges (filled in as the backward kernels land)."""
+"""Autograd bridges: torch.autograd.Function wrappers whose forward/backward run entirely on the egaze kernels.
+
+One Function per drop-in module (model_SP, single-stream VGG, TrunkSequential, late_fusion).  Activations needed by the
+backward (split-bf16 conv inputs for wgrad, raw fp32 conv outputs + batch statistics for BatchNorm backward) are kept
+in a Python-side record on ctx; gradients flow between layers as NHWC tensors and never leave the device.
+
+Backward schedule per layer (reverse order):
+  conv+BN+ReLU(+pool): bn_bwd (reduce -> apply; ReLU mask + max-pool routing fused) -> d(raw) split
+                       -> wgrad3x3_tc (dW) + col_sum (db) + conv3x3_tc with flipped weights (dgrad, fp32 out)
+  conv+ReLU(+ups)    : dgrad of the NEXT layer already applied this layer's ReLU mask (and the 2x2 sum that is the
+                       gradient of nn.Upsample) in its epilogue -> wgrad + col_sum + dgrad
+"""
+import torch
+import torch.nn as nn
+
+from . import engine, ops
 
 
-def _todo(what):
-    raise NotImplementedError("egaze: backward for %s is not built yet; run under torch.no_grad() / eval with "
-                              "requires_grad=False parameters" % what)
+def _req(p):
+    return p is not None and p.requires_grad
 
 
-def sequential_with_grad(seq, x):
-    _todo("TrunkSequential")
+class _GradBag(object):
+    """Collects parameter gradients by identity."""
+
+    def __init__(self):
+        self.d = {}
+
+    def put(self, p, g):
+        if p is not None and p.requires_grad:
+            self.d[id(p)] = g.reshape(p.shape)
+
+    def get(self, p):
+        return self.d.get(id(p))
+
+
+def _conv_param_grads(bag, conv, x_act, gpre_act):
+    """dW via the tcgen05 wgrad kernel, db via a column sum.  gpre_act: gradient w.r.t. the conv output."""
+    if _req(conv.weight):
+        gw = ops.wgrad3x3(x_act, gpre_act, conv.out_channels, conv.in_channels)
+        bag.put(conv.weight, gw)
+    if _req(conv.bias):
+        bag.put(conv.bias, ops.col_sum(gpre_act, conv.out_channels))
+
+
+def _dgrad(conv, gpre_act, **kw):
+    """Data gradient of a 3x3 conv: the same tcgen05 kernel with flipped / transposed weights."""
+    cin = conv.in_channels
+    rows_p = ops.pad_channels(cin) if cin % 16 else cin
+    wpack = ops.pack_cache.get(conv.weight, 1, rows_p=rows_p, cols_p=gpre_act.Cp)
+    return ops.conv3x3(gpre_act, wpack, **kw)
+
+
+def _any_req(mods):
+    return any(p.requires_grad for m in mods for p in m.parameters())
+
+
+def bn_sequential_backward(specs, saved, g, bag, need_input_grad):
+    """Backward through a conv+BN+ReLU(+pool) chain.  g: NHWC fp32 gradient w.r.t. the chain output.
+    Returns the NHWC fp32 gradient w.r.t. the chain input (or None)."""
+    first_needed = None
+    for i, sp in enumerate(specs):
+        if _any_req([sp.conv, sp.bn]):
+            first_needed = i
+            break
+    if first_needed is None and not need_input_grad:
+        return None
+    stop = 0 if need_input_grad else first_needed
+    for i in range(len(specs) - 1, stop - 1, -1):
+        sp, rec = specs[i], saved[i]
+        if "raw" not in rec:
+            raise NotImplementedError("egaze: backward through an eval-mode (folded) BatchNorm is not on the hot path")
+        draw, _, dgamma, dbeta = ops.bn_bwd(rec["raw"], g, rec["scale"], rec["shift"], rec["mean"], rec["invstd"],
+                                            pool=sp.pool, relu=sp.relu)
+        C = sp.conv.out_channels
+        bag.put(sp.bn.weight, dgamma[:C])
+        bag.put(sp.bn.bias, dbeta[:C])
+        _conv_param_grads(bag, sp.conv, rec["x"], draw)
+        if i > stop or (i == 0 and need_input_grad):
+            _, g, _ = _dgrad(sp.conv, draw, want_f32=True, want_split=False)
+        else:
+            g = None
+    return g
+
+
+def relu_sequential_backward(specs, saved, gpre, bag, want_input_grad_f32):
+    """Backward through a conv+bias+ReLU(+ups) chain.  gpre: split gradient w.r.t. the LAST conv's output
+    (its ReLU mask already applied).  Returns the NHWC fp32 gradient w.r.t. the chain input (or None)."""
+    for i in range(len(specs) - 1, -1, -1):
+        sp, rec = specs[i], saved[i]
+        _conv_param_grads(bag, sp.conv, rec["x"], gpre)
+        if i > 0:
+            prev = specs[i - 1]
+            gpre, _, _ = _dgrad(sp.conv, gpre, reduce=2 if prev.ups else 0, mask=saved[i - 1]["y"].hi, mask_ups=prev.ups)
+        elif want_input_grad_f32:
+            _, g, _ = _dgrad(sp.conv, gpre, want_f32=True, want_split=False)
+            return g
+    return None
+
+
+def _params(module):
+    return list(module.parameters())
+
+
+def _ret_grads(bag, params):
+    return tuple(bag.get(p) for p in params)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# model_SP
+# ---------------------------------------------------------------------------------------------------------------------
+class _ModelSPFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, x_s, x_t, *params):
+        saved_s, saved_t, saved_tail = [], [], []
+        specs_s, _ = engine.parse_sequential(model.features_s)
+        specs_t, _ = engine.parse_sequential(model.features_t)
+        a_s = ops.to_split(x_s, ops.pad_channels(specs_s[0].conv.in_channels))
+        a_t = ops.to_split(x_t, ops.pad_channels(specs_t[0].conv.in_channels))
+        for sp in specs_s:
+            a_s = engine.run_conv_spec(a_s, sp, saved_s)
+        for sp in specs_t:
+            a_t = engine.run_conv_spec(a_t, sp, saved_t)
+        # forward hooks registered on the trunks (AT.py:105 idiom) still fire, with detached NCHW views
+        for mod, act in ((model.features_s, a_s), (model.features_t, a_t)):
+            if mod._forward_hooks:
+                y = ops.from_split(act)
+                for hook in mod._forward_hooks.values():
+                    hook(mod, (None,), y)
+        out = engine.run_sp_tail(model, a_s, a_t, saved_tail)
+        ctx.model, ctx.rec = model, (specs_s, specs_t, saved_s, saved_t, saved_tail[0])
+        ctx.need_x = (x_s.requires_grad, x_t.requires_grad)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        model = ctx.model
+        specs_s, specs_t, saved_s, saved_t, tail = ctx.rec
+        bag = _GradBag()
+        dspecs, head = engine.parse_sequential(model.decoder)
+        dsaved = tail["decoder"]
+        # 1x1 conv + sigmoid backward; its dx already carries the last decoder ReLU's mask
+        gpre, dw, db = ops.head_bwd(tail["head_in"], head.weight, tail["out"], gout, relu_mask=True)
+        bag.put(head.weight, dw)
+        bag.put(head.bias, db)
+        trunk_need = _any_req([model.features_s, model.features_t]) or any(ctx.need_x)
+        upstream_need = trunk_need or _any_req([model.fusion, model.bn])
+        g = relu_sequential_backward(dspecs, dsaved, gpre, bag, upstream_need)
+        if upstream_need:
+            bn = model.bn
+            if "mean" not in tail:
+                raise NotImplementedError("egaze: backward through model_SP.bn in eval mode is not on the hot path")
+            _, dmx, dgamma, dbeta = ops.bn_bwd(tail["mx"], g, tail["scale"], tail["shift"], tail["mean"], tail["invstd"],
+                                               pool=False, relu=True, want_f32=True, want_split=False)
+            bag.put(bn.weight, dgamma)
+            bag.put(bn.bias, dbeta)
+            d2 = ops.pairmax_bwd(tail["raw2"], dmx)  # [2B,14,14,512] split: gradient routed to the arg-max stream
+            fus = model.fusion
+            if _req(fus.weight):
+                bag.put(fus.weight, ops.wgrad3x3(tail["cat"], d2, fus.out_channels, fus.in_channels))
+            if _req(fus.bias):
+                bag.put(fus.bias, ops.col_sum(d2, fus.out_channels))
+            if trunk_need:
+                wpack = ops.pack_cache.get(fus.weight, 1, cols_p=d2.Cp)
+                _, gf, _ = ops.conv3x3(d2, wpack, want_f32=True, want_split=False)
+                B = gf.shape[0] // 2
+                g_s, g_t = gf[:B], gf[B:]
+                gx_s = bn_sequential_backward(specs_s, saved_s, g_s, bag, ctx.need_x[0])
+                gx_t = bn_sequential_backward(specs_t, saved_t, g_t, bag, ctx.need_x[1])
+            else:
+                gx_s = gx_t = None
+        else:
+            gx_s = gx_t = None
+        gx_s = ops.nhwc_f32_to_nchw(gx_s, specs_s[0].conv.in_channels) if (gx_s is not None and ctx.need_x[0]) else None
+        gx_t = ops.nhwc_f32_to_nchw(gx_t, specs_t[0].conv.in_channels) if (gx_t is not None and ctx.need_x[1]) else None
+        ctx.rec = None
+        return (None, gx_s, gx_t) + _ret_grads(bag, _params(model))
 
 
 def model_sp_with_grad(model, x_s, x_t):
-    _todo("model_SP")
+    return _ModelSPFn.apply(model, x_s, x_t, *_params(model))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# TrunkSequential used on its own (e.g. the trainable flow trunk of temporalstream.py)
+# ---------------------------------------------------------------------------------------------------------------------
+class _SequentialFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, seq, x, *params):
+        specs, tail = engine.parse_sequential(seq)
+        if tail is not None or any(sp.bn is None for sp in specs):
+            raise NotImplementedError("egaze: stand-alone training is implemented for conv+BN+ReLU trunks")
+        saved = []
+        act = ops.to_split(x, ops.pad_channels(specs[0].conv.in_channels))
+        for sp in specs:
+            act = engine.run_conv_spec(act, sp, saved)
+        ctx.seq, ctx.rec, ctx.need_x = seq, (specs, saved), x.requires_grad
+        y = ops.from_split(act)
+        ctx.out_act = act
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        specs, saved = ctx.rec
+        bag = _GradBag()
+        g = ops.nchw_to_nhwc_f32(gy)
+        gx = bn_sequential_backward(specs, saved, g, bag, ctx.need_x)
+        gx = ops.nhwc_f32_to_nchw(gx, specs[0].conv.in_channels) if (gx is not None and ctx.need_x) else None
+        ctx.rec = None
+        return (None, gx) + _ret_grads(bag, _params(ctx.seq))
+
+
+def sequential_with_grad(seq, x):
+    return _SequentialFn.apply(seq, x, *_params(seq))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# single-stream VGG (script-local class of spatialstream.py / temporalstream.py)
+# ---------------------------------------------------------------------------------------------------------------------
+class _VGGFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, x, *params):
+        specs, _ = engine.parse_sequential(model.features)
+        saved_f, saved_d = [], []
+        act = ops.to_split(x, ops.pad_channels(specs[0].conv.in_channels))
+        for sp in specs:
+            act = engine.run_conv_spec(act, sp, saved_f)
+        feat_act = act
+        dspecs, head = engine.parse_sequential(model.decoder)
+        for sp in dspecs:
+            act = engine.run_conv_spec(act, sp, saved_d)
+        out = ops.head_fwd(act, head.weight, head.bias)
+        ctx.model, ctx.rec, ctx.need_x = model, (specs, saved_f, dspecs, saved_d, head, act, out), x.requires_grad
+        if model.return_features:
+            feat = ops.from_split(feat_act)
+            ctx.mark_non_differentiable(feat)
+            return out, feat
+        return out
+
+    @staticmethod
+    def backward(ctx, gout, *unused):
+        model = ctx.model
+        specs, saved_f, dspecs, saved_d, head, head_in, out = ctx.rec
+        bag = _GradBag()
+        gpre, dw, db = ops.head_bwd(head_in, head.weight, out, gout, relu_mask=True)
+        bag.put(head.weight, dw)
+        bag.put(head.bias, db)
+        trunk_need = _any_req([model.features]) or ctx.need_x
+        g = relu_sequential_backward(dspecs, saved_d, gpre, bag, trunk_need)
+        gx = bn_sequential_backward(specs, saved_f, g, bag, ctx.need_x) if trunk_need else None
+        gx = ops.nhwc_f32_to_nchw(gx, specs[0].conv.in_channels) if (gx is not None and ctx.need_x) else None
+        ctx.rec = None
+        return (None, gx) + _ret_grads(bag, _params(model))
+
+
+def vgg_with_grad(model, x):
+    return _VGGFn.apply(model, x, *_params(model))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# late_fusion
+# ---------------------------------------------------------------------------------------------------------------------
+class _LateFusionFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, f, g, *params):
+        x = torch.cat((f, g), dim=1)
+        specs, head = engine.parse_sequential(model.fusion)
+        saved = []
+        act = ops.to_split(x, ops.pad_channels(2))
+        for sp in specs:
+            act = engine.run_conv_spec(act, sp, saved)
+        out = ops.head_fwd(act, head.weight, head.bias)
+        ctx.model, ctx.rec = model, (specs, saved, head, act, out)
+        ctx.need_x = (f.requires_grad, g.requires_grad)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        model = ctx.model
+        specs, saved, head, head_in, out = ctx.rec
+        bag = _GradBag()
+        # the head's input is ReLU(BN(conv)): its dx (ReLU-masked) is the gradient w.r.t. the BN output; bn_bwd applies the
+        # same mask again (idempotent)
+        gact, dw, db = ops.head_bwd(head_in, head.weight, out, gout, relu_mask=True)
+        bag.put(head.weight, dw)
+        bag.put(head.bias, db)
+        g = ops.from_split_nhwc(gact)
+        need_x = any(ctx.need_x)
+        gx = bn_sequential_backward(specs, saved, g, bag, need_x)
+        gf = gg = None
+        if gx is not None and need_x:
+            gx = ops.nhwc_f32_to_nchw(gx, 2)
+            gf = gx[:, 0:1].contiguous() if ctx.need_x[0] else None
+            gg = gx[:, 1:2].contiguous() if ctx.need_x[1] else None
+        ctx.rec = None
+        return (None, gf, gg) + _ret_grads(bag, _params(model))
 
 
 def late_fusion_with_grad(model, f, g):
-    _todo("late_fusion")
+    return _LateFusionFn.apply(model, f, g, *_params(model))
 
 
 def lstmnet_with_grad(model, inp, h0, c0):
-    _todo("lstmnet")
+    raise NotImplementedError("egaze: lstmnet backward (AT.trainLSTM) is not built yet; forward/inference only")

@@ -84,6 +84,14 @@ def from_split(act, C=None):
     return out
 
 
+def from_split_nhwc(act):
+    """Act -> NHWC fp32 (same channel stride)."""
+    x = act.hi.float()
+    if act.lo is not None:
+        x += act.lo.float()
+    return x
+
+
 def nhwc_f32_to_nchw(x, C=None):
     N, H, W, Cs = x.shape
     C = Cs if C is None else C
@@ -170,7 +178,7 @@ def conv_tiles(N, H, W, need_even=False):
 
 
 def conv3x3(act, wpack, bias=None, scale=None, shift=None, relu=False, reduce=0, ups=False, mask=None,
-            want_f32=False, want_split=True, stats=False, precise=None):
+            want_f32=False, want_split=True, stats=False, precise=None, mask_ups=False):
     """3x3/pad-1 conv on the tcgen05 path.  wpack = (w_hi, w_lo, Cout_p, Cin_p) from pack_cache.
     Returns (out_act | None, out_f32 | None, (stats_partial, stats_cnt) | None)."""
     w_hi, w_lo, Cout, Cin_p = wpack
@@ -192,7 +200,7 @@ def conv3x3(act, wpack, bias=None, scale=None, shift=None, relu=False, reduce=0,
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
     call("egaze_conv3x3_tc", act.hi, act.lo if precise else None, w_hi, w_lo if precise else None, N, H, W, Cin_p, Cout,
-         bias, scale, shift, int(relu), int(reduce), int(ups), mask, out_f32,
+         bias, scale, shift, int(relu), int(reduce), int(ups), mask, int(mask_ups), out_f32,
          out_act.hi if out_act is not None else None, out_act.lo if out_act is not None else None,
          st[0] if st else None, st[1] if st else None, int(precise), stream_ptr())
     if _conv_timer["on"]:
@@ -259,6 +267,88 @@ def head_fwd(act, w, b, want_logit=False):
     call("egaze_head_fwd", act.hi, act.lo, wf, b.detach() if b is not None else None, wf.numel(), act.Cp, N * H * W, out,
          logit, stream_ptr())
     return (out, logit) if want_logit else out
+
+
+# ---- backward pieces --------------------------------------------------------------------------------------------
+def repad(act, Cp):
+    """Same activation with the channel stride padded (zeros) to Cp (wgrad needs 64-channel K chunks)."""
+    if act.Cp == Cp:
+        return act
+    hi = torch.zeros((act.N, act.H, act.W, Cp), dtype=BF16, device=act.hi.device)
+    hi[..., :act.Cp].copy_(act.hi)
+    lo = None
+    if act.lo is not None:
+        lo = torch.zeros((act.N, act.H, act.W, Cp), dtype=BF16, device=act.hi.device)
+        lo[..., :act.Cp].copy_(act.lo)
+    return Act(hi, lo, act.C)
+
+
+def wgrad3x3(x_act, dy_act, Cout, Cin, precise=None):
+    """dW (OIHW fp32 [Cout, Cin, 3, 3]) of a 3x3/pad-1 conv from its input activation and output gradient."""
+    precise = is_precise() if precise is None else precise
+    x_act = repad(x_act, (x_act.Cp + 63) // 64 * 64)
+    dy_act = repad(dy_act, (dy_act.Cp + 63) // 64 * 64)
+    N, H, W = x_act.N, x_act.H, x_act.W
+    dev = x_act.hi.device
+    dwp = torch.zeros((9, dy_act.Cp, x_act.Cp), dtype=F32, device=dev)
+    call("egaze_wgrad3x3_tc", x_act.hi, x_act.lo if precise else None, dy_act.hi, dy_act.lo if precise else None, N, H, W,
+         x_act.Cp, dy_act.Cp, dwp, int(precise), stream_ptr())
+    gw = torch.empty((Cout, Cin, 3, 3), dtype=F32, device=dev)
+    if dy_act.Cp != Cout:
+        dwp = dwp[:, :Cout].contiguous()
+    call("egaze_unpack_wgrad", dwp, Cout, Cin, x_act.Cp, 0.0, gw, stream_ptr())
+    return gw
+
+
+_bn_bwd_nblk = [None]
+
+
+def bn_bwd(raw, g, scale, shift, mean, invstd, pool, relu, want_f32=False, want_split=True):
+    """BatchNorm(+ReLU)(+MaxPool) backward.  raw: conv output NHWC fp32; g: grad w.r.t. the layer output (pooled res).
+    -> (draw Act | None, draw f32 | None, dgamma, dbeta)"""
+    N, H, W, C = raw.shape
+    dev = raw.device
+    if _bn_bwd_nblk[0] is None:
+        nb = ctypes.c_int(0)
+        call("egaze_bn_bwd_blocks", ctypes.addressof(nb))
+        _bn_bwd_nblk[0] = nb.value
+    partial = torch.empty((_bn_bwd_nblk[0], 2, C), dtype=F32, device=dev)
+    dgamma = torch.empty((C,), dtype=F32, device=dev)
+    dbeta = torch.empty((C,), dtype=F32, device=dev)
+    g = g.contiguous()
+    call("egaze_bn_bwd_reduce", raw, g, N, H, W, C, scale, shift, mean, invstd, int(pool), int(relu), partial, dgamma,
+         dbeta, stream_ptr())
+    out_act = empty_act(N, H, W, C, C, dev, lo=True) if want_split else None
+    out_f32 = torch.empty((N, H, W, C), dtype=F32, device=dev) if want_f32 else None
+    call("egaze_bn_bwd_apply", raw, g, N, H, W, C, scale, shift, mean, invstd, dgamma, dbeta, int(pool), int(relu), out_f32,
+         out_act.hi if out_act is not None else None, out_act.lo if out_act is not None else None, stream_ptr())
+    return out_act, out_f32, dgamma, dbeta
+
+
+def pairmax_bwd(raw2, dmx):
+    B2 = raw2.shape[0]
+    act = empty_act(B2, raw2.shape[1], raw2.shape[2], raw2.shape[3], raw2.shape[3], raw2.device, lo=True)
+    call("egaze_pairmax_bwd", raw2, dmx.contiguous(), dmx.numel(), act.hi, act.lo, stream_ptr())
+    return act
+
+
+def col_sum(act, C=None):
+    """sum over pixels of a split activation -> [C] fp32 (conv bias gradient)."""
+    out = torch.zeros((act.Cp,), dtype=F32, device=act.hi.device)
+    call("egaze_col_sum_split", act.hi, act.lo, act.N * act.H * act.W, act.Cp, out, stream_ptr())
+    return out if C is None or C == act.Cp else out[:C].contiguous()
+
+
+def head_bwd(act, w, y, gy, relu_mask=True):
+    """Backward of sigmoid(conv1x1(act)).  -> (dx Act, dw [C], db [1])"""
+    dev = act.hi.device
+    dx = empty_act(act.N, act.H, act.W, act.Cp, act.C, dev, lo=True)
+    wf = w.detach().reshape(-1).contiguous().float()
+    dw = torch.zeros((wf.numel(),), dtype=F32, device=dev)
+    db = torch.zeros((1,), dtype=F32, device=dev)
+    call("egaze_head_bwd", act.hi, act.lo, wf, wf.numel(), act.Cp, act.N * act.H * act.W, y.contiguous(),
+         gy.contiguous().float(), int(relu_mask), dx.hi, dx.lo, dw, db, stream_ptr())
+    return dx, dw, db
 
 
 # ---- floss -------------------------------------------------------------------------------------------------------

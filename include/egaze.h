@@ -45,15 +45,20 @@ int egaze_unpack_wgrad(const float* dwp, int Cout, int Cin, int Cin_p, float bet
 /* Tile geometry the kernel will use for an (N,H,W) map; num_tiles sizes the BN-statistics workspace. */
 int egaze_conv3x3_tiles(int N, int H, int W, int need_even, int* num_tiles, int* BH, int* BW);
 /* y = epilogue(conv3x3(x, w)):  v = acc + bias; v = v*scale + shift; relu; 2x2 reduce (1 max = MaxPool2d utils.py:68,
- * 2 sum = grad of nn.Upsample); mask (zero where mask <= 0: ReLU backward); 2x nearest replicate (ups: model_SP.py:16,20,24,27).
+ * 2 sum = grad of nn.Upsample); mask (zero where mask <= 0: ReLU backward; mask_ups: the mask tensor is stored 2x upsampled);
+ * 2x nearest replicate (ups: model_SP.py:16,20,24,27).
  *   x_hi/x_lo : [N][H][W][Cin_p] bf16        w_hi/w_lo : [9][Cout][Cin_p] bf16 (egaze_pack_w3x3)
  *   out_f32 / out_hi / out_lo : NHWC [N][Ho][Wo][Cout] (any non-NULL subset is written)
  *   stats [num_tiles][2][Cout], stats_cnt [num_tiles] : per-tile (mean, M2) of v BEFORE relu, for BatchNorm batch statistics
  *   precise != 0 : hi*hi + hi*lo + lo*hi (3 MMAs), needs x_lo and w_lo;  0 : single bf16 pass. */
 int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, int N, int H, int W,
                      int Cin_p, int Cout, const float* bias, const float* scale, const float* shift, int relu,
-                     int reduce, int ups, const void* mask, float* out_f32, void* out_hi, void* out_lo, float* stats,
-                     float* stats_cnt, int precise, void* stream);
+                     int reduce, int ups, const void* mask, int mask_ups, float* out_f32, void* out_hi, void* out_lo,
+                     float* stats, float* stats_cnt, int precise, void* stream);
+/* Weight gradient: dwp[9][Cout][Cin_p] (fp32, ACCUMULATED: zero first) += sum_pixels dY (x) X-window; tcgen05 GEMM with the
+ * pixel axis as K, MN-major operands straight from NHWC.  Cin_p % 64 == 0, Cout % 64 == 0.  (loss.backward(): SP.py:136) */
+int egaze_wgrad3x3_tc(const void* x_hi, const void* x_lo, const void* dy_hi, const void* dy_lo, int N, int H, int W,
+                      int Cin_p, int Cout, float* dwp, int precise, void* stream);
 
 /* ---- BatchNorm2d pieces (utils.py:72, model_SP.py:12, late_fusion.py:10-12) ---------------------------------- */
 int egaze_bn_finalize(const float* partial, const float* cnt, int T, int C, float eps, float momentum,
@@ -68,6 +73,16 @@ int egaze_bn_apply(const float* x, int N, int H, int W, int C, const float* scal
                    int pool, float* out_f32, void* out_hi, void* out_lo, void* stream);
 /* out[b] = max(x[b], x[b+B]) : Conv3d(1,3,3)+MaxPool3d((2,1,1)) second half (model_SP.py:11,43) */
 int egaze_pairmax(const float* x, long long per_stream, float* out, void* stream);
+/* backward pieces (autograd of the modules above; loss.backward() in SP.py:136, LF.py:98, spatialstream.py:140) */
+int egaze_bn_bwd_blocks(int* nblk);
+int egaze_bn_bwd_reduce(const float* raw, const float* g, int N, int H, int W, int C, const float* scale,
+                        const float* shift, const float* mean, const float* invstd, int pool, int relu, float* partial,
+                        float* dgamma, float* dbeta, void* stream);
+int egaze_bn_bwd_apply(const float* raw, const float* g, int N, int H, int W, int C, const float* scale,
+                       const float* shift, const float* mean, const float* invstd, const float* dgamma,
+                       const float* dbeta, int pool, int relu, float* out_f32, void* out_hi, void* out_lo, void* stream);
+int egaze_pairmax_bwd(const float* x, const float* g, long long per_stream, void* hi, void* lo, void* stream);
+int egaze_col_sum_split(const void* hi, const void* lo, long long rows, int C, float* out, void* stream);
 
 /* ---- 1x1 conv to one channel + sigmoid (model_SP.py:30,32 ; late_fusion.py:13,15) ---------------------------- */
 int egaze_head_fwd(const void* x_hi, const void* x_lo, const float* w, const float* b, int C, int Cs, long long P,

@@ -271,8 +271,10 @@ def bilinear_upsample(x, scale, align_corners=False):
 
 
 # ---- deterministic synthetic parameters / inputs (shared by golden generation, tests, bench) -------------------------
-def synth_state_dict(shapes, seed=0):
-    """Deterministic, box-independent parameters for a {key: shape} description (insertion-ordered)."""
+def synth_state_dict(shapes, seed=0, decoder_gain=1.0):
+    """Deterministic, box-independent parameters for a {key: shape} description (insertion-ordered).
+    decoder_gain scales the BN-less decoder conv weights: 1.0 is He init (random-init logits of std ~8, saturated
+    sigmoid, ill-conditioned gradients: stock fp32 is itself ~1e-2 away from fp64 there); ~0.8 keeps logits O(1)."""
     import zlib
     sd = {}
     for k, shp in shapes.items():
@@ -286,7 +288,8 @@ def synth_state_dict(shapes, seed=0):
             sd[k] = (rs.rand(*shp) + 0.5).astype(np.float32)
         elif len(shp) >= 3:  # conv weight
             fan = int(np.prod(shp[1:]))
-            sd[k] = (rs.randn(*shp) * math.sqrt(2.0 / fan)).astype(np.float32)
+            gain = decoder_gain if k.startswith('decoder.') else 1.0
+            sd[k] = (rs.randn(*shp) * (gain * math.sqrt(2.0 / fan))).astype(np.float32)
         elif len(shp) == 2:  # LSTM / Linear weight
             sd[k] = (rs.uniform(-1, 1, shp) / math.sqrt(shp[1])).astype(np.float32)
         elif 'lstm' in k or k.startswith('lin.'):

@@ -47,9 +47,9 @@ def extract_defs(path, names, ns):
     return ns
 
 
-def load_synth(model, seed):
+def load_synth(model, seed, decoder_gain=1.0):
     shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
-    sd = orc.synth_state_dict(shapes, seed)
+    sd = orc.synth_state_dict(shapes, seed, decoder_gain)
     model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
     return sd
 
@@ -79,25 +79,27 @@ def main():
                         f_s=blobs[0].numpy())
 
     # ---- model_SP train step (B=4, 32x32): forward, floss, backward, BN buffers ----------------------------------------
-    m = ref_sp.model_SP(make_layers(cfg['D'], 3), make_layers(cfg['D'], 20))
-    load_synth(m, 12)
-    m.train()
-    x_s, x_t, gt = orc.synth_sp_inputs(4, 32, 77)
-    crit = ref_floss.floss()
-    out = m(t(x_s), t(x_t))
-    loss = crit(out, t(gt))
-    loss.backward()
-    rec = dict(seed_w=12, seed_x=77, B=4, S=32, y=out.detach().numpy(), loss=float(loss))
-    for k, v in m.state_dict().items():
-        if "running_" in k:
-            rec["buf/" + k] = v.numpy()
-    for k, p in m.named_parameters():
-        g = p.grad.numpy()
-        rec["gnorm/" + k] = np.float64(np.sqrt((g.astype(np.float64) ** 2).sum()))
-        rec["ghead/" + k] = g.reshape(-1)[:64].copy()
-        if g.size <= 4096:
-            rec["grad/" + k] = g
-    np.savez_compressed(os.path.join(OUT, "sp_train_b4_s32.npz"), **rec)
+    # two regimes: He-init decoder (the reference's own init: saturated, ill-conditioned) and a damped decoder (logits O(1))
+    for tag, seed_w, gain in (("sp_train_b4_s32", 12, 1.0), ("sp_train_wellcond_b4_s32", 17, 0.8)):
+        m = ref_sp.model_SP(make_layers(cfg['D'], 3), make_layers(cfg['D'], 20))
+        load_synth(m, seed_w, gain)
+        m.train()
+        x_s, x_t, gt = orc.synth_sp_inputs(4, 32, 77)
+        crit = ref_floss.floss()
+        out = m(t(x_s), t(x_t))
+        loss = crit(out, t(gt))
+        loss.backward()
+        rec = dict(seed_w=seed_w, seed_x=77, B=4, S=32, decoder_gain=gain, y=out.detach().numpy(), loss=float(loss))
+        for k, v in m.state_dict().items():
+            if "running_" in k:
+                rec["buf/" + k] = v.numpy()
+        for k, p in m.named_parameters():
+            g = p.grad.numpy()
+            rec["gnorm/" + k] = np.float64(np.sqrt((g.astype(np.float64) ** 2).sum()))
+            rec["ghead/" + k] = g.reshape(-1)[:64].copy()
+            if g.size <= 4096:
+                rec["grad/" + k] = g
+        np.savez_compressed(os.path.join(OUT, tag + ".npz"), **rec)
 
     # ---- config 1: run_spatialstream.py plumbing on one synthetic 224x224 frame ---------------------------
     ns = {"__name__": "ref_run_spatialstream"}

@@ -38,6 +38,7 @@ def test_model_sp_eval_vs_reference_golden(cuda_dev):
 
 def test_model_sp_train_forward_vs_reference_golden(cuda_dev):
     g = np.load(os.path.join(GOLD, "sp_train_b4_s32.npz"))
+    assert float(g["decoder_gain"]) == 1.0
     m = make_sp(int(g["seed_w"]), cuda_dev).train()
     x_s, x_t, gt = orc.synth_sp_inputs(int(g["B"]), int(g["S"]), int(g["seed_x"]))
     with torch.no_grad():
