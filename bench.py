@@ -244,7 +244,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default=os.environ.get("EGAZE_BENCH_WORKLOAD", "sp_fwd"))
+    ap.add_argument("--workload", default=os.environ.get("EGAZE_BENCH_WORKLOAD", "sp_train"))
     ap.add_argument("--impl", default="egaze")
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--size", type=int, default=224)
@@ -335,7 +335,7 @@ def main():
         "e2e": {"value": frames / ms_e2e * 1e3, "unit": UNIT, "h2d_bytes_per_step": wl.h2d_bytes,
                 "d2h_bytes_per_step": wl.d2h_bytes},
         "gpu_launches": launches * K,
-        "roofline": {"bound": "tensor", "kernel": "conv3x3_tc_kernel (all 3x3 conv launches of the step)",
+        "roofline": {"bound": "tensor", "kernel": "tcgen05 conv kernels (conv3x3_tc fprop/dgrad + wgrad_tc launches of the step)",
                      "achieved": conv_tflops, "peak": peak_tf, "unit": "TFLOP/s", "frac": conv_tflops / peak_tf,
                      "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step)" % peak_src,
                      "launches_per_step": conv_launches / max(K, 1), "kernel_ms_per_step": conv_ms / max(K, 1),

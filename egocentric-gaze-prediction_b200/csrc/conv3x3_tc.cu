@@ -226,23 +226,52 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     ptx::tc_fence_before();
     ptx::named_bar_sync(1, kEpiThreads);
 
-    // -- phase 2: per-tile BatchNorm statistics (mean, M2 over the tile's valid pixels), one column per thread
+    // -- phase 2: per-tile BatchNorm statistics (mean, M2 over the tile's valid pixels).  Two threads per column
+    //    when BN <= 64 (row halves combined with Chan's formula), one otherwise; no per-row index arithmetic.
     if (p.stats) {
-      int cnt = 0;
-      for (int mm = 0; mm < p.BH * p.BW; ++mm) cnt += row_valid(p, mm, h0, w0) ? 1 : 0;
-      for (int c = et; c < p.BN; c += kEpiThreads) {
+      const int vh = min(p.BH, p.H - h0), vw = min(p.BW, p.W - w0);   // valid extent of this tile
+      const int cnt = vh * vw;
+      const int halves = (p.BN <= 64) ? 2 : 1;
+      float* red = stage + (size_t)128 * ldst;                        // scratch behind the staging tile
+      for (int cbase = 0; cbase < p.BN; cbase += kEpiThreads / halves) {
+        const int c = cbase + (et % (kEpiThreads / halves));
+        const int half = et / (kEpiThreads / halves);
+        const int r0 = halves == 2 ? (half == 0 ? 0 : vh / 2) : 0;
+        const int r1 = halves == 2 ? (half == 0 ? vh / 2 : vh) : vh;
+        const int n_loc = (r1 - r0) * vw;
         float sum = 0.f;
-        for (int mm = 0; mm < p.BH * p.BW; ++mm)
-          if (row_valid(p, mm, h0, w0)) sum += stage[(size_t)mm * ldst + c];
-        const float mean = sum / (float)cnt;
-        float m2 = 0.f;
-        for (int mm = 0; mm < p.BH * p.BW; ++mm)
-          if (row_valid(p, mm, h0, w0)) {
-            const float d = stage[(size_t)mm * ldst + c] - mean;
-            m2 = fmaf(d, d, m2);
+        if (c < p.BN)
+          for (int th = r0; th < r1; ++th) {
+            const float* rowp = stage + (size_t)(th * p.BW) * ldst + c;
+            for (int tw = 0; tw < vw; ++tw) sum += rowp[(size_t)tw * ldst];
           }
-        p.stats[((size_t)tile_linear * 2 + 0) * p.Cout + n0 + c] = mean;
-        p.stats[((size_t)tile_linear * 2 + 1) * p.Cout + n0 + c] = m2;
+        const float mean = n_loc > 0 ? sum / (float)n_loc : 0.f;
+        float m2 = 0.f;
+        if (c < p.BN)
+          for (int th = r0; th < r1; ++th) {
+            const float* rowp = stage + (size_t)(th * p.BW) * ldst + c;
+            for (int tw = 0; tw < vw; ++tw) {
+              const float d = rowp[(size_t)tw * ldst] - mean;
+              m2 = fmaf(d, d, m2);
+            }
+          }
+        if (halves == 2) {
+          if (half == 1 && c < p.BN) { red[c * 3 + 0] = mean; red[c * 3 + 1] = m2; red[c * 3 + 2] = (float)n_loc; }
+          ptx::named_bar_sync(2, kEpiThreads);
+          if (half == 0 && c < p.BN) {
+            const float nb = red[c * 3 + 2], mb = red[c * 3 + 0], m2b = red[c * 3 + 1];
+            const float na = (float)n_loc, nn = na + nb;
+            const float d = mb - mean;
+            const float mean_t = nn > 0.f ? mean + d * nb / nn : 0.f;
+            const float m2_t = m2 + m2b + (nn > 0.f ? d * d * na * nb / nn : 0.f);
+            p.stats[((size_t)tile_linear * 2 + 0) * p.Cout + n0 + c] = mean_t;
+            p.stats[((size_t)tile_linear * 2 + 1) * p.Cout + n0 + c] = m2_t;
+          }
+          ptx::named_bar_sync(2, kEpiThreads);
+        } else if (c < p.BN) {
+          p.stats[((size_t)tile_linear * 2 + 0) * p.Cout + n0 + c] = mean;
+          p.stats[((size_t)tile_linear * 2 + 1) * p.Cout + n0 + c] = m2;
+        }
       }
       if (et == 0 && nt == 0) p.stats_cnt[tile_linear] = (float)cnt;
     }
@@ -379,7 +408,7 @@ extern "C" int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* 
   EGAZE_CHECK_ARG(sb >= 2, "conv3x3_tc: tile does not fit shared memory");
   p.SB = sb;
   size_t smem = (size_t)p.SA * p.nsplit * p.a_slot_bytes + (size_t)p.SB * p.nsplit * p.b_slot_bytes;
-  const size_t stage_bytes = (size_t)128 * (p.BN + 4) * 4;
+  const size_t stage_bytes = (size_t)128 * (p.BN + 4) * 4 + 3 * 64 * 4;
   if (smem < stage_bytes) smem = stage_bytes;
   smem += 1024;  // alignment slack
   p.bias = bias; p.scale = scale; p.shift = shift; p.relu = relu; p.reduce = reduce; p.ups = ups;

@@ -166,7 +166,13 @@ def conv_timer_read():
     """-> (total ms, number of launches) since the last reset."""
     torch.cuda.synchronize()
     ev = _conv_timer["events"]
-    return sum(a.elapsed_time(b) for a, b in ev), len(ev)
+    return sum(e[0].elapsed_time(e[1]) for e in ev), len(ev)
+
+
+def conv_timer_table():
+    """-> [(description, ms)] per timed launch since the last reset."""
+    torch.cuda.synchronize()
+    return [(e[2], e[0].elapsed_time(e[1])) for e in _conv_timer["events"]]
 
 
 def conv_tiles(N, H, W, need_even=False):
@@ -205,7 +211,7 @@ def conv3x3(act, wpack, bias=None, scale=None, shift=None, relu=False, reduce=0,
          st[0] if st else None, st[1] if st else None, int(precise), stream_ptr())
     if _conv_timer["on"]:
         ev1.record()
-        _conv_timer["events"].append((ev0, ev1))
+        _conv_timer["events"].append((ev0, ev1, ("conv", N, H, W, Cin_p, Cout, int(reduce), int(ups), bool(stats))))
     return out_act, out_f32, st
 
 
@@ -291,8 +297,14 @@ def wgrad3x3(x_act, dy_act, Cout, Cin, precise=None):
     N, H, W = x_act.N, x_act.H, x_act.W
     dev = x_act.hi.device
     dwp = torch.zeros((9, dy_act.Cp, x_act.Cp), dtype=F32, device=dev)
+    if _conv_timer["on"]:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     call("egaze_wgrad3x3_tc", x_act.hi, x_act.lo if precise else None, dy_act.hi, dy_act.lo if precise else None, N, H, W,
          x_act.Cp, dy_act.Cp, dwp, int(precise), stream_ptr())
+    if _conv_timer["on"]:
+        ev1.record()
+        _conv_timer["events"].append((ev0, ev1, ("wgrad", N, H, W, x_act.Cp, dy_act.Cp, 0, 0, False)))
     gw = torch.empty((Cout, Cin, 3, 3), dtype=F32, device=dev)
     if dy_act.Cp != Cout:
         dwp = dwp[:, :Cout].contiguous()
