@@ -44,6 +44,7 @@ struct ConvTcParams {
   int tile_groups;     // ceil(total_tiles / CS)
   int num_items;       // tile_groups * tiles_n
   int nsplit;          // 1 = single bf16 pass, 2 = hi/lo split (3 MMAs per product)
+  int merged;          // precise mode: A_hi x [B_hi | B_lo] as ONE MMA of N = 2*BN (the two halves are summed in the epilogue)
   int SA, SB;          // ring depths
   int a_slot_bytes;    // bytes of one A plane slot (1024-aligned)
   int b_slot_bytes;    // bytes of one B plane slot
@@ -118,7 +119,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     ptx::prefetch_tmap(&tmB_hi);
     if (NSPLIT == 2) { ptx::prefetch_tmap(&tmA_lo); ptx::prefetch_tmap(&tmB_lo); }
   }
-  const uint32_t acc_cols = p.BN < 32 ? 32u : (uint32_t)p.BN;   // columns of one accumulator stage
+  const uint32_t acc_cols = p.merged ? 2u * (uint32_t)p.BN : (p.BN < 32 ? 32u : (uint32_t)p.BN);   // columns of one accumulator stage
   const uint32_t tmem_cols = 2 * acc_cols;                       // power of two in [64, 512]
   if (warp == 1) {
     ptx::tmem_alloc(&tmem_base_smem, tmem_cols);
@@ -175,6 +176,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     // ================================ MMA issuer ================================
     if (lane == 0) {
       const uint32_t idesc = ptx::make_idesc_bf16(128, p.BN, 0, 0);
+      const uint32_t idesc2 = ptx::make_idesc_bf16(128, 2 * p.BN, 0, 0);
       const uint32_t sbo = 8u * (uint32_t)row_bytes;
       // Descriptors differ only in their 14-bit start-address field (smem address >> 4; smem < 256 KB so the
       // field never carries): build the static part once, then a descriptor is one 64-bit add.
@@ -203,17 +205,28 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
               ptx::tc_fence_after();
               const uint64_t ad = a_desc0 + (uint64_t)((uint32_t)r * r_step16);
               const uint64_t bd = b_ring_desc + (uint64_t)((uint32_t)sb * b_slot16);
-              // products: (hi,hi) [, (hi,lo), (lo,hi)]
+              // products: (hi,hi) [, (hi,lo), (lo,hi)].  merged: the hi and lo weight planes are contiguous in the slot, so
+              // A_hi x [B_hi | B_lo] is ONE MMA of N = 2*BN (A_hi is read from smem once instead of twice -- the MMA is
+              // shared-memory-read bound at N <= 128); its two column halves are added in the epilogue.
+              if (NSPLIT == 2 && p.merged) {
 #pragma unroll
-              for (int k = 0; k < KSTEPS; ++k) {
-                ptx::umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, accumulate);
-                accumulate = 1;
-              }
-              if (NSPLIT == 2) {
+                for (int k = 0; k < KSTEPS; ++k) {
+                  ptx::umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc2, accumulate);
+                  ptx::umma_bf16(d_tmem, ad + a_plane16 + 2 * k, bd + 2 * k, idesc, 1);
+                  accumulate = 1;
+                }
+              } else {
 #pragma unroll
-                for (int k = 0; k < KSTEPS; ++k) ptx::umma_bf16(d_tmem, ad + 2 * k, bd + b_plane16 + 2 * k, idesc, 1);
+                for (int k = 0; k < KSTEPS; ++k) {
+                  ptx::umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, accumulate);
+                  accumulate = 1;
+                }
+                if (NSPLIT == 2) {
 #pragma unroll
-                for (int k = 0; k < KSTEPS; ++k) ptx::umma_bf16(d_tmem, ad + a_plane16 + 2 * k, bd + 2 * k, idesc, 1);
+                  for (int k = 0; k < KSTEPS; ++k) ptx::umma_bf16(d_tmem, ad + 2 * k, bd + b_plane16 + 2 * k, idesc, 1);
+#pragma unroll
+                  for (int k = 0; k < KSTEPS; ++k) ptx::umma_bf16(d_tmem, ad + a_plane16 + 2 * k, bd + 2 * k, idesc, 1);
+                }
               }
               if (CS > 1) ptx::umma_commit_mc(&b_empty[sb], kMask);
               else ptx::umma_commit(&b_empty[sb]);
@@ -266,7 +279,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         for (int c0 = colsel * 32; c0 < CW; c0 += 64) {
           uint32_t v[32];
           ptx::tmem_ld_32x32(t_acc + (uint32_t)(cc + c0), v);
-          ptx::tmem_ld_wait();
+          if (p.merged) {
+            uint32_t v2[32];
+            ptx::tmem_ld_32x32(t_acc + (uint32_t)(p.BN + cc + c0), v2);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+          } else {
+            ptx::tmem_ld_wait();
+          }
           float* dst = stage + (size_t)m * ldst + c0;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -492,12 +513,25 @@ extern "C" int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* 
   p.b_slot_bytes = ((p.BN * row_bytes + 1023) / 1024) * 1024;
   const int CW = p.BN < 64 ? p.BN : 64;
   const int stage_bytes = ((128 * (CW + 4) * 4 + 4 * 64 * 3 * 4 + 1023) / 1024) * 1024;
+  static int sa_env = -1;
+  if (sa_env < 0) {
+    const char* e = getenv("EGAZE_CONV_SA");
+    sa_env = e ? atoi(e) : 0;
+  }
   p.SA = 2;
   const int budget = 222 * 1024 - stage_bytes;
+  if (sa_env >= 2 && sa_env <= kMaxSA && (budget - sa_env * p.nsplit * p.a_slot_bytes) / (p.nsplit * p.b_slot_bytes) >= 3)
+    p.SA = sa_env;
   int sb = (budget - p.SA * p.nsplit * p.a_slot_bytes) / (p.nsplit * p.b_slot_bytes);
   if (sb > 6) sb = 6;
   EGAZE_CHECK_ARG(sb >= 2, "conv3x3_tc: tile does not fit shared memory");
   p.SB = sb;
+  // merged hi|lo weight MMA needs the two planes back to back (no slot padding) and 2*BN accumulator columns x 2 stages
+  p.merged = (precise && p.b_slot_bytes == p.BN * row_bytes && 4 * p.BN <= 512 && 2 * p.BN <= 256) ? 1 : 0;
+  {
+    const char* e = getenv("EGAZE_CONV_MERGED");
+    if (e && atoi(e) == 0) p.merged = 0;
+  }
   p.stage_off = p.SA * p.nsplit * p.a_slot_bytes + p.SB * p.nsplit * p.b_slot_bytes;
   const size_t smem = (size_t)p.stage_off + stage_bytes + 1024;  // + alignment slack
   p.bias = bias; p.scale = scale; p.shift = shift; p.relu = relu; p.reduce = reduce; p.ups = ups;

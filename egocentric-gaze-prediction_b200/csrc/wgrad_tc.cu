@@ -57,7 +57,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid_constan
     ptx::prefetch_tmap(&tmY_hi);
     ptx::prefetch_tmap(&tmX_hi);
   }
-  constexpr uint32_t kTmemCols = 256;  // 3 accumulators x 64 columns, rounded to a power of two
+  // precise: A_hi x [X_hi | X_lo] is ONE MMA of N = 128 (the X planes are 64-channel chunks LBO = plane stride apart),
+  // so each tap owns 128 accumulator columns whose halves are added in the epilogue; fast: 64 columns per tap.
+  constexpr uint32_t kAccCols = NSPLIT == 2 ? 128 : 64;
+  constexpr uint32_t kTmemCols = NSPLIT == 2 ? 512 : 256;
   if (warp == 1) {
     ptx::tmem_alloc(&tmem_base_smem, kTmemCols);
     ptx::tmem_relinquish();
@@ -97,11 +100,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid_constan
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = ptx::make_idesc_bf16(128, 64, 1, 1);  // both operands MN-major
+      const uint32_t idesc = ptx::make_idesc_bf16(128, 64, 1, 1);    // both operands MN-major
+      const uint32_t idesc2 = ptx::make_idesc_bf16(128, 128, 1, 1);  // N = [X_hi | X_lo]
       // MN-major SWIZZLE_128B canonical layout: 64 channels (128 B) contiguous, 8 pixel rows per 1024 B atom (SBO),
       // next 64-channel chunk LBO bytes away.
       const uint64_t a_static = ptx::make_smem_desc(0, dy_box_bytes, 1024, 128);
-      const uint64_t b_static = ptx::make_smem_desc(0, x_box_bytes, 1024, 128);
+      const uint64_t b_static = ptx::make_smem_desc(0, NSPLIT == 2 ? (uint32_t)p.x_plane_bytes : x_box_bytes, 1024, 128);
       const int ksteps = KP / 16;
       int st = 0;
       uint32_t par = 0;
@@ -113,20 +117,20 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid_constan
         const uint64_t a_hi = a_static + (uint64_t)(base >> 4);
         const uint64_t a_lo = a_hi + (uint64_t)((uint32_t)p.dy_plane_bytes >> 4);
         const uint64_t b_hi = b_static + (uint64_t)((base + (uint32_t)NSPLIT * p.dy_plane_bytes) >> 4);
-        const uint64_t b_lo = b_hi + (uint64_t)((uint32_t)p.x_plane_bytes >> 4);
         const uint32_t r_step16 = (uint32_t)(p.BW * 128) >> 4;
 #pragma unroll 1
         for (int r = 0; r < 3; ++r) {
-          const uint32_t d = tmem_base + (uint32_t)(r * 64);
-          const uint64_t br_hi = b_hi + (uint64_t)(r * r_step16), br_lo = b_lo + (uint64_t)(r * r_step16);
+          const uint32_t d = tmem_base + (uint32_t)r * kAccCols;
+          const uint64_t br_hi = b_hi + (uint64_t)(r * r_step16);
           for (int k = 0; k < ksteps; ++k) {  // 16 pixel rows = 2048 B per K step
             const uint64_t ko = (uint64_t)(k * 128);
-            ptx::umma_bf16(d, a_hi + ko, br_hi + ko, idesc, acc[r]);
-            acc[r] = 1;
             if (NSPLIT == 2) {
-              ptx::umma_bf16(d, a_hi + ko, br_lo + ko, idesc, 1);
-              ptx::umma_bf16(d, a_lo + ko, br_hi + ko, idesc, 1);
+              ptx::umma_bf16(d, a_hi + ko, br_hi + ko, idesc2, acc[r]);   // dY_hi x [X_hi | X_lo]
+              ptx::umma_bf16(d, a_lo + ko, br_hi + ko, idesc, 1);         // dY_lo x X_hi
+            } else {
+              ptx::umma_bf16(d, a_hi + ko, br_hi + ko, idesc, acc[r]);
             }
+            acc[r] = 1;
           }
         }
         ptx::umma_commit(&empty[st]);
@@ -145,8 +149,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid_constan
 #pragma unroll 1
       for (int c0 = 0; c0 < 64; c0 += 32) {
         uint32_t v[32];
-        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(r * 64 + c0), v);
-        ptx::tmem_ld_wait();
+        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(r * kAccCols + c0), v);
+        if (NSPLIT == 2) {
+          uint32_t v2[32];
+          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(r * kAccCols + 64 + c0), v2);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+        } else {
+          ptx::tmem_ld_wait();
+        }
         if (any_tile && co0 + m < p.Cout) {
           float* dst = p.dwp + ((size_t)(r * 3 + s) * p.Cout + co0 + m) * p.Cin_p + ci0 + c0;
 #pragma unroll
@@ -223,10 +235,27 @@ extern "C" int egaze_wgrad3x3_tc(const void* x_hi, const void* x_lo, const void*
     rc = egaze_encode_tmap(&tmX_lo, precise ? x_lo : x_hi, 4, dims, str, box, 128, 2);
     if (rc) return rc;
   }
+  // split-K factor: one CTA per SM is resident (208 KB of smem), so pick the factor that fills whole waves of SMs best
   const int jobs = p.co_tiles * p.ci_tiles * 3;
-  int ksplit = (148 * 2 + jobs - 1) / jobs;
-  if (ksplit > p.total_tiles) ksplit = p.total_tiles;
-  if (ksplit < 1) ksplit = 1;
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    EGAZE_CUDA(cudaGetDevice(&dev));
+    EGAZE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  int ksplit = 1;
+  double best_util = -1.0;
+  const int kmax = p.total_tiles < 4 * sms ? p.total_tiles : 4 * sms;
+  for (int k = 1; k <= kmax; ++k) {
+    const long long ctas = (long long)jobs * k;
+    if (ctas > 8LL * sms) break;
+    const long long waves = (ctas + sms - 1) / sms;
+    const int tiles_per_cta = (p.total_tiles + k - 1) / k;
+    // time ~ waves * tiles_per_cta (+ a fixed per-CTA prologue/epilogue worth ~6 tiles)
+    const double cost = (double)waves * (tiles_per_cta + 6);
+    const double util = 1.0 / cost;
+    if (util > best_util * 1.0001) { best_util = util; ksplit = k; }
+  }
   dim3 grid((unsigned)ksplit, (unsigned)jobs);
   if (precise) {
     static bool attr = false;

@@ -153,6 +153,8 @@ def test_model_sp_frozen_trunks(cuda_dev):
     for (k, p), (_, q) in zip(m.named_parameters(), m_ref.named_parameters()):
         if k.startswith("features"):
             assert p.grad is None
+        elif q.grad.norm().item() < 1e-6:   # fusion.bias feeds a batch-stat BatchNorm: exactly zero up to rounding noise
+            assert p.grad.norm().item() < 1e-4, k
         else:
             assert rel_l2(p.grad, q.grad) <= 5e-2, k
 
