@@ -145,7 +145,7 @@ class Workload(object):
             if self.flat is not None:
                 self.flat.zero_()
             else:
-                self.opt.zero_grad(set_to_none=False)
+                self.opt.zero_grad(set_to_none=True)
             out = self.model(x_s, x_t)
             loss = self.crit(out, gt.view(out.size()))
             loss.backward()

@@ -13,7 +13,8 @@ namespace {
 
 // partial: [T][2][C] (mean, M2), cnt: [T].  One thread column per channel, 32 slices of tiles per block.
 __global__ void __launch_bounds__(1024)
-bn_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ cnt, int T, int C, float eps,
+bn_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ cnt, int cnt_stride, int cnt_div,
+                   int T, int C, float eps,
                    float momentum, const float* __restrict__ gamma, const float* __restrict__ beta,
                    float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ mean_out,
                    float* __restrict__ invstd_out, float* __restrict__ scale_out, float* __restrict__ shift_out) {
@@ -24,7 +25,8 @@ bn_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ 
   double n = 0.0, sm = 0.0;
   if (c < C)
     for (int t = sl; t < T; t += 32) {
-      const double nb = (double)cnt[t];
+      const double nb = (double)cnt[(size_t)t * cnt_stride + c / cnt_div];
+      if (nb <= 0.0) continue;   // unused partial slot: its (mean, M2) are uninitialised
       n += nb;
       sm = fma(nb, (double)partial[((size_t)t * 2 + 0) * C + c], sm);
     }
@@ -39,8 +41,10 @@ bn_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ 
   double m2 = 0.0;
   if (c < C)
     for (int t = sl; t < T; t += 32) {
+      const double nb = (double)cnt[(size_t)t * cnt_stride + c / cnt_div];
+      if (nb <= 0.0) continue;
       const double d = (double)partial[((size_t)t * 2 + 0) * C + c] - mean;
-      m2 += (double)partial[((size_t)t * 2 + 1) * C + c] + (double)cnt[t] * d * d;
+      m2 += (double)partial[((size_t)t * 2 + 1) * C + c] + nb * d * d;
     }
   s_a[sl][threadIdx.x] = m2;
   __syncthreads();
@@ -349,12 +353,13 @@ __global__ void col_sum_split_kernel(const __nv_bfloat16* __restrict__ hi, const
 
 }  // namespace
 
-extern "C" int egaze_bn_finalize(const float* partial, const float* cnt, int T, int C, float eps, float momentum,
+extern "C" int egaze_bn_finalize(const float* partial, const float* cnt, int cnt_stride, int cnt_div, int T, int C,
+                                 float eps, float momentum,
                                  const float* gamma, const float* beta, float* running_mean, float* running_var,
                                  float* mean_out, float* invstd_out, float* scale_out, float* shift_out, void* stream) {
-  EGAZE_CHECK_ARG(partial && cnt && T > 0 && C > 0, "bn_finalize: bad args");
+  EGAZE_CHECK_ARG(partial && cnt && T > 0 && C > 0 && cnt_stride > 0 && cnt_div > 0, "bn_finalize: bad args");
   dim3 block(32, 32), grid(ceil_div(C, 32));
-  bn_finalize_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(partial, cnt, T, C, eps, momentum, gamma, beta,
+  bn_finalize_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(partial, cnt, cnt_stride, cnt_div, T, C, eps, momentum, gamma, beta,
                                                                running_mean, running_var, mean_out, invstd_out,
                                                                scale_out, shift_out);
   EGAZE_LAUNCH_CHECK();
@@ -413,7 +418,7 @@ static void bn_bwd_block(int C, dim3* block) {
 
 // partial: [nblk][2][C] with nblk = egaze_bn_bwd_blocks(); dgamma/dbeta: [C]
 extern "C" int egaze_bn_bwd_blocks(int* nblk) {
-  *nblk = 148 * 4;
+  *nblk = 148 * 8;
   return EGAZE_OK;
 }
 
@@ -424,7 +429,7 @@ extern "C" int egaze_bn_bwd_reduce(const float* raw, const float* g, int N, int 
   EGAZE_CHECK_ARG(C % 4 == 0 && C <= 4096, "bn_bwd_reduce: unsupported C=%d", C);
   dim3 block;
   bn_bwd_block(C, &block);
-  const int nblk = 148 * 4;
+  const int nblk = 148 * 8;
   const size_t smem = (size_t)block.y * 2 * C * sizeof(float);
   bn_bwd_reduce_kernel<<<nblk, block, smem, (cudaStream_t)stream>>>(raw, g, N, H, W, C, scale, shift, mean, invstd, pool,
                                                                     relu, partial);

@@ -61,8 +61,8 @@ struct ConvTcParams {
   float* out_f32;             // optional NHWC fp32 [N,Ho*,Wo*,Cout]
   __nv_bfloat16* out_hi;      // optional NHWC bf16
   __nv_bfloat16* out_lo;      // optional (precise) NHWC bf16
-  float* stats;               // optional [num_tiles][2][Cout] per-tile (mean, M2) of the pre-activation
-  float* stats_cnt;           // [num_tiles] valid-pixel count of each tile
+  float* stats;               // optional [gridDim][2][Cout] per-CTA (mean, M2) of the pre-activation (acc + bias)
+  float* stats_cnt;           // [gridDim][tiles_n] pixel count behind each per-CTA partial
 };
 
 struct Item {
@@ -251,6 +251,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     const int CW = p.BN < 64 ? p.BN : 64;    // staged column chunk (power of two)
     const int ldst = CW + 4;                 // padded staging row (floats)
     float* red = stage + (size_t)128 * ldst; // [4][64][3] floats of scratch
+    float* run_stats = red + 4 * 64 * 3;     // [Cout][3] running (n, mean, M2) of this CTA (BatchNorm statistics)
+    if (p.stats) {
+      for (int i = et; i < p.Cout * 3; i += kEpiThreads) run_stats[i] = 0.f;
+      ptx::named_bar_sync(1, kEpiThreads);
+    }
     const int gpp = CW >> 2;                 // float4 channel groups per pixel (power of two)
     const int gpp_log = 31 - __clz(gpp);
     const int g = et & (gpp - 1);            // this thread's channel group ...
@@ -332,7 +337,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
             }
             ptx::named_bar_sync(2, kEpiThreads);
             if (q == 0 && c < CW) {
-              float na = 0.f, ma = 0.f, m2a = 0.f;
+              // merge the four row quarters, then fold the tile into this CTA's running (n, mean, M2) of the column
+              float* run = run_stats + (size_t)(it.nt * p.BN + cc + c) * 3;
+              float na = run[0], ma = run[1], m2a = run[2];
 #pragma unroll
               for (int qq = 0; qq < 4; ++qq) {
                 const float* rp = red + (size_t)(qq * 64 + c) * 3;
@@ -344,11 +351,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                   na = nn;
                 }
               }
-              if (p.bias) ma += __ldg(p.bias + n0 + c);
-              p.stats[((size_t)it.tile * 2 + 0) * p.Cout + n0 + c] = ma;
-              p.stats[((size_t)it.tile * 2 + 1) * p.Cout + n0 + c] = m2a;
+              run[0] = na; run[1] = ma; run[2] = m2a;
             }
-            if (et == 0 && it.nt == 0 && cc == 0) p.stats_cnt[it.tile] = (float)(vh * vw);
           }
 
           // -- phase 3: (+bias, *scale+shift, relu) -> 2x2 max/sum -> mask -> coalesced NHWC stores.
@@ -430,6 +434,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
       }
       as ^= 1;
     }
+    if (p.stats) {
+      // one (mean, M2, n) partial per CTA and channel; bias shifts the mean only
+      for (int c = et; c < p.Cout; c += kEpiThreads) {
+        const float* run = run_stats + (size_t)c * 3;
+        p.stats[((size_t)blockIdx.x * 2 + 0) * p.Cout + c] = run[1] + (p.bias ? __ldg(p.bias + c) : 0.f);
+        p.stats[((size_t)blockIdx.x * 2 + 1) * p.Cout + c] = run[2];
+        if (c % p.BN == 0) p.stats_cnt[(size_t)blockIdx.x * p.tiles_n + c / p.BN] = run[0];
+      }
+    }
   }
 
   __syncthreads();
@@ -460,6 +473,27 @@ extern "C" int egaze_conv3x3_tiles(int N, int H, int W, int need_even, int* num_
   if (num_tiles) *num_tiles = N * ceil_div(H, BH) * ceil_div(W, BW);
   if (BH_out) *BH_out = BH;
   if (BW_out) *BW_out = BW;
+  return EGAZE_OK;
+}
+
+static int conv_pick_bn(int Cout, int precise) {
+  int bn = 16;
+  for (int b : {32, 64, 128}) if (Cout % b == 0) bn = b;
+  if (!precise && Cout % 256 == 0) bn = 256;
+  return bn;
+}
+
+// Shape of the BatchNorm-statistics workspace of egaze_conv3x3_tc (one partial per persistent CTA):
+//   stats [partials][2][Cout], stats_cnt [partials][cnt_stride] (ZERO-initialised by the caller: unused CTAs count 0);
+//   the count behind channel c of partial t is stats_cnt[t*cnt_stride + c/cnt_div].
+extern "C" int egaze_conv3x3_stats_shape(int Cout, int precise, int* partials, int* cnt_stride, int* cnt_div) {
+  int dev = 0, sms = 0;
+  EGAZE_CUDA(cudaGetDevice(&dev));
+  EGAZE_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int bn = conv_pick_bn(Cout, precise);
+  *partials = sms;
+  *cnt_stride = Cout / bn;
+  *cnt_div = bn;
   return EGAZE_OK;
 }
 
@@ -496,9 +530,7 @@ extern "C" int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* 
   pick_tile(H, W, reduce != 0, &p.BH, &p.BW);
   p.nsplit = precise ? 2 : 1;
   // N tile: largest of 128/64/32/16 dividing Cout (256 only in fast mode where the rings fit).
-  p.BN = 16;
-  for (int bn : {32, 64, 128}) if (Cout % bn == 0) p.BN = bn;
-  if (!precise && Cout % 256 == 0) p.BN = 256;
+  p.BN = conv_pick_bn(Cout, precise);
   p.tiles_h = ceil_div(H, p.BH); p.tiles_w = ceil_div(W, p.BW); p.tiles_n = Cout / p.BN;
   p.total_tiles = N * p.tiles_h * p.tiles_w;
   // clusters of 2 share every weight box through TMA multicast; the split needs 8-row-aligned halves
@@ -512,7 +544,7 @@ extern "C" int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* 
   p.a_slot_bytes = ((a_rows * row_bytes + 1023) / 1024) * 1024;
   p.b_slot_bytes = ((p.BN * row_bytes + 1023) / 1024) * 1024;
   const int CW = p.BN < 64 ? p.BN : 64;
-  const int stage_bytes = ((128 * (CW + 4) * 4 + 4 * 64 * 3 * 4 + 1023) / 1024) * 1024;
+  const int stage_bytes = ((128 * (CW + 4) * 4 + 4 * 64 * 3 * 4 + (stats ? Cout * 3 * 4 : 0) + 1023) / 1024) * 1024;
   static int sa_env = -1;
   if (sa_env < 0) {
     const char* e = getenv("EGAZE_CONV_SA");

@@ -189,6 +189,18 @@ def conv_tiles(N, H, W, need_even=False):
     return nt.value, bh.value, bw.value
 
 
+_stats_shape_cache = {}
+
+
+def conv_stats_shape(Cout, precise):
+    key = (Cout, bool(precise))
+    if key not in _stats_shape_cache:
+        a, b, c = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+        call("egaze_conv3x3_stats_shape", Cout, int(precise), ctypes.addressof(a), ctypes.addressof(b), ctypes.addressof(c))
+        _stats_shape_cache[key] = (a.value, b.value, c.value)
+    return _stats_shape_cache[key]
+
+
 def conv3x3(act, wpack, bias=None, scale=None, shift=None, relu=False, reduce=0, ups=False, mask=None,
             want_f32=False, want_split=True, stats=False, precise=None, mask_ups=False):
     """3x3/pad-1 conv on the tcgen05 path.  wpack = (w_hi, w_lo, Cout_p, Cin_p) from pack_cache.
@@ -206,8 +218,8 @@ def conv3x3(act, wpack, bias=None, scale=None, shift=None, relu=False, reduce=0,
     out_f32 = torch.empty((N, Ho, Wo, Cout), dtype=F32, device=dev) if want_f32 else None
     st = None
     if stats:
-        nt, _, _ = conv_tiles(N, H, W, bool(reduce))
-        st = (torch.empty((nt, 2, Cout), dtype=F32, device=dev), torch.empty((nt,), dtype=F32, device=dev))
+        parts, cs, cd = conv_stats_shape(Cout, precise)
+        st = (torch.empty((parts, 2, Cout), dtype=F32, device=dev), torch.zeros((parts, cs), dtype=F32, device=dev), cs, cd)
     if _conv_timer["on"]:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
@@ -223,13 +235,13 @@ def conv3x3(act, wpack, bias=None, scale=None, shift=None, relu=False, reduce=0,
 
 def bn_finalize(st, C, eps, momentum, gamma, beta, running_mean, running_var):
     """-> (mean, invstd, scale, shift); updates running stats in place when given."""
-    partial, cnt = st
+    partial, cnt, cnt_stride, cnt_div = st
     dev = partial.device
     mean = torch.empty((C,), dtype=F32, device=dev)
     invstd = torch.empty((C,), dtype=F32, device=dev)
     scale = torch.empty((C,), dtype=F32, device=dev)
     shift = torch.empty((C,), dtype=F32, device=dev)
-    call("egaze_bn_finalize", partial, cnt, partial.shape[0], C, float(eps), float(momentum), gamma, beta, running_mean,
+    call("egaze_bn_finalize", partial, cnt, cnt_stride, cnt_div, partial.shape[0], C, float(eps), float(momentum), gamma, beta, running_mean,
          running_var, mean, invstd, scale, shift, stream_ptr())
     return mean, invstd, scale, shift
 
@@ -248,7 +260,7 @@ def col_stats(x2d):
     partial = torch.empty((nb, 2, C), dtype=F32, device=x2d.device)
     cnt = torch.empty((nb,), dtype=F32, device=x2d.device)
     call("egaze_col_stats", x2d, rows, C, partial, cnt, stream_ptr())
-    return partial, cnt
+    return partial, cnt, 1, C
 
 
 def bn_apply(x_nhwc, scale, shift, relu=True, pool=False, want_f32=False, want_split=True):

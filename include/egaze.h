@@ -44,12 +44,15 @@ int egaze_unpack_wgrad(const float* dwp, int Cout, int Cin, int Cin_p, float bet
 /* ---- 3x3 convolution, tcgen05 implicit GEMM (replaces nn.Conv2d(k=3,p=1): utils.py:70, model_SP.py:10,13-30) - */
 /* Tile geometry the kernel will use for an (N,H,W) map; num_tiles sizes the BN-statistics workspace. */
 int egaze_conv3x3_tiles(int N, int H, int W, int need_even, int* num_tiles, int* BH, int* BW);
+/* BatchNorm-statistics workspace of egaze_conv3x3_tc: stats [partials][2][Cout], stats_cnt [partials][cnt_stride] (zeroed by
+ * the caller); one (mean, M2, n) partial per persistent CTA. */
+int egaze_conv3x3_stats_shape(int Cout, int precise, int* partials, int* cnt_stride, int* cnt_div);
 /* y = epilogue(conv3x3(x, w)):  v = acc + bias; v = v*scale + shift; relu; 2x2 reduce (1 max = MaxPool2d utils.py:68,
  * 2 sum = grad of nn.Upsample); mask (zero where mask <= 0: ReLU backward; mask_ups: the mask tensor is stored 2x upsampled);
  * 2x nearest replicate (ups: model_SP.py:16,20,24,27).
  *   x_hi/x_lo : [N][H][W][Cin_p] bf16        w_hi/w_lo : [9][Cout][Cin_p] bf16 (egaze_pack_w3x3)
  *   out_f32 / out_hi / out_lo : NHWC [N][Ho][Wo][Cout] (any non-NULL subset is written)
- *   stats [num_tiles][2][Cout], stats_cnt [num_tiles] : per-tile (mean, M2) of v BEFORE relu, for BatchNorm batch statistics
+ *   stats / stats_cnt : per-CTA (mean, M2, n) partials of (acc + bias) for BatchNorm batch statistics (egaze_conv3x3_stats_shape)
  *   precise != 0 : hi*hi + hi*lo + lo*hi (3 MMAs), needs x_lo and w_lo;  0 : single bf16 pass. */
 int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, int N, int H, int W,
                      int Cin_p, int Cout, const float* bias, const float* scale, const float* shift, int relu,
@@ -61,8 +64,9 @@ int egaze_wgrad3x3_tc(const void* x_hi, const void* x_lo, const void* dy_hi, con
                       int Cin_p, int Cout, float* dwp, int precise, void* stream);
 
 /* ---- BatchNorm2d pieces (utils.py:72, model_SP.py:12, late_fusion.py:10-12) ---------------------------------- */
-int egaze_bn_finalize(const float* partial, const float* cnt, int T, int C, float eps, float momentum,
-                      const float* gamma, const float* beta, float* running_mean, float* running_var, float* mean_out,
+/* partial [T][2][C] (mean, M2); count behind (t, c) = cnt[t*cnt_stride + c/cnt_div] */
+int egaze_bn_finalize(const float* partial, const float* cnt, int cnt_stride, int cnt_div, int T, int C, float eps,
+                      float momentum, const float* gamma, const float* beta, float* running_mean, float* running_var, float* mean_out,
                       float* invstd_out, float* scale_out, float* shift_out, void* stream);
 int egaze_bn_fold(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                   const float* conv_bias, float eps, int C, float* scale, float* shift, void* stream);
