@@ -100,7 +100,8 @@ class Workload(object):
         torch.manual_seed(0)  # identical replicas on every rank
         self.model = model_SP(make_layers(cfg['D'], 3), make_layers(cfg['D'], 20)).to(device)
         self.crit = floss_mod.floss()
-        x_s, x_t, gt = orc.synth_sp_inputs(B, S, 1234 + rank)
+        from egaze.ddp import shard_seed
+        x_s, x_t, gt = orc.synth_sp_inputs(B, S, shard_seed(1234, rank))
         self.host = [torch.from_numpy(a).pin_memory() for a in (x_s, x_t, gt)]
         self.dev = [t.to(device) for t in self.host]
         self.h2d_bytes = sum(t.numel() * 4 for t in self.host[:2]) + (self.host[2].numel() * 4 if name == "sp_train" else 0)
@@ -131,26 +132,23 @@ class Workload(object):
 
     def _make_flat_grads(self):
         """All weight grads live in ONE flat fp32 buffer so the per-step NCCL allreduce needs no pack/copy."""
-        ps = [p for p in self.model.parameters() if p.requires_grad]
-        self.flat = torch.zeros(sum(p.numel() for p in ps), device=self.device)
-        off = 0
-        for p in ps:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
+        from egaze.ddp import FlatGradBucket, broadcast_parameters
+        broadcast_parameters(self.model, 0)
+        self.flat = FlatGradBucket(self.model.parameters(), self.device)
 
     def step(self, x_s, x_t, gt):
         """One pass of the hot path; returns the tensor a user would read back."""
         from egaze import ops
         if self.name == "sp_train":
             if self.flat is not None:
-                self.flat.zero_()
+                self.flat.zero()
             else:
                 self.opt.zero_grad(set_to_none=True)
             out = self.model(x_s, x_t)
             loss = self.crit(out, gt.view(out.size()))
             loss.backward()
             if self.flat is not None:
-                torch.distributed.all_reduce(self.flat, op=torch.distributed.ReduceOp.AVG)
+                self.flat.allreduce()
             self.opt.step()
             return loss
         with torch.no_grad():
