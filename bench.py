@@ -292,17 +292,36 @@ def main():
     clocks = sampler.finish() if sampler else None
 
     # ---- end to end: host (pinned) inputs in, result read back, every step -----------------------------------------------
-    def e2e_step():
-        xs = [t.to(device, non_blocking=True) for t in wl.host]
-        res = wl.step(*xs)
-        return res.detach().to("cpu", non_blocking=False)
-    for _ in range(2):
-        e2e_step()
+    # What a data loader does: the H2D copy of batch i+1 runs on a copy stream while batch i computes (double-buffered
+    # device inputs).  Every step's input bytes cross PCIe inside the timed region and every step's result is read back.
+    copy_stream = torch.cuda.Stream(device=device)
+    bufs = [[torch.empty_like(t, device=device) for t in wl.host] for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+
+    def prefetch(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[i % 2])
+            for b, h in zip(bufs[i % 2], wl.host):
+                b.copy_(h, non_blocking=True)
+            ready[i % 2].record(copy_stream)
+
+    def e2e_run(n):
+        for ev in freed:
+            ev.record()
+        prefetch(0)
+        for i in range(n):
+            torch.cuda.current_stream().wait_event(ready[i % 2])
+            if i + 1 < n:
+                prefetch(i + 1)
+            res = wl.step(*bufs[i % 2])
+            freed[i % 2].record()
+            res.detach().to("cpu", non_blocking=False)
+    e2e_run(2)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    for _ in range(K):
-        e2e_step()
+    e2e_run(K)
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1) / K

@@ -59,6 +59,43 @@ weighted_map_kernel(const float* __restrict__ feat, const float* __restrict__ w,
   for (int p = threadIdx.x; p < HW; p += blockDim.x) out[(size_t)b * HW + p] = (sm[p] - vmin) / denom;
 }
 
+// AT.crop_align_feature (AT.py:41-56) + mean (AT.py:239-241): bilinear x`up` upsample (align_corners=True), crop a
+// (size*up)^2 window centred at clip(gaze, size*up/2, H*up - size*up/2), average.  The bilinear weights are separable, so
+// the mean over the window is sum_ij F[i][j]*wy[i]*wx[j]: the upsampled (B,512,224,224) map is never materialised.
+__global__ void crop_align_mean_kernel(const float* __restrict__ feat, const int* __restrict__ gaze, int C, int H, int W,
+                                       int size, int up, float* __restrict__ out) {
+  __shared__ float wy[64], wx[64];
+  const int b = blockIdx.y;
+  const int HS = H * up, WS = W * up, win = size * up;
+  if (threadIdx.x < 64) { wy[threadIdx.x] = 0.f; wx[threadIdx.x] = 0.f; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    const int n_in = threadIdx.x == 0 ? H : W, n_out = threadIdx.x == 0 ? HS : WS;
+    float* wv = threadIdx.x == 0 ? wy : wx;
+    int f = gaze[2 * b + threadIdx.x];
+    f = min(max(f, win / 2), HS - win / 2);   // reference clips both coordinates with H (=224)
+    const float scale = n_out > 1 ? (float)(n_in - 1) / (float)(n_out - 1) : 0.f;
+    for (int o = f - win / 2; o < f + win / 2; ++o) {
+      const float src = (float)o * scale;
+      const int i0 = min((int)src, n_in - 1), i1 = min(i0 + 1, n_in - 1);
+      const float l = src - (float)i0;
+      wv[i0] += 1.f - l;
+      wv[i1] += l;
+    }
+  }
+  __syncthreads();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float* f = feat + ((size_t)b * C + c) * H * W;
+  float s = 0.f;
+  for (int i = 0; i < H; ++i) {
+    float r = 0.f;
+    for (int j = 0; j < W; ++j) r = fmaf(f[i * W + j], wx[j], r);
+    s = fmaf(r, wy[i], s);
+  }
+  out[(size_t)b * C + c] = s / (float)(win * win);
+}
+
 // F.upsample(scale_factor=S, mode='bilinear') == align_corners=False (run_spatialstream.py:136). x: [B][h][w] -> [B][hS][wS]
 __global__ void bilinear_up_kernel(const float* __restrict__ x, int B, int h, int w, int S, int align_corners,
                                    float* __restrict__ out) {
@@ -96,6 +133,16 @@ extern "C" int egaze_crop_mean(const float* feat_nchw, const int* gaze, int B, i
   EGAZE_CHECK_ARG(size >= 1 && size <= H && size <= W && down >= 1, "crop_mean: bad crop size");
   dim3 grid(ceil_div(C, 128), B);
   crop_mean_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(feat_nchw, gaze, B, C, H, W, size, down, out);
+  EGAZE_LAUNCH_CHECK();
+  return EGAZE_OK;
+}
+
+extern "C" int egaze_crop_align_mean(const float* feat_nchw, const int* gaze, int B, int C, int H, int W, int size, int up,
+                                     float* out, void* stream) {
+  EGAZE_CHECK_ARG(feat_nchw && gaze && out && B > 0 && C > 0, "crop_align_mean: bad args");
+  EGAZE_CHECK_ARG(H <= 64 && W <= 64 && size >= 1 && up >= 1 && size * up <= H * up, "crop_align_mean: unsupported shape");
+  dim3 grid(ceil_div(C, 128), B);
+  crop_align_mean_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(feat_nchw, gaze, C, H, W, size, up, out);
   EGAZE_LAUNCH_CHECK();
   return EGAZE_OK;
 }

@@ -129,6 +129,81 @@ linear512_kernel(const float* __restrict__ x, const float* __restrict__ w, const
   }
 }
 
+
+// ---- backward (BPTT) ------------------------------------------------------------------------------------------------
+// dz = gout * (out > 0)   (ReLU after the Linear, LSTMnet.py:37)
+__global__ void relu_mask_kernel(const float* __restrict__ g, const float* __restrict__ out, size_t n, float* __restrict__ dz) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dz[i] = out[i] > 0.f ? g[i] : 0.f;
+}
+
+// One cell, one time step: dh = dh_a + dh_b;  gates = post-activation (i,f,g,o);  dc_io holds dc from step t+1 on entry
+// and dc for step t-1 on exit.  dgates = gradients w.r.t. the PRE-activation gates.
+__global__ void lstm_gate_bwd_kernel(const float* __restrict__ dh_a, const float* __restrict__ dh_b,
+                                     const float* __restrict__ gates, const float* __restrict__ c,
+                                     const float* __restrict__ c_prev, int B, float* __restrict__ dc_io,
+                                     float* __restrict__ dgates) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * HID) return;
+  const int b = idx / HID, j = idx % HID;
+  const float* gp = gates + (size_t)b * 4 * HID + j;
+  const float i_ = gp[0], f_ = gp[HID], g_ = gp[2 * HID], o_ = gp[3 * HID];
+  float dh = dh_a[idx];
+  if (dh_b) dh += dh_b[idx];
+  const float tc = tanhf(c[idx]);
+  const float dc = dh * o_ * (1.f - tc * tc) + dc_io[idx];
+  float* dg = dgates + (size_t)b * 4 * HID + j;
+  dg[0] = dc * g_ * i_ * (1.f - i_);
+  dg[HID] = dc * c_prev[idx] * f_ * (1.f - f_);
+  dg[2 * HID] = dc * i_ * (1.f - g_ * g_);
+  dg[3 * HID] = dh * tc * o_ * (1.f - o_);
+  dc_io[idx] = dc * f_;
+}
+
+// Y[r][n] (+)= sum_k X[r][k] * W[k][n]      (dx = dgates . W_ih, dh_prev = dgates . W_hh, dh_top = dz . W_lin)
+__global__ void matmul_nn_kernel(const float* __restrict__ X, const float* __restrict__ W, int R, int K, int N,
+                                 float* __restrict__ Y) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (n >= N || r >= R) return;
+  const float* x = X + (size_t)r * K;
+  float acc = 0.f;
+#pragma unroll 4
+  for (int k = 0; k < K; ++k) acc = fmaf(__ldg(x + k), W[(size_t)k * N + n], acc);
+  Y[(size_t)r * N + n] = acc;
+}
+
+// dW[m][n] (+)= sum_{t<T,b<B} A[t*a_st + b*a_sb + m] * Bm[t*b_st + b*b_sb + n]   (weight gradients over all rows)
+__global__ void matmul_tn_kernel(const float* __restrict__ A, size_t a_st, size_t a_sb, const float* __restrict__ Bm,
+                                 size_t b_st, size_t b_sb, int T, int B, int M, int N, int accumulate,
+                                 float* __restrict__ dW) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y;
+  if (n >= N || m >= M) return;
+  float acc = accumulate ? dW[(size_t)m * N + n] : 0.f;
+  for (int t = 0; t < T; ++t)
+    for (int b = 0; b < B; ++b)
+      acc = fmaf(__ldg(A + t * a_st + b * a_sb + m), Bm[t * b_st + b * b_sb + n], acc);
+  dW[(size_t)m * N + n] = acc;
+}
+
+__global__ void col_sum_f32_kernel(const float* __restrict__ X, size_t ld, int R, int N, float* __restrict__ out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float acc = 0.f;
+  for (int r = 0; r < R; ++r) acc += X[(size_t)r * ld + n];
+  out[n] = acc;
+}
+
+// xt = tanh(x) ; optionally dx = g * (1 - tanh(x)^2)
+__global__ void tanh_kernel(const float* __restrict__ x, size_t n, float* __restrict__ xt) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) xt[i] = tanhf(x[i]);
+}
+__global__ void tanh_bwd_kernel(const float* __restrict__ xt, const float* __restrict__ g, size_t n, float* __restrict__ dx) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dx[i] = g[i] * (1.f - xt[i] * xt[i]);
+}
+
 }  // namespace
 
 // Sequence forward.  All pointers device fp32.
@@ -172,5 +247,79 @@ extern "C" int egaze_lstm_seq_fwd(const float* x, const float* h0, const float* 
   }
   EGAZE_CUDA(cudaMemcpyAsync(hn, ws_h + ((size_t)(T - 1) * 2) * sl, 2 * sl * sizeof(float), cudaMemcpyDeviceToDevice, st));
   EGAZE_CUDA(cudaMemcpyAsync(cn, ws_c + ((size_t)(T - 1) * 2) * sl, 2 * sl * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return EGAZE_OK;
+}
+
+// Sequence backward (BPTT) of lstmnet.forward -- what loss.backward() runs in AT.trainLSTM (AT.py:138-142).
+//  gout [T][B][512] gradient w.r.t. the ReLU output; ghn/gcn [2][B][512] gradients w.r.t. the returned state (may be NULL)
+//  out  [T][B][512] forward output (ReLU mask); ws_h/ws_c [T][2][B][512], ws_gates [T][2][B][4][512]: forward workspaces
+//  workspaces: xt, dz, dh_top [T][B][512]; dgates [2][T][B][2048]; tmp_x [B][512]; dh_next, dc_next [2][B][512];
+//              dx0 [T][B][512] (only when dinput != NULL)
+//  outputs: dw_ih/dw_hh: 2 pointers to [2048][512]; db: 2 pointers to [2048] (d bias_ih == d bias_hh); dlin_w [512][512];
+//           dlin_b [512]; dinput [T][B][512] (optional); dh0/dc0 [2][B][512] (optional)
+extern "C" int egaze_lstm_seq_bwd(const float* x, const float* h0, const float* c0, const float* const* w_ih,
+                                  const float* const* w_hh, const float* lin_w, int T, int B, const float* out,
+                                  const float* gout, const float* ghn, const float* gcn, const float* ws_h,
+                                  const float* ws_c, const float* ws_gates, float* xt, float* dz, float* dgates,
+                                  float* dh_top, float* tmp_x, float* dh_next, float* dc_next, float* dx0,
+                                  float* const* dw_ih, float* const* dw_hh, float* const* db, float* dlin_w,
+                                  float* dlin_b, float* dinput, float* dh0, float* dc0, void* stream) {
+  EGAZE_CHECK_ARG(x && h0 && c0 && w_ih && w_hh && lin_w && out && gout && ws_h && ws_c && ws_gates, "lstm_seq_bwd: null input");
+  EGAZE_CHECK_ARG(xt && dz && dgates && dh_top && tmp_x && dh_next && dc_next && dw_ih && dw_hh && db && dlin_w && dlin_b,
+                  "lstm_seq_bwd: null workspace/output");
+  EGAZE_CHECK_ARG(!dinput || dx0, "lstm_seq_bwd: dinput needs the dx0 workspace");
+  EGAZE_CHECK_ARG(T > 0 && B > 0, "lstm_seq_bwd: bad T=%d B=%d", T, B);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t sl = (size_t)B * HID;
+  const size_t n_all = (size_t)T * sl;
+  int eb = (int)((n_all + 255) / 256);
+  if (eb > 148 * 8) eb = 148 * 8;
+  tanh_kernel<<<eb, 256, 0, st>>>(x, n_all, xt);
+  relu_mask_kernel<<<eb, 256, 0, st>>>(gout, out, n_all, dz);
+  EGAZE_LAUNCH_CHECK();
+  // Linear (LSTMnet.py:36): dW = dz^T . h_top, db = sum dz, dh_top = dz . W
+  matmul_tn_kernel<<<dim3(HID / 128, HID), 128, 0, st>>>(dz, sl, HID, ws_h + sl, 2 * sl, HID, T, B, HID, HID, 0, dlin_w);
+  col_sum_f32_kernel<<<HID / 128, 128, 0, st>>>(dz, HID, T * B, HID, dlin_b);
+  matmul_nn_kernel<<<dim3(HID / 128, T * B), 128, 0, st>>>(dz, lin_w, T * B, HID, HID, dh_top);
+  EGAZE_LAUNCH_CHECK();
+  if (ghn) EGAZE_CUDA(cudaMemcpyAsync(dh_next, ghn, 2 * sl * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  else EGAZE_CUDA(cudaMemsetAsync(dh_next, 0, 2 * sl * sizeof(float), st));
+  if (gcn) EGAZE_CUDA(cudaMemcpyAsync(dc_next, gcn, 2 * sl * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  else EGAZE_CUDA(cudaMemsetAsync(dc_next, 0, 2 * sl * sizeof(float), st));
+  const int gb = (int)((sl + 255) / 256);
+  for (int t = T - 1; t >= 0; --t) {
+    for (int l = 1; l >= 0; --l) {
+      const float* gates = ws_gates + ((size_t)t * 2 + l) * sl * 4;
+      const float* cc = ws_c + ((size_t)t * 2 + l) * sl;
+      const float* cprev = t == 0 ? c0 + l * sl : ws_c + ((size_t)(t - 1) * 2 + l) * sl;
+      float* dg = dgates + ((size_t)l * T + t) * sl * 4;
+      const float* dh_a = l == 1 ? dh_top + (size_t)t * sl : tmp_x;   // from above: the Linear (layer 1) or layer 1's dx (layer 0)
+      lstm_gate_bwd_kernel<<<gb, 256, 0, st>>>(dh_a, dh_next + l * sl, gates, cc, cprev, B, dc_next + l * sl, dg);
+      matmul_nn_kernel<<<dim3(HID / 128, B), 128, 0, st>>>(dg, w_hh[l], B, 4 * HID, HID, dh_next + l * sl);   // -> h_{t-1}
+      if (l == 1) matmul_nn_kernel<<<dim3(HID / 128, B), 128, 0, st>>>(dg, w_ih[1], B, 4 * HID, HID, tmp_x);   // -> layer 0's h_t
+      else if (dinput) matmul_nn_kernel<<<dim3(HID / 128, B), 128, 0, st>>>(dg, w_ih[0], B, 4 * HID, HID, dx0 + (size_t)t * sl);
+      EGAZE_LAUNCH_CHECK();
+    }
+  }
+  if (dinput) {
+    tanh_bwd_kernel<<<eb, 256, 0, st>>>(xt, dx0, n_all, dinput);
+    EGAZE_LAUNCH_CHECK();
+  }
+  if (dh0) EGAZE_CUDA(cudaMemcpyAsync(dh0, dh_next, 2 * sl * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (dc0) EGAZE_CUDA(cudaMemcpyAsync(dc0, dc_next, 2 * sl * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  // weight gradients: one pass over all (t, b) rows per matrix
+  for (int l = 0; l < 2; ++l) {
+    const float* dg = dgates + (size_t)l * T * sl * 4;   // [T][B][2048]
+    const size_t g_st = sl * 4, g_sb = 4 * HID;
+    dim3 grid(HID / 128, 4 * HID);
+    if (l == 0) matmul_tn_kernel<<<grid, 128, 0, st>>>(dg, g_st, g_sb, xt, sl, HID, T, B, 4 * HID, HID, 0, dw_ih[0]);
+    else matmul_tn_kernel<<<grid, 128, 0, st>>>(dg, g_st, g_sb, ws_h, 2 * sl, HID, T, B, 4 * HID, HID, 0, dw_ih[1]);
+    // recurrent weights: h_{t-1} is the initial state for t = 0 and ws_h[t-1] afterwards
+    matmul_tn_kernel<<<grid, 128, 0, st>>>(dg, g_st, g_sb, h0 + l * sl, 0, HID, 1, B, 4 * HID, HID, 0, dw_hh[l]);
+    if (T > 1)
+      matmul_tn_kernel<<<grid, 128, 0, st>>>(dg + g_st, g_st, g_sb, ws_h + l * sl, 2 * sl, HID, T - 1, B, 4 * HID, HID, 1, dw_hh[l]);
+    col_sum_f32_kernel<<<4 * HID / 128, 128, 0, st>>>(dg, 4 * HID, T * B, 4 * HID, db[l]);
+    EGAZE_LAUNCH_CHECK();
+  }
   return EGAZE_OK;
 }

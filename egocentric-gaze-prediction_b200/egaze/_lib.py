@@ -98,6 +98,8 @@ def call(name, *args):
     rc = fn(*[_arg(a) for a in args])
     if name == "egaze_lstm_seq_fwd":
         _launch_count += 3 * int(args[9])  # 2 cell kernels + 1 linear per time step
+    elif name == "egaze_lstm_seq_bwd":
+        _launch_count += 6 * int(args[6]) + 16  # per step: 2 x (gate grad + 2 small GEMMs); + Linear / weight-grad passes
     else:
         _launch_count += _LAUNCHES.get(name, 1)
     if rc != 0:

@@ -305,5 +305,36 @@ def late_fusion_with_grad(model, f, g):
     return _LateFusionFn.apply(model, f, g, *_params(model))
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# lstmnet (AT.trainLSTM: one-step-ahead MSE on stored 512-vectors, AT.py:118-147)
+# ---------------------------------------------------------------------------------------------------------------------
+class _LstmNetFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, inp, h0, c0, *params):
+        out, hn, cn, ws = ops.lstm_seq_fwd(inp, h0, c0, model.lstm, model.lin, save_gates=True)
+        ctx.model, ctx.rec = model, (inp.detach(), h0.detach(), c0.detach(), out, ws)
+        ctx.need = (inp.requires_grad, h0.requires_grad or c0.requires_grad)
+        return out, hn, cn
+
+    @staticmethod
+    def backward(ctx, gout, ghn, gcn):
+        model = ctx.model
+        inp, h0, c0, out, ws = ctx.rec
+        if gout is None:
+            gout = torch.zeros_like(out)
+        r = ops.lstm_seq_bwd(inp, h0, c0, model.lstm, model.lin, out, ws, gout, ghn, gcn, ctx.need[0], ctx.need[1])
+        bag = _GradBag()
+        for l in range(2):
+            bag.put(getattr(model.lstm, "weight_ih_l%d" % l), r["dw_ih"][l])
+            bag.put(getattr(model.lstm, "weight_hh_l%d" % l), r["dw_hh"][l])
+            bag.put(getattr(model.lstm, "bias_ih_l%d" % l), r["db"][l])
+            bag.put(getattr(model.lstm, "bias_hh_l%d" % l), r["db"][l].clone())
+        bag.put(model.lin.weight, r["dlin_w"])
+        bag.put(model.lin.bias, r["dlin_b"])
+        ctx.rec = None
+        return (None, r["dinput"], r["dh0"], r["dc0"]) + _ret_grads(bag, _params(model))
+
+
 def lstmnet_with_grad(model, inp, h0, c0):
-    raise NotImplementedError("egaze: lstmnet backward (AT.trainLSTM) is not built yet; forward/inference only")
+    out, hn, cn = _LstmNetFn.apply(model, inp, h0, c0, *_params(model))
+    return (out, (hn, cn))

@@ -423,6 +423,16 @@ def crop_mean(feat, gaze, size=3, down=16):
     return out
 
 
+def crop_align_mean(feat, gaze, size=3, up=16):
+    """AT.crop_align_feature + mean (align=True branch of AT.extract_late): -> [B, C]."""
+    feat = feat.contiguous().float()
+    B, C, H, W = feat.shape
+    g = torch.as_tensor(gaze, dtype=torch.int32, device=feat.device).reshape(B, 2).contiguous()
+    out = torch.empty((B, C), dtype=F32, device=feat.device)
+    call("egaze_crop_align_mean", feat, g, B, C, H, W, int(size), int(up), out, stream_ptr())
+    return out
+
+
 def weighted_map(chn_weight, feat):
     feat = feat.contiguous().float()
     B, C, H, W = feat.shape
@@ -468,3 +478,33 @@ def lstm_seq_fwd(x, h0, c0, lstm, lin, save_gates=False):
          stream_ptr())
     del k1, k2, k3, k4
     return out, hn, cn, (ws_h, ws_c, ws_g)
+
+
+def lstm_seq_bwd(x, h0, c0, lstm, lin, out, ws, gout, ghn, gcn, need_input, need_state):
+    """BPTT of lstm_seq_fwd.  ws = (ws_h, ws_c, ws_gates) from the forward (save_gates=True).
+    -> dict with dw_ih, dw_hh, db (lists of 2), dlin_w, dlin_b, dinput | None, dh0 | None, dc0 | None."""
+    x = x.contiguous().float()
+    T, B, Hd = x.shape
+    dev = x.device
+    ws_h, ws_c, ws_g = ws
+    new = lambda *shape: torch.empty(shape, dtype=F32, device=dev)
+    xt, dz, dh_top = new(T, B, Hd), new(T, B, Hd), new(T, B, Hd)
+    dgates = new(2, T, B, 4 * Hd)
+    tmp_x, dh_next, dc_next = new(B, Hd), new(2, B, Hd), new(2, B, Hd)
+    dx0 = new(T, B, Hd) if need_input else None
+    dinput = new(T, B, Hd) if need_input else None
+    dh0 = new(2, B, Hd) if need_state else None
+    dc0 = new(2, B, Hd) if need_state else None
+    dw_ih = [new(4 * Hd, Hd) for _ in range(2)]
+    dw_hh = [new(4 * Hd, Hd) for _ in range(2)]
+    db = [new(4 * Hd) for _ in range(2)]
+    dlin_w, dlin_b = new(Hd, Hd), new(Hd)
+    parr = lambda ts: (ctypes.c_void_p * 2)(*[t.data_ptr() for t in ts])
+    keep = [getattr(lstm, "weight_ih_l%d" % l).detach().contiguous() for l in range(2)]
+    keep2 = [getattr(lstm, "weight_hh_l%d" % l).detach().contiguous() for l in range(2)]
+    call("egaze_lstm_seq_bwd", x, h0.contiguous().float(), c0.contiguous().float(), parr(keep), parr(keep2),
+         lin.weight.detach().contiguous(), T, B, out, gout.contiguous().float(),
+         ghn.contiguous().float() if ghn is not None else None, gcn.contiguous().float() if gcn is not None else None,
+         ws_h, ws_c, ws_g, xt, dz, dgates, dh_top, tmp_x, dh_next, dc_next, dx0, parr(dw_ih), parr(dw_hh), parr(db),
+         dlin_w, dlin_b, dinput, dh0, dc0, stream_ptr())
+    return dict(dw_ih=dw_ih, dw_hh=dw_hh, db=db, dlin_w=dlin_w, dlin_b=dlin_b, dinput=dinput, dh0=dh0, dc0=dc0)

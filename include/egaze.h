@@ -105,6 +105,9 @@ int egaze_floss_bwd(const float* input, const float* target, const double* centr
 /* ---- AT glue (AT.py:25-39,58-66,236-241 ; run_spatialstream.py:85-104,136) ------------------------------------ */
 int egaze_crop_mean(const float* feat_nchw, const int* gaze, int B, int C, int H, int W, int size, int down, float* out,
                     void* stream);
+/* AT.crop_align_feature + mean (AT.py:41-56,239-241): bilinear x`up` (align_corners=True), (size*up)^2 crop, average */
+int egaze_crop_align_mean(const float* feat_nchw, const int* gaze, int B, int C, int H, int W, int size, int up, float* out,
+                          void* stream);
 int egaze_weighted_map(const float* feat_nchw, const float* chn_weight, int B, int C, int HW, float* out, void* stream);
 int egaze_bilinear_up(const float* x, int B, int h, int w, int scale, int align_corners, float* out, void* stream);
 
@@ -113,6 +116,16 @@ int egaze_lstm_seq_fwd(const float* x, const float* h0, const float* c0, const f
                        const float* const* w_hh, const float* const* b_ih, const float* const* b_hh, const float* lin_w,
                        const float* lin_b, int T, int B, float* out, float* hn, float* cn, float* ws_h, float* ws_c,
                        float* ws_gates, void* stream);
+
+/* BPTT of lstmnet.forward (loss.backward() in AT.trainLSTM, AT.py:138-142); all workspaces / outputs are caller-allocated:
+ * xt, dz, dh_top [T][B][512]; dgates [2][T][B][2048]; tmp_x [B][512]; dh_next, dc_next [2][B][512]; dx0 [T][B][512] iff dinput;
+ * dw_ih / dw_hh / db: arrays of 2 device pointers ([2048][512] / [2048]); dlin_w [512][512]; dlin_b [512]. */
+int egaze_lstm_seq_bwd(const float* x, const float* h0, const float* c0, const float* const* w_ih,
+                       const float* const* w_hh, const float* lin_w, int T, int B, const float* out, const float* gout,
+                       const float* ghn, const float* gcn, const float* ws_h, const float* ws_c, const float* ws_gates,
+                       float* xt, float* dz, float* dgates, float* dh_top, float* tmp_x, float* dh_next, float* dc_next,
+                       float* dx0, float* const* dw_ih, float* const* dw_hh, float* const* db, float* dlin_w,
+                       float* dlin_b, float* dinput, float* dh0, float* dc0, void* stream);
 
 #ifdef __cplusplus
 }

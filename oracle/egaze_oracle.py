@@ -237,6 +237,20 @@ def crop_mean(feature, maxind, size=3):
     return c.reshape(c.shape[0], c.shape[1], -1).mean(axis=2, dtype=np.float32)
 
 
+def crop_align_mean(feature, maxind, size=3):
+    """AT.crop_align_feature (AT.py:41-56) + mean (AT.py:239-241): bilinear x16 (align_corners=True), 48x48 crop around
+    clip(gaze, 24, 224-24), mean -> [B,512]."""
+    H = 224
+    win = size * 16
+    up = bilinear_upsample(feature, 16, align_corners=True)
+    res = []
+    for b in range(feature.shape[0]):
+        fmax = np.clip(np.array(maxind[b]), win // 2, H - win // 2).astype(np.int64)
+        c = up[b, :, fmax[0] - win // 2:fmax[0] + win // 2, fmax[1] - win // 2:fmax[1] + win // 2]
+        res.append(c.reshape(c.shape[0], -1).mean(axis=1, dtype=np.float32))
+    return np.stack(res)
+
+
 def get_weighted(chn_weight, feature):
     """AT.get_weighted (AT.py:58-66) applied per sample (the reference only ever passes batch 1)."""
     out = []

@@ -188,13 +188,19 @@ def main():
     rs = np.random.RandomState(9)
     feats = np.maximum(rs.randn(4, 512, 14, 14), 0).astype(np.float32)
     gazes = np.array([[0, 0], [223, 223], [100, 37], [15, 208]])
-    vecs, maps = [], []
+    vecs, maps, avecs = [], [], []
+    import warnings
     for b in range(4):
         c = ref_at.crop_feature(t(feats[b:b + 1]), [list(gazes[b])], 3).contiguous()
         v = torch.mean(c.view(1, 512, -1), 2)
         vecs.append(v.numpy())
         maps.append(ref_at.get_weighted(v, t(feats[b:b + 1])).numpy())
-    np.savez_compressed(os.path.join(OUT, "at_glue.npz"), seed=9, gazes=gazes, vec=np.concatenate(vecs), map=np.concatenate(maps))
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ca = ref_at.crop_align_feature(t(feats[b:b + 1]), [list(gazes[b])], 3).contiguous()
+        avecs.append(torch.mean(ca.view(1, 512, -1), 2).numpy())
+    np.savez_compressed(os.path.join(OUT, "at_glue.npz"), seed=9, gazes=gazes, vec=np.concatenate(vecs), map=np.concatenate(maps),
+                        align_vec=np.concatenate(avecs))
     print("golden fixtures written to", OUT)
     for fn in sorted(os.listdir(OUT)):
         print("  %-36s %8d bytes" % (fn, os.path.getsize(os.path.join(OUT, fn))))

@@ -147,3 +147,5 @@ def test_at_glue_vs_reference_golden(cuda_dev):
     assert np.abs(vec.cpu().numpy() - g["vec"]).max() <= 1e-6
     wm = ops.weighted_map(vec, feats)
     assert np.abs(wm.cpu().numpy() - g["map"]).max() <= 2e-5
+    av = ops.crop_align_mean(feats, g["gazes"].tolist(), 3)
+    assert np.abs(av.cpu().numpy() - g["align_vec"]).max() <= 1e-5

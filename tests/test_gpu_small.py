@@ -158,3 +158,33 @@ def test_lstmnet_hidden_none(cuda_dev):
             assert out.shape == (30, 16, 512)
         finally:
             L.batch_size = 1
+
+
+@pytest.mark.parametrize("T,B", [(1, 1), (4, 3), (30, 16)])
+def test_lstmnet_bwd(cuda_dev, T, B):
+    """BPTT through the egaze LSTM kernels vs PyTorch autograd of nn.LSTM/nn.Linear over the same parameters
+    (AT.trainLSTM's loss: MSE against tanh(target), AT.py:138)."""
+    import copy
+    import models.LSTMnet as L
+    torch.manual_seed(1)
+    net = L.lstmnet().to(cuda_dev).train()
+    ref = copy.deepcopy(net)
+    x = torch.randn(T, B, 512, device=cuda_dev)
+    h0 = (torch.randn(2, B, 512, device=cuda_dev) * 0.3).requires_grad_(True)
+    c0 = (torch.randn(2, B, 512, device=cuda_dev) * 0.3).requires_grad_(True)
+    tgt = torch.tanh(torch.randn(T, B, 512, device=cuda_dev))
+    xa = x.clone().requires_grad_(True)
+    out, (hn, cn) = net(xa, (h0, c0))
+    loss = torch.nn.functional.mse_loss(out, tgt) + 0.1 * hn.sum() + 0.05 * cn.pow(2).sum()
+    loss.backward()
+    xb = x.clone().requires_grad_(True)
+    h0r, c0r = h0.detach().clone().requires_grad_(True), c0.detach().clone().requires_grad_(True)
+    outr, (hnr, cnr) = torch_ref.lstmnet_forward(ref, xb, h0r, c0r)
+    lossr = torch.nn.functional.mse_loss(outr, tgt) + 0.1 * hnr.sum() + 0.05 * cnr.pow(2).sum()
+    lossr.backward()
+    assert abs(loss.item() - lossr.item()) <= 1e-5 * abs(lossr.item())
+    rel = lambda a, b: ((a - b).norm() / b.norm().clamp_min(1e-20)).item()
+    for (k, p), (_, q) in zip(net.named_parameters(), ref.named_parameters()):
+        assert rel(p.grad, q.grad) <= 1e-4, "%s: %.3e" % (k, rel(p.grad, q.grad))
+    assert rel(xa.grad, xb.grad) <= 1e-4
+    assert rel(h0.grad, h0r.grad) <= 1e-4 and rel(c0.grad, c0r.grad) <= 1e-4
