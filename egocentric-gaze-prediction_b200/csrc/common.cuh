@@ -58,6 +58,16 @@ __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
 __device__ __forceinline__ float bf16_bits_to_float(uint32_t bits16) { return __uint_as_float(bits16 << 16); }
+// Four values at once with the packed converter (cvt.rn.bf16x2.f32 -> F2FP, ALU pipe; the scalar F2F goes through the
+// quarter-rate XU pipe).  Bit-identical to four split_bf16 calls; hi2/lo2 are ready for an 8-byte NHWC store.
+__device__ __forceinline__ void split_bf16x4(const float4& v, uint2& hi2, uint2& lo2) {
+  const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
+  const uint32_t u01 = *reinterpret_cast<const uint32_t*>(&h01), u23 = *reinterpret_cast<const uint32_t*>(&h23);
+  const __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - __uint_as_float(u01 << 16), v.y - __uint_as_float(u01 & 0xffff0000u));
+  const __nv_bfloat162 l23 = __floats2bfloat162_rn(v.z - __uint_as_float(u23 << 16), v.w - __uint_as_float(u23 & 0xffff0000u));
+  hi2 = make_uint2(u01, u23);
+  lo2 = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+}
 
 // ---------------------------------------------------------------------------------------------
 // warp / block reductions
@@ -89,6 +99,22 @@ __device__ __forceinline__ float warp_min(float v) {
 namespace ptx {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// explicit shared-space accesses by 32-bit shared address (a pointer carved out of the dynamic smem window by integer
+// arithmetic is "generic" to the compiler, which then emits the slower LD/ST instead of LDS/STS)
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
@@ -124,6 +150,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       "{\n\t"
       ".reg .pred P1;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, 0x989680;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Non-blocking probe of a phase (no suspend hint): issue it early, consume the predicate later -- the ~90-cycle latency of
+// a barrier query then overlaps whatever is issued in between.
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, P1;\n\t"
       "}\n"
       : "=r"(ok)

@@ -44,7 +44,19 @@ struct ConvTcParams {
   int tile_groups;     // ceil(total_tiles / CS)
   int num_items;       // tile_groups * tiles_n
   int nsplit;          // 1 = single bf16 pass, 2 = hi/lo split (3 MMAs per product)
-  int merged;          // precise mode: A_hi x [B_hi | B_lo] as ONE MMA of N = 2*BN (the two halves are summed in the epilogue)
+  // How the hi/lo products are spread over TMEM accumulator blocks of BN columns (the epilogue adds the `nsum` blocks).
+  // Back-to-back tcgen05.mma into the SAME accumulator columns serialise (+~43 cycles each, tools/probe_mma_rate.cu), so
+  // consecutive MMAs always target different blocks:
+  //   0  one block, every MMA into it (fast mode; small-Cout fallbacks)
+  //   1  A_hi x [B_hi | B_lo] as ONE MMA of N = 2*BN into blocks 0-1, A_lo x B_hi into block 0   (previous default)
+  //   2  like 1, but A_lo x B_hi goes to its own block 2 (fits TMEM for BN <= 64)
+  //   3  three N = BN MMAs per K step alternating between blocks X = 0 and Y = 1:
+  //      even k: hi*hi -> X, hi*lo -> Y, lo*hi -> X;  odd k: hi*lo -> Y, hi*hi -> X, lo*hi -> Y
+  int acc_mode;
+  int nsum;            // accumulator blocks the epilogue adds (1, 2 or 3)
+  int acc_cols;        // TMEM columns of one accumulator stage (power of two >= 32)
+  int win;             // 1 = "window" mode: ONE (BH+2) x (BW+2) activation window per K chunk serves all nine taps
+  int win_bo;          // window mode: fill the descriptor's base_offset field with (start >> 7) & 7
   int SA, SB;          // ring depths
   int a_slot_bytes;    // bytes of one A plane slot (1024-aligned)
   int b_slot_bytes;    // bytes of one B plane slot
@@ -63,7 +75,12 @@ struct ConvTcParams {
   __nv_bfloat16* out_lo;      // optional (precise) NHWC bf16
   float* stats;               // optional [gridDim][2][Cout] per-CTA (mean, M2) of the pre-activation (acc + bias)
   float* stats_cnt;           // [gridDim][tiles_n] pixel count behind each per-CTA partial
+  long long* prof;            // optional [gridDim][16] cycle counters per role (tools/conv_prof.py); null in production
 };
+
+// cycle accounting of the three roles (debug aid, enabled by egaze_conv3x3_set_prof)
+#define PROF_T0(p) const long long prof_t0 = (p).prof ? clock64() : 0
+#define PROF_ADD(p, acc) do { if ((p).prof) (acc) += clock64() - prof_t0; } while (0)
 
 struct Item {
   int nt, tile, img, h0, w0;
@@ -84,6 +101,138 @@ __device__ __forceinline__ Item decode_item(const ConvTcParams& p, int w, int cs
   it.w0 = tw_i * p.BW;
   return it;
 }
+
+// Per-tile constants of the lean store loop below.
+struct EpiTile {
+  uint32_t st_addr;     // shared address of this thread's channel group in staging row 0
+  int ldst_b;           // staging row pitch (bytes)
+  int pl, PS, npix;     // this thread's first output pixel, pixels per sweep, output pixels per tile
+  int obw_log;          // log2(output tile width)
+  int vh, vw;           // valid output extent of this tile
+  int BW;               // conv tile width = staging rows per tile row
+  float4 s4, t4;        // v = acc * s4 + t4 (bias and folded BatchNorm)
+  float lo_clamp;       // 0 with ReLU, -inf without
+  size_t out_base;      // element offset of (img, oh0*rep, ow0*rep, first channel of this thread)
+  int out_row, out_px;  // element pitch of one tile row / pixel in the output (already times the replicate factor)
+  int ws_c;             // element pitch of one output image row (nearest-2x replicate)
+  size_t mask_base;     // same for the ReLU mask tensor
+  int mask_row, mask_px;
+};
+
+__device__ __forceinline__ float4 epi_affine(float4 a, const float4& s, const float4& t, float lo) {
+  a.x = fmaxf(fmaf(a.x, s.x, t.x), lo);
+  a.y = fmaxf(fmaf(a.y, s.y, t.y), lo);
+  a.z = fmaxf(fmaf(a.z, s.z, t.z), lo);
+  a.w = fmaxf(fmaf(a.w, s.w, t.w), lo);
+  return a;
+}
+
+// Phase 3 of the epilogue with every mode flag resolved at compile time and power-of-two tile widths: the accumulator
+// tile is drained at ~40 instructions per float4 instead of ~220 in the flag-driven loop.  Layers with a short K loop
+// (K = 9*64 .. 9*128) are bound by exactly this loop, not by the MMAs.
+template <int RED, bool MASK, bool UPS, bool F32, bool SPLIT>
+__device__ __forceinline__ void epi_store(const ConvTcParams& p, const EpiTile& e) {
+  const int obw_mask = (1 << e.obw_log) - 1;
+#pragma unroll 2
+  for (int pix = e.pl; pix < e.npix; pix += e.PS) {
+    const int ph = pix >> e.obw_log, pw = pix & obw_mask;
+    if (ph >= e.vh || pw >= e.vw) continue;
+    float4 v;
+    if (RED == 0) {
+      v = epi_affine(ptx::lds128(e.st_addr + (uint32_t)(pix * e.ldst_b)), e.s4, e.t4, e.lo_clamp);
+    } else {
+      const uint32_t rb = e.st_addr + (uint32_t)(((2 * ph) * e.BW + 2 * pw) * e.ldst_b);
+      const float4 a = epi_affine(ptx::lds128(rb), e.s4, e.t4, e.lo_clamp);
+      const float4 b = epi_affine(ptx::lds128(rb + (uint32_t)e.ldst_b), e.s4, e.t4, e.lo_clamp);
+      const float4 c = epi_affine(ptx::lds128(rb + (uint32_t)(e.BW * e.ldst_b)), e.s4, e.t4, e.lo_clamp);
+      const float4 d = epi_affine(ptx::lds128(rb + (uint32_t)((e.BW + 1) * e.ldst_b)), e.s4, e.t4, e.lo_clamp);
+      if (RED == 1) {
+        v.x = fmaxf(fmaxf(a.x, b.x), fmaxf(c.x, d.x));
+        v.y = fmaxf(fmaxf(a.y, b.y), fmaxf(c.y, d.y));
+        v.z = fmaxf(fmaxf(a.z, b.z), fmaxf(c.z, d.z));
+        v.w = fmaxf(fmaxf(a.w, b.w), fmaxf(c.w, d.w));
+      } else {
+        v.x = (a.x + b.x) + (c.x + d.x);
+        v.y = (a.y + b.y) + (c.y + d.y);
+        v.z = (a.z + b.z) + (c.z + d.z);
+        v.w = (a.w + b.w) + (c.w + d.w);
+      }
+    }
+    if (MASK) {
+      const uint2 mk = __ldg(reinterpret_cast<const uint2*>(p.mask + e.mask_base + (size_t)(ph * e.mask_row + pw * e.mask_px)));
+      if (!(bf16_bits_to_float(mk.x & 0xffffu) > 0.f)) v.x = 0.f;
+      if (!(bf16_bits_to_float(mk.x >> 16) > 0.f)) v.y = 0.f;
+      if (!(bf16_bits_to_float(mk.y & 0xffffu) > 0.f)) v.z = 0.f;
+      if (!(bf16_bits_to_float(mk.y >> 16) > 0.f)) v.w = 0.f;
+    }
+    uint2 hi2, lo2;
+    if (SPLIT) split_bf16x4(v, hi2, lo2);
+    const size_t off = e.out_base + (size_t)(ph * e.out_row + pw * e.out_px);
+#pragma unroll
+    for (int dy = 0; dy < (UPS ? 2 : 1); ++dy)
+#pragma unroll
+      for (int dx = 0; dx < (UPS ? 2 : 1); ++dx) {
+        const size_t o = off + (size_t)(dy * e.ws_c + dx * p.Cout);
+        if (F32) *reinterpret_cast<float4*>(p.out_f32 + o) = v;
+        if (SPLIT) {
+          *reinterpret_cast<uint2*>(p.out_hi + o) = hi2;
+          *reinterpret_cast<uint2*>(p.out_lo + o) = lo2;
+        }
+      }
+  }
+}
+
+// One tap of the precise-mode "merged" schedule -- per K step A_hi x [B_hi | B_lo] (N = 2*BN) then A_lo x B_hi (N = BN) --
+// with two barrier probes fused into the same asm block: mbarrier.test_wait on the NEXT weight slot and the NEXT
+// activation slot is issued BEFORE the MMAs and its predicate is read AFTER them.  A barrier query costs ~100 cycles
+// even when the phase completed long ago and the tensor pipe's instruction queue is shallow, so a query sitting between
+// two taps is tensor-pipe idle time; issued here its latency hides behind the (blocking) MMA issue.
+// Returns bit 0: next B slot has landed, bit 1: next A slot has landed.
+#define EGAZE_MMA_PAIR(OFF)                                                                \
+  "add.s64 ah, %2, " #OFF ";\n\t"                                                          \
+  "add.s64 al, %3, " #OFF ";\n\t"                                                          \
+  "add.s64 bb, %4, " #OFF ";\n\t"                                                          \
+  "tcgen05.mma.cta_group::1.kind::f16 [%1], ah, bb, %5, pt;\n\t"                           \
+  "tcgen05.mma.cta_group::1.kind::f16 [%1], al, bb, %6, pt;\n\t"
+template <int KSTEPS>
+__device__ __forceinline__ uint32_t tap_merged_probe(uint32_t d_tmem, uint64_t ad_hi, uint64_t ad_lo, uint64_t bd,
+                                                     uint32_t idesc2, uint32_t idesc, uint32_t accumulate, uint32_t bar_b,
+                                                     uint32_t par_b, uint32_t bar_a, uint32_t par_a) {
+  uint32_t flags;
+#define EGAZE_TAP_HEAD                                                                     \
+  "{\n\t"                                                                                  \
+  ".reg .pred pb, pa, pacc, pt;\n\t"                                                       \
+  ".reg .b64 ah, al, bb;\n\t"                                                              \
+  ".reg .b32 rb, ra;\n\t"                                                                  \
+  "mbarrier.test_wait.parity.shared::cta.b64 pb, [%8], %9;\n\t"                            \
+  "mbarrier.test_wait.parity.shared::cta.b64 pa, [%10], %11;\n\t"                          \
+  "setp.ne.b32 pacc, %7, 0;\n\t"                                                           \
+  "setp.eq.b32 pt, %7, %7;\n\t"                                                            \
+  "tcgen05.mma.cta_group::1.kind::f16 [%1], %2, %4, %5, pacc;\n\t"                         \
+  "tcgen05.mma.cta_group::1.kind::f16 [%1], %3, %4, %6, pt;\n\t"
+#define EGAZE_TAP_TAIL                                                                     \
+  "selp.u32 rb, 1, 0, pb;\n\t"                                                             \
+  "selp.u32 ra, 2, 0, pa;\n\t"                                                             \
+  "or.b32 %0, rb, ra;\n\t"                                                                 \
+  "}\n"
+#define EGAZE_TAP_OPERANDS                                                                                            \
+  : "=r"(flags)                                                                                                       \
+  : "r"(d_tmem), "l"(ad_hi), "l"(ad_lo), "l"(bd), "r"(idesc2), "r"(idesc), "r"(accumulate), "r"(bar_b), "r"(par_b),   \
+    "r"(bar_a), "r"(par_a)                                                                                            \
+  : "memory"
+  if (KSTEPS == 4) {
+    asm volatile(EGAZE_TAP_HEAD EGAZE_MMA_PAIR(2) EGAZE_MMA_PAIR(4) EGAZE_MMA_PAIR(6) EGAZE_TAP_TAIL EGAZE_TAP_OPERANDS);
+  } else if (KSTEPS == 2) {
+    asm volatile(EGAZE_TAP_HEAD EGAZE_MMA_PAIR(2) EGAZE_TAP_TAIL EGAZE_TAP_OPERANDS);
+  } else {
+    asm volatile(EGAZE_TAP_HEAD EGAZE_TAP_TAIL EGAZE_TAP_OPERANDS);
+  }
+#undef EGAZE_TAP_HEAD
+#undef EGAZE_TAP_TAIL
+#undef EGAZE_TAP_OPERANDS
+  return flags;
+}
+#undef EGAZE_MMA_PAIR
 
 template <int NSPLIT, int KSTEPS, int CS>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -119,7 +268,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     ptx::prefetch_tmap(&tmB_hi);
     if (NSPLIT == 2) { ptx::prefetch_tmap(&tmA_lo); ptx::prefetch_tmap(&tmB_lo); }
   }
-  const uint32_t acc_cols = p.merged ? 2u * (uint32_t)p.BN : (p.BN < 32 ? 32u : (uint32_t)p.BN);   // columns of one accumulator stage
+  const uint32_t acc_cols = (uint32_t)p.acc_cols;                // columns of one accumulator stage
   const uint32_t tmem_cols = 2 * acc_cols;                       // power of two in [64, 512]
   if (warp == 1) {
     ptx::tmem_alloc(&tmem_base_smem, tmem_cols);
@@ -133,7 +282,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
 
   const int chunks = p.Cin_p / p.KC;
   const int row_bytes = p.KC * 2;
-  const uint32_t a_box_bytes = (uint32_t)((p.BH + 2) * p.BW * row_bytes);
+  const int AW = p.win ? p.BW + 2 : p.BW;                        // pixel columns of one activation window
+  const uint32_t a_box_bytes = (uint32_t)((p.BH + 2) * AW * row_bytes);
+  const int a_loads = p.win ? 1 : 3;                             // windows per K chunk (one per horizontal tap, or one in all)
+  const int a_taps = p.win ? 9 : 3;                              // weight boxes consumed per window
   const uint32_t b_box_bytes = (uint32_t)(p.BN * row_bytes);
   const int b_rows_cta = p.BN / CS;                              // weight rows this CTA fetches (and multicasts)
 
@@ -141,21 +293,25 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     // ================================ TMA producer ================================
     if (lane == 0) {
       int sa = 0, sb = 0;
+      long long prof_c[2] = {0, 0};
+      const long long prof_start = p.prof ? clock64() : 0;
       uint32_t a_par = 1, b_par = 1;  // a fresh mbarrier passes a parity-1 wait: the first lap never blocks
       for (int w = cluster_id; w < p.num_items; w += num_clusters) {
         const Item it = decode_item(p, w, CS, rank);
         const int n0 = it.nt * p.BN;
         for (int kc = 0; kc < chunks; ++kc) {
-          for (int s = 0; s < 3; ++s) {
-            ptx::mbar_wait(&a_empty[sa], a_par);
+          for (int al = 0; al < a_loads; ++al) {
+            { PROF_T0(p); ptx::mbar_wait(&a_empty[sa], a_par); PROF_ADD(p, prof_c[0]); }
             ptx::mbar_arrive_expect_tx(&a_full[sa], a_box_bytes * NSPLIT);
             uint8_t* a_dst = a_ring + (size_t)sa * NSPLIT * p.a_slot_bytes;
-            ptx::tma_load_4d(a_dst, &tmA_hi, &a_full[sa], kc * p.KC, it.w0 - 1 + s, it.h0 - 1, it.img);
+            const int wx = p.win ? it.w0 - 1 : it.w0 - 1 + al;
+            ptx::tma_load_4d(a_dst, &tmA_hi, &a_full[sa], kc * p.KC, wx, it.h0 - 1, it.img);
             if (NSPLIT == 2)
-              ptx::tma_load_4d(a_dst + p.a_slot_bytes, &tmA_lo, &a_full[sa], kc * p.KC, it.w0 - 1 + s, it.h0 - 1, it.img);
+              ptx::tma_load_4d(a_dst + p.a_slot_bytes, &tmA_lo, &a_full[sa], kc * p.KC, wx, it.h0 - 1, it.img);
             if (++sa == p.SA) { sa = 0; a_par ^= 1; }
-            for (int r = 0; r < 3; ++r) {
-              ptx::mbar_wait(&b_empty[sb], b_par);   // every CTA of the cluster has drained this slot
+            for (int t = 0; t < a_taps; ++t) {
+              const int s = p.win ? t / 3 : al, r = p.win ? t - 3 * s : t;
+              { PROF_T0(p); ptx::mbar_wait(&b_empty[sb], b_par); PROF_ADD(p, prof_c[1]); }   // every CTA of the cluster has drained this slot
               ptx::mbar_arrive_expect_tx(&b_full[sb], b_box_bytes * NSPLIT);
               uint8_t* b_dst = b_ring + (size_t)sb * NSPLIT * p.b_slot_bytes + (size_t)rank * b_rows_cta * row_bytes;
               const int brow = (r * 3 + s) * p.Cout + n0 + rank * b_rows_cta;
@@ -171,73 +327,130 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
           }
         }
       }
+      if (p.prof) {
+        long long* o = p.prof + (size_t)blockIdx.x * 16;
+        o[0] = prof_c[0]; o[1] = prof_c[1]; o[2] = clock64() - prof_start;
+      }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
+    // The WHOLE warp walks the pipeline (barrier waits, descriptor arithmetic) so that control flow stays warp-uniform
+    // and ptxas keeps the descriptors in uniform registers; one elected lane issues the tcgen05 instructions.  (With the
+    // loop nest under `if (lane == 0)` every operand of every MMA went through an R2UR move and the single thread
+    // needed ~100 cycles per tcgen05.mma -- more than an N <= 128 MMA takes to execute.)
+    {
+      const bool leader = ptx::elect_one();
       const uint32_t idesc = ptx::make_idesc_bf16(128, p.BN, 0, 0);
       const uint32_t idesc2 = ptx::make_idesc_bf16(128, 2 * p.BN, 0, 0);
       const uint32_t sbo = 8u * (uint32_t)row_bytes;
+      // window mode: the 8-pixel row segment of tile row th starts (BW+2) window rows after the one of th-1
+      const uint32_t sbo_a = p.win ? (uint32_t)AW * (uint32_t)row_bytes : sbo;
       // Descriptors differ only in their 14-bit start-address field (smem address >> 4; smem < 256 KB so the
       // field never carries): build the static part once, then a descriptor is one 64-bit add.
       const uint64_t desc_static = ptx::make_smem_desc(0, 16, sbo, (uint32_t)row_bytes);
-      const uint64_t a_ring_desc = desc_static + (uint64_t)(ptx::smem_u32(a_ring) >> 4);
+      const uint64_t a_ring_desc = ptx::make_smem_desc(0, 16, sbo_a, (uint32_t)row_bytes) + (uint64_t)(ptx::smem_u32(a_ring) >> 4);
       const uint64_t b_ring_desc = desc_static + (uint64_t)(ptx::smem_u32(b_ring) >> 4);
       const uint32_t a_slot16 = (uint32_t)(NSPLIT * p.a_slot_bytes) >> 4, a_plane16 = (uint32_t)p.a_slot_bytes >> 4;
       const uint32_t b_slot16 = (uint32_t)(NSPLIT * p.b_slot_bytes) >> 4, b_plane16 = (uint32_t)p.b_slot_bytes >> 4;
-      const uint32_t r_step16 = (uint32_t)(p.BW * row_bytes) >> 4;
+      const uint32_t r_step16 = (uint32_t)(AW * row_bytes) >> 4;   // one tile row down inside the window
+      const uint32_t s_step16 = (uint32_t)row_bytes >> 4;          // one pixel to the right (window mode)
+      const int acc_mode = NSPLIT == 2 ? p.acc_mode : 0;
+      const uint32_t bn = (uint32_t)p.BN;
       int sa = 0, sb = 0, as = 0;
+      long long prof_c[3] = {0, 0, 0};
+      const long long prof_start = p.prof ? clock64() : 0;
       uint32_t a_par = 0, b_par = 0, acc_par[2] = {1, 1};
+      // Only the elected lane waits on barriers and issues; the other lanes just keep the loop nest warp-uniform.
+      bool a_ready = false, a_next_ready = false, b_ready = false;
       for (int w = cluster_id; w < p.num_items; w += num_clusters) {
-        ptx::mbar_wait(&acc_empty[as], acc_par[as]);   // epilogue has drained this accumulator stage
+        if (leader) { PROF_T0(p); ptx::mbar_wait(&acc_empty[as], acc_par[as]); PROF_ADD(p, prof_c[0]); }   // epilogue has drained this accumulator stage
         acc_par[as] ^= 1;
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)as * acc_cols;
         uint32_t accumulate = 0;
         for (int kc = 0; kc < chunks; ++kc) {
-          for (int s = 0; s < 3; ++s) {
-            ptx::mbar_wait(&a_full[sa], a_par);
+          for (int al = 0; al < a_loads; ++al) {
+            if (leader && !a_ready) { PROF_T0(p); ptx::mbar_wait(&a_full[sa], a_par); PROF_ADD(p, prof_c[1]); }
             ptx::tc_fence_after();
             const uint64_t a_desc0 = a_ring_desc + (uint64_t)((uint32_t)sa * a_slot16);
+            const int nsa = sa + 1 == p.SA ? 0 : sa + 1;
+            const uint32_t na_bar = ptx::smem_u32(&a_full[nsa]), na_par = nsa == 0 ? a_par ^ 1 : a_par;
 #pragma unroll 1
-            for (int r = 0; r < 3; ++r) {
-              ptx::mbar_wait(&b_full[sb], b_par);
-              ptx::tc_fence_after();
-              const uint64_t ad = a_desc0 + (uint64_t)((uint32_t)r * r_step16);
-              const uint64_t bd = b_ring_desc + (uint64_t)((uint32_t)sb * b_slot16);
-              // products: (hi,hi) [, (hi,lo), (lo,hi)].  merged: the hi and lo weight planes are contiguous in the slot, so
-              // A_hi x [B_hi | B_lo] is ONE MMA of N = 2*BN (A_hi is read from smem once instead of twice -- the MMA is
-              // shared-memory-read bound at N <= 128); its two column halves are added in the epilogue.
-              if (NSPLIT == 2 && p.merged) {
-#pragma unroll
-                for (int k = 0; k < KSTEPS; ++k) {
-                  ptx::umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc2, accumulate);
-                  ptx::umma_bf16(d_tmem, ad + a_plane16 + 2 * k, bd + 2 * k, idesc, 1);
-                  accumulate = 1;
-                }
+            for (int t = 0; t < a_taps; ++t) {
+              uint64_t ad;
+              if (p.win) {
+                const int s = t / 3, r = t - 3 * s;
+                ad = a_desc0 + (uint64_t)((uint32_t)r * r_step16 + (uint32_t)s * s_step16);
               } else {
-#pragma unroll
-                for (int k = 0; k < KSTEPS; ++k) {
-                  ptx::umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, accumulate);
-                  accumulate = 1;
-                }
-                if (NSPLIT == 2) {
-#pragma unroll
-                  for (int k = 0; k < KSTEPS; ++k) ptx::umma_bf16(d_tmem, ad + 2 * k, bd + b_plane16 + 2 * k, idesc, 1);
-#pragma unroll
-                  for (int k = 0; k < KSTEPS; ++k) ptx::umma_bf16(d_tmem, ad + a_plane16 + 2 * k, bd + 2 * k, idesc, 1);
-                }
+                ad = a_desc0 + (uint64_t)((uint32_t)t * r_step16);
               }
-              if (CS > 1) ptx::umma_commit_mc(&b_empty[sb], kMask);
-              else ptx::umma_commit(&b_empty[sb]);
+              const uint64_t bd = b_ring_desc + (uint64_t)((uint32_t)sb * b_slot16);
+              const int nsb = sb + 1 == p.SB ? 0 : sb + 1;
+              const uint32_t nb_bar = ptx::smem_u32(&b_full[nsb]), nb_par = nsb == 0 ? b_par ^ 1 : b_par;
+              // products: (hi,hi) [, (hi,lo), (lo,hi)].  merged: the hi and lo weight planes are contiguous in the slot, so
+              // A_hi x [B_hi | B_lo] is ONE MMA of N = 2*BN; its two column halves are added in the epilogue.
+              if (leader) {
+                if (!b_ready) { PROF_T0(p); ptx::mbar_wait(&b_full[sb], b_par); PROF_ADD(p, prof_c[2]); }
+                ptx::tc_fence_after();
+                b_ready = false;
+                if (acc_mode == 1) {
+                  const uint32_t fl = tap_merged_probe<KSTEPS>(d_tmem, ad, ad + a_plane16, bd, idesc2, idesc, accumulate, nb_bar,
+                                                               nb_par, na_bar, na_par);
+                  b_ready = (fl & 1u) != 0;
+                  a_next_ready = (fl & 2u) != 0;
+                } else if (acc_mode == 3) {
+#pragma unroll
+                  for (int k = 0; k < KSTEPS; ++k) {
+                    if ((k & 1) == 0) {
+                      ptx::umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, accumulate);                    // hi*hi -> X
+                      ptx::umma_bf16(d_tmem + bn, ad + 2 * k, bd + b_plane16 + 2 * k, idesc, accumulate);   // hi*lo -> Y
+                      ptx::umma_bf16(d_tmem, ad + a_plane16 + 2 * k, bd + 2 * k, idesc, 1);                 // lo*hi -> X
+                    } else {
+                      ptx::umma_bf16(d_tmem + bn, ad + 2 * k, bd + b_plane16 + 2 * k, idesc, 1);            // hi*lo -> Y
+                      ptx::umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, 1);                             // hi*hi -> X
+                      ptx::umma_bf16(d_tmem + bn, ad + a_plane16 + 2 * k, bd + 2 * k, idesc, 1);            // lo*hi -> Y
+                    }
+                    accumulate = 1;
+                  }
+                } else if (acc_mode == 2) {
+#pragma unroll
+                  for (int k = 0; k < KSTEPS; ++k) {
+                    ptx::umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc2, accumulate);                          // blocks 0-1
+                    ptx::umma_bf16(d_tmem + 2 * bn, ad + a_plane16 + 2 * k, bd + 2 * k, idesc, accumulate);      // block 2
+                    accumulate = 1;
+                  }
+                } else {
+#pragma unroll
+                  for (int k = 0; k < KSTEPS; ++k) {
+                    ptx::umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, accumulate);
+                    accumulate = 1;
+                  }
+                  if (NSPLIT == 2) {
+#pragma unroll
+                    for (int k = 0; k < KSTEPS; ++k) ptx::umma_bf16(d_tmem, ad + 2 * k, bd + b_plane16 + 2 * k, idesc, 1);
+#pragma unroll
+                    for (int k = 0; k < KSTEPS; ++k) ptx::umma_bf16(d_tmem, ad + a_plane16 + 2 * k, bd + 2 * k, idesc, 1);
+                  }
+                }
+                if (CS > 1) ptx::umma_commit_mc(&b_empty[sb], kMask);
+                else ptx::umma_commit(&b_empty[sb]);
+              }
+              accumulate = 1;
               if (++sb == p.SB) { sb = 0; b_par ^= 1; }
             }
-            ptx::umma_commit(&a_empty[sa]);
+            if (leader) ptx::umma_commit(&a_empty[sa]);
+            a_ready = a_next_ready;   // the probe fused into this slot's last tap
+            a_next_ready = false;
+            __syncwarp();
             if (++sa == p.SA) { sa = 0; a_par ^= 1; }
           }
         }
-        ptx::umma_commit(&acc_full[as]);
+        if (leader) ptx::umma_commit(&acc_full[as]);
         as ^= 1;
+      }
+      if (p.prof && leader) {
+        long long* o = p.prof + (size_t)blockIdx.x * 16;
+        o[3] = prof_c[0]; o[4] = prof_c[1]; o[5] = prof_c[2]; o[6] = clock64() - prof_start;
       }
     }
   } else {
@@ -250,6 +463,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     const int et = threadIdx.x - 64;         // 0..255
     const int CW = p.BN < 64 ? p.BN : 64;    // staged column chunk (power of two)
     const int ldst = CW + 4;                 // padded staging row (floats)
+    const uint32_t stage_s = ptx::smem_u32(stage);
     float* red = stage + (size_t)128 * ldst; // [4][64][3] floats of scratch
     float* run_stats = red + 4 * 64 * 3;     // [Cout][3] running (n, mean, M2) of this CTA (BatchNorm statistics)
     if (p.stats) {
@@ -266,14 +480,33 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     const int Ho = p.reduce ? p.H / 2 : p.H;
     const int Wo = p.reduce ? p.W / 2 : p.W;
     const int ph_start = pl / oBW, pw_start = pl - ph_start * oBW;
+    const int obw_log = 31 - __clz(oBW);
+    const bool lean_ok = (oBW & (oBW - 1)) == 0;
+    // which compile-time specialisation of the store loop serves this launch (0 = the generic flag-driven loop)
+    int lean_mode = 0;
+    {
+      const bool f32 = p.out_f32 != nullptr, spl = p.out_hi != nullptr && p.out_lo != nullptr;
+      const bool half_split = (p.out_hi != nullptr) != (p.out_lo != nullptr);
+      if (!half_split) {
+        if (!p.mask && !p.ups && p.reduce == 0 && f32 && !spl) lean_mode = 1;
+        else if (!p.mask && !p.ups && p.reduce == 0 && !f32 && spl) lean_mode = 2;
+        else if (!p.mask && p.ups && p.reduce == 0 && !f32 && spl) lean_mode = 3;
+        else if (!p.mask && !p.ups && p.reduce == 1 && !f32 && spl) lean_mode = 4;
+        else if (p.mask && !p.ups && p.reduce == 0 && !f32 && spl) lean_mode = 5;
+        else if (p.mask && !p.ups && p.reduce == 2 && !f32 && spl) lean_mode = 6;
+        else if (!p.mask && !p.ups && p.reduce == 0 && f32 && spl) lean_mode = 7;
+      }
+    }
     const int rep = p.ups ? 2 : 1;
     const int Hs = Ho * rep, Ws = Wo * rep;
     int as = 0;
     uint32_t full_par[2] = {0, 0};
+    long long prof_c[2] = {0, 0};
+    const long long prof_start = p.prof ? clock64() : 0;
     for (int w = cluster_id; w < p.num_items; w += num_clusters) {
       const Item it = decode_item(p, w, CS, rank);
       const int h0 = it.h0, w0 = it.w0, img = it.img;
-      ptx::mbar_wait(&acc_full[as], full_par[as]);
+      { PROF_T0(p); ptx::mbar_wait(&acc_full[as], full_par[as]); PROF_ADD(p, prof_c[0]); }
       full_par[as] ^= 1;
       ptx::tc_fence_after();
       const uint32_t t_acc = tmem_base + (uint32_t)as * acc_cols + ((uint32_t)(lg * 32) << 16);
@@ -284,21 +517,26 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         for (int c0 = colsel * 32; c0 < CW; c0 += 64) {
           uint32_t v[32];
           ptx::tmem_ld_32x32(t_acc + (uint32_t)(cc + c0), v);
-          if (p.merged) {
+          if (p.nsum >= 2) {
             uint32_t v2[32];
             ptx::tmem_ld_32x32(t_acc + (uint32_t)(p.BN + cc + c0), v2);
             ptx::tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+            if (p.nsum == 3) {
+              ptx::tmem_ld_32x32(t_acc + (uint32_t)(2 * p.BN + cc + c0), v2);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+            }
           } else {
             ptx::tmem_ld_wait();
           }
-          float* dst = stage + (size_t)m * ldst + c0;
+          const uint32_t dst = stage_s + (uint32_t)((m * ldst + c0) * 4);
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (c0 + j >= CW) break;  // BN == 16: only half of the 32-column TMEM load is live
-            *reinterpret_cast<uint4*>(dst + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          }
+          for (int j = 0; j < 32; j += 4)
+            if (c0 + j < CW)   // BN == 16: only half of the 32-column TMEM load is live
+              ptx::sts128(dst + j * 4, v[j], v[j + 1], v[j + 2], v[j + 3]);
         }
         if (cc + CW >= p.BN) {
           // last chunk read: hand the accumulator stage back to the MMA warp (one arrive per epilogue warp)
@@ -319,14 +557,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
             float sum = 0.f, mean = 0.f, m2 = 0.f;
             if (c < CW && n_loc > 0) {
               for (int th = r0; th < r1; ++th) {
-                const float* rowp = stage + (size_t)(th * p.BW) * ldst + c;
-                for (int tw = 0; tw < vw; ++tw) sum += rowp[(size_t)tw * ldst];
+                const uint32_t rowp = stage_s + (uint32_t)(((th * p.BW) * ldst + c) * 4);
+                for (int tw = 0; tw < vw; ++tw) sum += ptx::lds32(rowp + (uint32_t)(tw * ldst * 4));
               }
               mean = sum / (float)n_loc;
               for (int th = r0; th < r1; ++th) {
-                const float* rowp = stage + (size_t)(th * p.BW) * ldst + c;
+                const uint32_t rowp = stage_s + (uint32_t)(((th * p.BW) * ldst + c) * 4);
                 for (int tw = 0; tw < vw; ++tw) {
-                  const float d = rowp[(size_t)tw * ldst] - mean;
+                  const float d = ptx::lds32(rowp + (uint32_t)(tw * ldst * 4)) - mean;
                   m2 = fmaf(d, d, m2);
                 }
               }
@@ -369,8 +607,35 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
           const bool affine = p.bias || p.scale;
           const int oh0 = p.reduce ? h0 / 2 : h0;
           const int ow0 = p.reduce ? w0 / 2 : w0;
+          bool done = false;
+          if (lean_ok) {
+            EpiTile e;
+            e.st_addr = stage_s + (uint32_t)(g * 16);
+            e.ldst_b = ldst * 4;
+            e.pl = pl; e.PS = PS; e.npix = oBH * oBW; e.obw_log = obw_log;
+            e.vh = min(oBH, Ho - oh0); e.vw = min(oBW, Wo - ow0);
+            e.BW = p.BW;
+            e.s4 = s4; e.t4 = t4;
+            e.lo_clamp = p.relu ? 0.f : -INFINITY;
+            e.out_base = ((size_t)(img * Hs + oh0 * rep) * Ws + (size_t)(ow0 * rep)) * p.Cout + ch;
+            e.out_row = rep * Ws * p.Cout; e.out_px = rep * p.Cout; e.ws_c = Ws * p.Cout;
+            const int mf = p.mask_ups ? 2 : 1;
+            e.mask_base = ((size_t)(img * mf * Ho + mf * oh0) * (mf * Wo) + (size_t)(mf * ow0)) * p.Cout + ch;
+            e.mask_row = mf * mf * Wo * p.Cout; e.mask_px = mf * p.Cout;
+            done = true;
+            switch (lean_mode) {
+              case 1: epi_store<0, false, false, true, false>(p, e); break;   // fp32 out: train-mode trunk / dgrad into BN
+              case 2: epi_store<0, false, false, false, true>(p, e); break;   // split out: decoder / eval trunk
+              case 3: epi_store<0, false, true, false, true>(p, e); break;    // ... + nearest-2x replicate
+              case 4: epi_store<1, false, false, false, true>(p, e); break;   // ... + 2x2 max-pool
+              case 5: epi_store<0, true, false, false, true>(p, e); break;    // decoder dgrad: ReLU mask
+              case 6: epi_store<2, true, false, false, true>(p, e); break;    // ... + 2x2 sum (grad of Upsample)
+              case 7: epi_store<0, false, false, true, true>(p, e); break;    // both outputs
+              default: done = false;
+            }
+          }
           int ph = ph_start, pw = pw_start;
-          for (int pix = pl; pix < oBH * oBW; pix += PS) {
+          for (int pix = pl; pix < (done ? 0 : oBH * oBW); pix += PS) {
             const int oh = oh0 + ph, ow = ow0 + pw;
             if (oh < Ho && ow < Wo) {
               float4 v;
@@ -434,6 +699,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
       }
       as ^= 1;
     }
+    if (p.prof && et == 0) {
+      long long* o = p.prof + (size_t)blockIdx.x * 16;
+      o[7] = prof_c[0]; o[8] = clock64() - prof_start; o[9] = (p.num_items - cluster_id + num_clusters - 1) / num_clusters;
+    }
     if (p.stats) {
       // one (mean, M2, n) partial per CTA and channel; bias shifts the mean only
       for (int c = et; c < p.Cout; c += kEpiThreads) {
@@ -462,6 +731,18 @@ void pick_tile(int H, int W, int need_even, int* BH, int* BW) {
     const double score = eff - 0.01 * halo;
     if (score > best) { best = score; *BH = bh; *BW = bw; }
   }
+}
+
+// Window mode (one (BH+2) x 10-pixel window per K chunk serves all nine taps) needs BW == 8: every 8-row group of the
+// A operand is then one tile row, and the groups are a uniform (BW+2) window rows apart.  Returns the tile efficiency.
+double pick_window_tile(int H, int W, int need_even, int* BH) {
+  double best = -1.0;
+  for (int bh = 16; bh >= 2; bh -= 2) {
+    (void)need_even;  // every candidate is even
+    const double eff = (double)H * W / ((double)ceil_div(H, bh) * ceil_div(W, 8) * 128.0);
+    if (eff > best * 1.0001) { best = eff; *BH = bh; }
+  }
+  return best;
 }
 
 }  // namespace
@@ -497,6 +778,15 @@ extern "C" int egaze_conv3x3_stats_shape(int Cout, int precise, int* partials, i
   return EGAZE_OK;
 }
 
+static long long* g_conv_prof = nullptr;
+// Debug aid: per-CTA cycle counters of the following egaze_conv3x3_tc launches are written to buf ([grid][16] int64;
+// producer: 0 a_empty wait, 1 b_empty wait, 2 total | MMA: 3 acc_empty, 4 a_full, 5 b_full, 6 total | epilogue: 7 acc_full
+// wait, 8 total, 9 items).  Pass null to switch it off.
+extern "C" int egaze_conv3x3_set_prof(void* buf) {
+  g_conv_prof = (long long*)buf;
+  return EGAZE_OK;
+}
+
 // See include/egaze.h for the contract.
 extern "C" int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, int N, int H, int W,
                                 int Cin_p, int Cout, const float* bias, const float* scale, const float* shift, int relu,
@@ -528,6 +818,29 @@ extern "C" int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* 
   p.N = N; p.H = H; p.W = W; p.Cin_p = Cin_p; p.Cout = Cout;
   p.KC = (Cin_p % 64 == 0) ? 64 : ((Cin_p % 32 == 0) ? 32 : 16);
   pick_tile(H, W, reduce != 0, &p.BH, &p.BW);
+  static int win_env = -1;
+  if (win_env < 0) {
+    const char* e = getenv("EGAZE_CONV_WINDOW");
+    win_env = e ? atoi(e) : 0;
+  }
+  static int win_minsb = 3;
+  if (win_env > 0 && p.KC == 64) {
+    const char* e = getenv("EGAZE_CONV_WINDOW_MINSB");
+    if (e) win_minsb = atoi(e);
+    int wbh = 16;
+    const double eff_w = pick_window_tile(H, W, reduce != 0, &wbh);
+    const double eff_c = (double)H * W / ((double)ceil_div(H, p.BH) * ceil_div(W, p.BW) * 128.0);
+    // ring depth the weight boxes would get next to two 180-row windows (see the smem budget below)
+    const int bn = conv_pick_bn(Cout, precise), ns = precise ? 2 : 1;
+    const int stage_b = ((128 * ((bn < 64 ? bn : 64) + 4) * 4 + 4 * 64 * 3 * 4 + (stats ? Cout * 3 * 4 : 0) + 1023) / 1024) * 1024;
+    const int sb_w = (222 * 1024 - stage_b - 2 * ns * 23552) / (ns * bn * 128);
+    if (eff_w >= eff_c * 0.999 && sb_w >= win_minsb) {
+      p.win = 1;
+      p.win_bo = win_env == 2 ? 1 : 0;
+      p.BH = wbh;
+      p.BW = 8;
+    }
+  }
   p.nsplit = precise ? 2 : 1;
   // N tile: largest of 128/64/32/16 dividing Cout (256 only in fast mode where the rings fit).
   p.BN = conv_pick_bn(Cout, precise);
@@ -541,6 +854,8 @@ extern "C" int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* 
   const int row_bytes = p.KC * 2;
   int a_rows = (p.BH + 2) * p.BW;
   if (a_rows < 2 * p.BW + 128) a_rows = 2 * p.BW + 128;
+  // window mode: the MMA always walks 16 row groups, (BW+2) window rows apart, from up to 2 rows + 2 pixels in
+  if (p.win) a_rows = 17 * (p.BW + 2) + 2 + 8;
   p.a_slot_bytes = ((a_rows * row_bytes + 1023) / 1024) * 1024;
   p.b_slot_bytes = ((p.BN * row_bytes + 1023) / 1024) * 1024;
   const int CW = p.BN < 64 ? p.BN : 64;
@@ -558,11 +873,30 @@ extern "C" int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* 
   if (sb > 6) sb = 6;
   EGAZE_CHECK_ARG(sb >= 2, "conv3x3_tc: tile does not fit shared memory");
   p.SB = sb;
-  // merged hi|lo weight MMA needs the two planes back to back (no slot padding) and 2*BN accumulator columns x 2 stages
-  p.merged = (precise && p.b_slot_bytes == p.BN * row_bytes && 4 * p.BN <= 512 && 2 * p.BN <= 256) ? 1 : 0;
+  // accumulator layout (see ConvTcParams::acc_mode).  The N = 2*BN MMA of modes 1/2 needs the two weight planes back to
+  // back in the slot (no padding) and 2*BN <= 256.
   {
-    const char* e = getenv("EGAZE_CONV_MERGED");
-    if (e && atoi(e) == 0) p.merged = 0;
+    static int mode_env = -2;
+    if (mode_env == -2) {
+      const char* e = getenv("EGAZE_CONV_ACCMODE");
+      mode_env = e ? atoi(e) : -1;
+    }
+    const bool can_merge = p.b_slot_bytes == p.BN * row_bytes && 2 * p.BN <= 256;
+    int mode = 0;
+    if (precise) {
+      // measured (B=32 SP layers): mode 1 beats 2 and 3 -- fewer, larger MMAs win; the extra smem operand reads of mode 3
+      // cost more than any accumulator interleaving gains
+      mode = can_merge ? 1 : 3;
+      if (mode_env >= 0) mode = mode_env;
+      if ((mode == 1 || mode == 2) && !can_merge) mode = 3;
+      if (mode == 2 && p.BN > 64) mode = 1;
+    }
+    p.acc_mode = mode;
+    p.nsum = mode == 0 ? 1 : (mode == 2 ? 3 : 2);
+    int cols = p.nsum * p.BN;
+    p.acc_cols = 32;
+    while (p.acc_cols < cols) p.acc_cols *= 2;
+    EGAZE_CHECK_ARG(2 * p.acc_cols <= 512, "conv3x3_tc: accumulators do not fit TMEM (BN=%d mode=%d)", p.BN, mode);
   }
   p.stage_off = p.SA * p.nsplit * p.a_slot_bytes + p.SB * p.nsplit * p.b_slot_bytes;
   const size_t smem = (size_t)p.stage_off + stage_bytes + 1024;  // + alignment slack
@@ -571,12 +905,13 @@ extern "C" int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* 
   p.mask_ups = mask_ups;
   p.out_f32 = out_f32; p.out_hi = (__nv_bfloat16*)out_hi; p.out_lo = (__nv_bfloat16*)out_lo;
   p.stats = stats; p.stats_cnt = stats_cnt;
+  p.prof = g_conv_prof;
 
   CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
   {
     uint64_t dims[4] = {(uint64_t)Cin_p, (uint64_t)W, (uint64_t)H, (uint64_t)N};
     uint64_t str[3] = {(uint64_t)Cin_p * 2, (uint64_t)W * Cin_p * 2, (uint64_t)H * W * Cin_p * 2};
-    uint32_t box[4] = {(uint32_t)p.KC, (uint32_t)p.BW, (uint32_t)(p.BH + 2), 1};
+    uint32_t box[4] = {(uint32_t)p.KC, (uint32_t)(p.win ? p.BW + 2 : p.BW), (uint32_t)(p.BH + 2), 1};
     int rc = egaze_encode_tmap(&tmA_hi, x_hi, 4, dims, str, box, row_bytes, 2);
     if (rc) return rc;
     rc = egaze_encode_tmap(&tmA_lo, precise ? x_lo : x_hi, 4, dims, str, box, row_bytes, 2);

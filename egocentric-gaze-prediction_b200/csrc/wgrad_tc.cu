@@ -4,12 +4,16 @@
 //
 // (autograd of nn.Conv2d on the reference hot path: loss.backward() in SP.py:136, spatialstream.py:140.)
 //
-// GEMM view per CTA: M = 128 output channels, N = 64 input channels, K = pixels of the spatial tiles this CTA owns
-// (split-K over tiles), one fp32 TMEM accumulator per vertical tap r (3 x 64 columns).  Both operands are
+// GEMM view per CTA: M = 128 output channels, N = 3 vertical taps x 64 input channels = 192, K = pixels of the spatial
+// tiles this CTA owns (split-K over tiles).  The three taps read the SAME dY tile, so their X operands (the window at row
+// offsets 0, BW, 2*BW) are concatenated along N in one MMA: 64-channel chunks LBO = BW*128 bytes apart.  Both operands are
 // "MN-major" for the tensor core: dY^T tile [K px][64 co] and X window [K px][64 ci] are exactly what TMA delivers
 // from NHWC (pixel rows of 128 B, SWIZZLE_128B), so no transposes are materialised.  Like the forward kernel, the
 // X window for horizontal tap s is fetched once with a (BH+2)-row halo and the three vertical taps read it at a row
-// offset of r*BW rows.  precise mode: dYhi*Xhi + dYhi*Xlo + dYlo*Xhi.
+// offset of r*BW rows.  precise mode: dYhi*Xhi + dYhi*Xlo + dYlo*Xhi as three N = 192 MMAs per K step, alternating between
+// two accumulator blocks D1 / D2 (back-to-back MMAs into the same TMEM columns serialise, tools/probe_mma_rate.cu); the
+// epilogue adds D1 + D2.  Cout == 64: the M rows are [dY_hi ; dY_lo] of the same 64 channels and two MMAs do all four
+// products.
 //
 // Grid: x = split-K slice, y = (co-tile, ci-tile, s).  Epilogue: TMEM -> registers -> vector fp32 atomics into the
 // packed [9][Cout][Cin_p] accumulator (zeroed by the caller), which egaze_unpack_wgrad turns into the OIHW .grad.
@@ -25,6 +29,8 @@ struct WgradParams {
   int tiles_h, tiles_w, total_tiles;
   int co_tiles, ci_tiles;
   int m_chunks;        // 64-channel chunks of dY actually present (1 when Cout == 64, else 2)
+  int stacked;         // Cout == 64, precise: the M = 128 rows are [dY_hi ; dY_lo] of the same 64 channels, so ONE MMA against
+                       // [X_hi | X_lo] yields all four hi/lo products (the epilogue adds the two lane halves into the same dW rows)
   int nsplit;
   int stage_bytes, dy_plane_bytes, x_plane_bytes;
   float* dwp;          // [9][Cout][Cin_p]
@@ -59,7 +65,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid_constan
   }
   // precise: A_hi x [X_hi | X_lo] is ONE MMA of N = 128 (the X planes are 64-channel chunks LBO = plane stride apart),
   // so each tap owns 128 accumulator columns whose halves are added in the epilogue; fast: 64 columns per tap.
-  constexpr uint32_t kAccCols = NSPLIT == 2 ? 128 : 64;
+  constexpr uint32_t kD2 = 256;                       // column offset of the second accumulator block (precise)
   constexpr uint32_t kTmemCols = NSPLIT == 2 ? 512 : 256;
   if (warp == 1) {
     ptx::tmem_alloc(&tmem_base_smem, kTmemCols);
@@ -90,7 +96,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid_constan
         for (int c = 0; c < p.m_chunks; ++c) {
           ptx::tma_load_4d(base + c * dy_box_bytes, &tmY_hi, &full[st], co0 + 64 * c, w0, h0, img);
           if (NSPLIT == 2)
-            ptx::tma_load_4d(base + p.dy_plane_bytes + c * dy_box_bytes, &tmY_lo, &full[st], co0 + 64 * c, w0, h0, img);
+            ptx::tma_load_4d(base + (p.stacked ? dy_box_bytes : (uint32_t)p.dy_plane_bytes + c * dy_box_bytes), &tmY_lo, &full[st],
+                             co0 + 64 * c, w0, h0, img);
         }
         uint8_t* xb = base + (size_t)NSPLIT * p.dy_plane_bytes;
         ptx::tma_load_4d(xb, &tmX_hi, &full[st], ci0, w0 - 1 + s, h0 - 1, img);
@@ -99,17 +106,19 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = ptx::make_idesc_bf16(128, 64, 1, 1);    // both operands MN-major
-      const uint32_t idesc2 = ptx::make_idesc_bf16(128, 128, 1, 1);  // N = [X_hi | X_lo]
+    // The whole warp walks the pipeline so that the descriptors stay in uniform registers; one elected lane issues
+    // (see conv3x3_tc.cu: a loop nest under `if (lane == 0)` costs ~100 cycles of R2UR traffic per tcgen05.mma).
+    {
+      const bool leader = ptx::elect_one();
+      const uint32_t idesc = ptx::make_idesc_bf16(128, 192, 1, 1);   // both operands MN-major, N = 3 taps x 64 channels
       // MN-major SWIZZLE_128B canonical layout: 64 channels (128 B) contiguous, 8 pixel rows per 1024 B atom (SBO),
-      // next 64-channel chunk LBO bytes away.
+      // next 64-channel chunk LBO bytes away: the other dY chunk for A, the window shifted by one tile row for B.
       const uint64_t a_static = ptx::make_smem_desc(0, dy_box_bytes, 1024, 128);
-      const uint64_t b_static = ptx::make_smem_desc(0, NSPLIT == 2 ? (uint32_t)p.x_plane_bytes : x_box_bytes, 1024, 128);
+      const uint64_t b_static = ptx::make_smem_desc(0, (uint32_t)p.BW * 128u, 1024, 128);
       const int ksteps = KP / 16;
       int st = 0;
       uint32_t par = 0;
-      uint32_t acc[3] = {0, 0, 0};
+      uint32_t acc = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         ptx::mbar_wait(&full[st], par);
         ptx::tc_fence_after();
@@ -117,26 +126,34 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid_constan
         const uint64_t a_hi = a_static + (uint64_t)(base >> 4);
         const uint64_t a_lo = a_hi + (uint64_t)((uint32_t)p.dy_plane_bytes >> 4);
         const uint64_t b_hi = b_static + (uint64_t)((base + (uint32_t)NSPLIT * p.dy_plane_bytes) >> 4);
-        const uint32_t r_step16 = (uint32_t)(p.BW * 128) >> 4;
-#pragma unroll 1
-        for (int r = 0; r < 3; ++r) {
-          const uint32_t d = tmem_base + (uint32_t)r * kAccCols;
-          const uint64_t br_hi = b_hi + (uint64_t)(r * r_step16);
+        const uint64_t b_lo = b_hi + (uint64_t)((uint32_t)p.x_plane_bytes >> 4);
+        if (leader) {
+#pragma unroll 2
           for (int k = 0; k < ksteps; ++k) {  // 16 pixel rows = 2048 B per K step
             const uint64_t ko = (uint64_t)(k * 128);
-            if (NSPLIT == 2) {
-              ptx::umma_bf16(d, a_hi + ko, br_hi + ko, idesc2, acc[r]);   // dY_hi x [X_hi | X_lo]
-              ptx::umma_bf16(d, a_lo + ko, br_hi + ko, idesc, 1);         // dY_lo x X_hi
+            const uint32_t first = acc | (uint32_t)k;   // 0 only for the very first K step of this CTA
+            if (NSPLIT == 1) {
+              ptx::umma_bf16(tmem_base, a_hi + ko, b_hi + ko, idesc, first);
+            } else if (p.stacked) {
+              ptx::umma_bf16(tmem_base, a_hi + ko, b_hi + ko, idesc, first);         // [dY_hi ; dY_lo] x X_hi -> D1
+              ptx::umma_bf16(tmem_base + kD2, a_hi + ko, b_lo + ko, idesc, first);   // [dY_hi ; dY_lo] x X_lo -> D2
+            } else if ((k & 1) == 0) {
+              ptx::umma_bf16(tmem_base, a_hi + ko, b_hi + ko, idesc, first);         // hi*hi -> D1
+              ptx::umma_bf16(tmem_base + kD2, a_hi + ko, b_lo + ko, idesc, first);   // hi*lo -> D2
+              ptx::umma_bf16(tmem_base, a_lo + ko, b_hi + ko, idesc, 1);             // lo*hi -> D1
             } else {
-              ptx::umma_bf16(d, a_hi + ko, br_hi + ko, idesc, acc[r]);
+              ptx::umma_bf16(tmem_base + kD2, a_hi + ko, b_lo + ko, idesc, 1);       // hi*lo -> D2
+              ptx::umma_bf16(tmem_base, a_hi + ko, b_hi + ko, idesc, 1);             // hi*hi -> D1
+              ptx::umma_bf16(tmem_base + kD2, a_lo + ko, b_hi + ko, idesc, 1);       // lo*hi -> D2
             }
-            acc[r] = 1;
           }
+          ptx::umma_commit(&empty[st]);
         }
-        ptx::umma_commit(&empty[st]);
+        acc = 1;
+        __syncwarp();
         if (++st == 2) { st = 0; par ^= 1; }
       }
-      ptx::umma_commit(&acc_full);
+      if (leader) ptx::umma_commit(&acc_full);
     }
   } else {
     // epilogue: thread = output-channel row; 64 consecutive ci per tap -> float4 atomics
@@ -149,18 +166,19 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid_constan
 #pragma unroll 1
       for (int c0 = 0; c0 < 64; c0 += 32) {
         uint32_t v[32];
-        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(r * kAccCols + c0), v);
+        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(r * 64 + c0), v);
         if (NSPLIT == 2) {
           uint32_t v2[32];
-          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(r * kAccCols + 64 + c0), v2);
+          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + kD2 + (uint32_t)(r * 64 + c0), v2);
           ptx::tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
         } else {
           ptx::tmem_ld_wait();
         }
-        if (any_tile && co0 + m < p.Cout) {
-          float* dst = p.dwp + ((size_t)(r * 3 + s) * p.Cout + co0 + m) * p.Cin_p + ci0 + c0;
+        const int co = p.stacked ? (m & 63) : co0 + m;   // stacked: lanes 64..127 hold the dY_lo products of channels 0..63
+        if (any_tile && co < p.Cout) {
+          float* dst = p.dwp + ((size_t)(r * 3 + s) * p.Cout + co) * p.Cin_p + ci0 + c0;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             float4 val = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
@@ -207,6 +225,11 @@ extern "C" int egaze_wgrad3x3_tc(const void* x_hi, const void* x_lo, const void*
   p.co_tiles = ceil_div(Cout, 128); p.ci_tiles = Cin_p / 64;
   p.m_chunks = Cout >= 128 ? 2 : 1;
   p.nsplit = precise ? 2 : 1;
+  p.stacked = (precise && Cout == 64) ? 1 : 0;
+  {
+    const char* e = getenv("EGAZE_WGRAD_STACKED");
+    if (e && atoi(e) == 0) p.stacked = 0;
+  }
   const int KP = p.BH * p.BW;
   p.dy_plane_bytes = 2 * KP * 128;                                  // room for both 64-channel chunks
   p.x_plane_bytes = ((p.BH + 2) * p.BW * 128 + 1023) / 1024 * 1024;

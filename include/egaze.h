@@ -47,6 +47,9 @@ int egaze_conv3x3_tiles(int N, int H, int W, int need_even, int* num_tiles, int*
 /* BatchNorm-statistics workspace of egaze_conv3x3_tc: stats [partials][2][Cout], stats_cnt [partials][cnt_stride] (zeroed by
  * the caller); one (mean, M2, n) partial per persistent CTA. */
 int egaze_conv3x3_stats_shape(int Cout, int precise, int* partials, int* cnt_stride, int* cnt_div);
+/* Debug aid (tools/conv_prof.py): per-CTA cycle counters of the following egaze_conv3x3_tc launches go to buf
+ * ([grid][16] int64 on the device); null switches it off.  Not used on the product path. */
+int egaze_conv3x3_set_prof(void* buf);
 /* y = epilogue(conv3x3(x, w)):  v = acc + bias; v = v*scale + shift; relu; 2x2 reduce (1 max = MaxPool2d utils.py:68,
  * 2 sum = grad of nn.Upsample); mask (zero where mask <= 0: ReLU backward; mask_ups: the mask tensor is stored 2x upsampled);
  * 2x nearest replicate (ups: model_SP.py:16,20,24,27).

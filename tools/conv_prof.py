@@ -1,0 +1,50 @@
+"""Per-role cycle accounting of the tcgen05 conv kernel (egaze_conv3x3_set_prof) for a few SP layers at B=32.
+
+Prints, per layer, the average over CTAs of: cycles per work item, and the share of its time each role spent
+waiting on each barrier (producer: A/B slot free; MMA issuer: accumulator free, A landed, B landed; epilogue:
+accumulator ready)."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "egocentric-gaze-prediction_b200"))
+import torch
+from egaze import ops
+from egaze._lib import call
+
+LAYERS = [  # name, N, H, W, Cin, Cout, kwargs
+    ("trunk 64->64 @224 f32+stats", 32, 224, 224, 64, 64, dict(want_f32=True, want_split=False, stats=True)),
+    ("dgrad 64->64 @224 f32", 32, 224, 224, 64, 64, dict(want_f32=True, want_split=False)),
+    ("dec 64->64 @224 relu split", 32, 224, 224, 64, 64, dict(relu=True)),
+    ("dec 128->64 @224 relu split", 32, 224, 224, 128, 64, dict(relu=True)),
+    ("trunk 64->128 @112 f32+stats", 32, 112, 112, 64, 128, dict(want_f32=True, want_split=False, stats=True)),
+    ("trunk 128->128 @112 f32+stats", 32, 112, 112, 128, 128, dict(want_f32=True, want_split=False, stats=True)),
+    ("trunk 256->256 @56 f32+stats", 32, 56, 56, 256, 256, dict(want_f32=True, want_split=False, stats=True)),
+    ("dec 512->256 @56 relu split", 32, 56, 56, 512, 256, dict(relu=True)),
+    ("trunk 512->512 @28 f32+stats", 32, 28, 28, 512, 512, dict(want_f32=True, want_split=False, stats=True)),
+    ("trunk 512->512 @14 f32+stats", 32, 14, 14, 512, 512, dict(want_f32=True, want_split=False, stats=True)),
+]
+prof = torch.zeros(160, 16, dtype=torch.int64, device="cuda")
+for name, N, H, W, Ci, Co, kw in LAYERS:
+    x = torch.randn(N, Ci, H, W, device="cuda")
+    w = torch.randn(Co, Ci, 3, 3, device="cuda") * 0.02
+    b = torch.zeros(Co, device="cuda")
+    act = ops.to_split(x)
+    wp = ops.pack_cache.get(w, 0, cols_p=act.Cp)
+    for _ in range(2):
+        ops.conv3x3(act, wp, bias=b, **kw)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); ops.conv3x3(act, wp, bias=b, **kw); e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    prof.zero_()
+    call("egaze_conv3x3_set_prof", prof)
+    ops.conv3x3(act, wp, bias=b, **kw)
+    torch.cuda.synchronize()
+    call("egaze_conv3x3_set_prof", None)
+    p = prof[prof[:, 9] > 0].double()
+    items = p[:, 9].mean().item()
+    tot = p[:, 6].mean().item()
+    f = lambda c, d: 100.0 * (p[:, c] / p[:, d]).mean().item()
+    fl = 2.0 * N * H * W * Co * Ci * 9
+    print("%-32s %.3f ms %6.1f TF/s | %5.1f items/CTA %7.0f clk/item | producer waits A-free %4.1f%% B-free %4.1f%% | "
+          "MMA waits acc-free %4.1f%% A-landed %4.1f%% B-landed %4.1f%% | epilogue waits acc-ready %4.1f%%"
+          % (name, ms, fl / ms / 1e9, items, tot / items, f(0, 2), f(1, 2), f(3, 6), f(4, 6), f(5, 6), f(7, 8)))
