@@ -98,47 +98,52 @@ __global__ void col_stats_kernel(const float* __restrict__ x, int rows, int C, i
 }
 
 // y = relu?(x*scale+shift), optional 2x2 max pool; x NHWC fp32 [N,H,W,C]; outputs NHWC [N,Ho,Wo,C].
-__global__ void bn_apply_kernel(const float* __restrict__ x, int N, int H, int W, int C, const float* __restrict__ scale,
-                                const float* __restrict__ shift, int relu, int pool, float* __restrict__ out_f32,
-                                __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
+// A thread keeps ONE float4 channel group (its scale / shift live in registers) and strides over pixels; all index
+// arithmetic is 32-bit (the entry point checks the element count), with no division on the un-pooled path.
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const float* __restrict__ x, int N, int H, int W, int C, const float* __restrict__ scale,
+                const float* __restrict__ shift, int relu, int pool, float* __restrict__ out_f32,
+                __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
   const int Ho = pool ? H / 2 : H, Wo = pool ? W / 2 : W;
   const int C4 = C / 4;
-  const size_t total = (size_t)N * Ho * Wo * C4;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c4 = (int)(i % C4);
-    size_t pix = i / C4;
-    const int ow = (int)(pix % Wo);
-    pix /= Wo;
-    const int oh = (int)(pix % Ho);
-    const int n = (int)(pix / Ho);
+  const int tpp = C4 < 256 ? C4 : 256;               // threads per pixel
+  const int ppb = 256 / tpp;                         // pixels per block sweep
+  const int lane_c = threadIdx.x % tpp, pl = threadIdx.x / tpp;
+  if (pl >= ppb) return;                             // C/4 does not divide 256: the spare threads idle
+  const uint32_t npix = (uint32_t)N * Ho * Wo;
+  const float lo_clamp = relu ? 0.f : -INFINITY;
+  for (int c4 = lane_c; c4 < C4; c4 += tpp) {
     const float4 sc = *reinterpret_cast<const float4*>(scale + c4 * 4);
     const float4 sh = *reinterpret_cast<const float4*>(shift + c4 * 4);
-    float4 v;
-    if (!pool) {
-      const float4 a = *reinterpret_cast<const float4*>(x + (((size_t)n * H + oh) * W + ow) * C + c4 * 4);
-      v.x = fmaf(a.x, sc.x, sh.x); v.y = fmaf(a.y, sc.y, sh.y); v.z = fmaf(a.z, sc.z, sh.z); v.w = fmaf(a.w, sc.w, sh.w);
-    } else {
-      v = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    for (uint32_t pix = blockIdx.x * ppb + pl; pix < npix; pix += gridDim.x * ppb) {
+      float4 v;
+      if (!pool) {
+        const float4 a = *reinterpret_cast<const float4*>(x + (size_t)pix * C + c4 * 4);
+        v.x = fmaf(a.x, sc.x, sh.x); v.y = fmaf(a.y, sc.y, sh.y); v.z = fmaf(a.z, sc.z, sh.z); v.w = fmaf(a.w, sc.w, sh.w);
+      } else {
+        const uint32_t ow = pix % Wo, t = pix / Wo, oh = t % Ho, n = t / Ho;
+        const float* src = x + ((size_t)(n * H + 2 * oh) * W + 2 * ow) * C + c4 * 4;
+        v = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
 #pragma unroll
-      for (int dy = 0; dy < 2; ++dy)
+        for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
-        for (int dx = 0; dx < 2; ++dx) {
-          const float4 a =
-              *reinterpret_cast<const float4*>(x + (((size_t)n * H + 2 * oh + dy) * W + 2 * ow + dx) * C + c4 * 4);
-          v.x = fmaxf(v.x, fmaf(a.x, sc.x, sh.x));
-          v.y = fmaxf(v.y, fmaf(a.y, sc.y, sh.y));
-          v.z = fmaxf(v.z, fmaf(a.z, sc.z, sh.z));
-          v.w = fmaxf(v.w, fmaf(a.w, sc.w, sh.w));
-        }
-    }
-    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-    const size_t o = i * 4;
-    if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = v;
-    if (out_hi) {
-      __nv_bfloat16 h[4], l[4];
-      split_bf16(v.x, h[0], l[0]); split_bf16(v.y, h[1], l[1]); split_bf16(v.z, h[2], l[2]); split_bf16(v.w, h[3], l[3]);
-      *reinterpret_cast<uint2*>(out_hi + o) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
-      if (out_lo) *reinterpret_cast<uint2*>(out_lo + o) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+          for (int dx = 0; dx < 2; ++dx) {
+            const float4 a = *reinterpret_cast<const float4*>(src + ((size_t)dy * W + dx) * C);
+            v.x = fmaxf(v.x, fmaf(a.x, sc.x, sh.x));
+            v.y = fmaxf(v.y, fmaf(a.y, sc.y, sh.y));
+            v.z = fmaxf(v.z, fmaf(a.z, sc.z, sh.z));
+            v.w = fmaxf(v.w, fmaf(a.w, sc.w, sh.w));
+          }
+      }
+      v.x = fmaxf(v.x, lo_clamp); v.y = fmaxf(v.y, lo_clamp); v.z = fmaxf(v.z, lo_clamp); v.w = fmaxf(v.w, lo_clamp);
+      const size_t o = (size_t)pix * C + c4 * 4;
+      if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = v;
+      if (out_hi) {
+        uint2 hi2, lo2;
+        split_bf16x4(v, hi2, lo2);
+        *reinterpret_cast<uint2*>(out_hi + o) = hi2;
+        if (out_lo) *reinterpret_cast<uint2*>(out_lo + o) = lo2;
+      }
     }
   }
 }
@@ -165,19 +170,19 @@ struct BnSrc {
   float xh[4][4];
 };
 
-__device__ __forceinline__ void bn_route(const float* __restrict__ raw, int H, int W, int C, int n, int oh, int ow,
-                                         int c4, int pool, int relu, const float4& g, const float4& sc,
-                                         const float4& sh, const float4& mean, const float4& invstd, BnSrc& o) {
+// src: the (top-left) source pixel's channel group; row_pitch: floats between image rows of raw.
+__device__ __forceinline__ void bn_route(const float* __restrict__ src, size_t row_pitch, int C, int pool, int relu,
+                                         const float4& g, const float4& sc, const float4& sh, const float4& mean,
+                                         const float4& invstd, BnSrc& o) {
   const int np = pool ? 4 : 1;
   float z[4][4];
+  const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+  const float mv[4] = {mean.x, mean.y, mean.z, mean.w}, iv[4] = {invstd.x, invstd.y, invstd.z, invstd.w};
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     if (q < np) {
-      const int h = pool ? 2 * oh + (q >> 1) : oh, w = pool ? 2 * ow + (q & 1) : ow;
-      const float4 a = *reinterpret_cast<const float4*>(raw + (((size_t)n * H + h) * W + w) * C + c4 * 4);
+      const float4 a = *reinterpret_cast<const float4*>(src + (size_t)(q >> 1) * row_pitch + (size_t)(q & 1) * C);
       const float av[4] = {a.x, a.y, a.z, a.w};
-      const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
-      const float mv[4] = {mean.x, mean.y, mean.z, mean.w}, iv[4] = {invstd.x, invstd.y, invstd.z, invstd.w};
 #pragma unroll
       for (int l = 0; l < 4; ++l) {
         z[q][l] = fmaf(av[l], scv[l], shv[l]);
@@ -212,14 +217,19 @@ __global__ void bn_bwd_reduce_kernel(const float* __restrict__ raw, const float*
   const float4 sc = *reinterpret_cast<const float4*>(scale + c4 * 4), sh = *reinterpret_cast<const float4*>(shift + c4 * 4);
   const float4 mn = *reinterpret_cast<const float4*>(mean + c4 * 4), iv = *reinterpret_cast<const float4*>(invstd + c4 * 4);
   float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
-  const size_t npix = (size_t)N * Ho * Wo;
-  for (size_t pix = (size_t)blockIdx.x * blockDim.y + threadIdx.y; pix < npix; pix += (size_t)gridDim.x * blockDim.y) {
-    const int ow = (int)(pix % Wo);
-    const int oh = (int)((pix / Wo) % Ho);
-    const int n = (int)(pix / ((size_t)Wo * Ho));
-    const float4 gg = *reinterpret_cast<const float4*>(g + pix * C + c4 * 4);
+  const uint32_t npix = (uint32_t)N * Ho * Wo;
+  const size_t row_pitch = (size_t)W * C;
+  for (uint32_t pix = blockIdx.x * blockDim.y + threadIdx.y; pix < npix; pix += gridDim.x * blockDim.y) {
+    const float* src;
+    if (pool) {
+      const uint32_t ow = pix % Wo, t = pix / Wo, oh = t % Ho, n = t / Ho;
+      src = raw + ((size_t)(n * H + 2 * oh) * W + 2 * ow) * C + c4 * 4;
+    } else {
+      src = raw + (size_t)pix * C + c4 * 4;
+    }
+    const float4 gg = *reinterpret_cast<const float4*>(g + (size_t)pix * C + c4 * 4);
     BnSrc o;
-    bn_route(raw, H, W, C, n, oh, ow, c4, pool, relu, gg, sc, sh, mn, iv, o);
+    bn_route(src, row_pitch, C, pool, relu, gg, sc, sh, mn, iv, o);
     const int np = pool ? 4 : 1;
 #pragma unroll
     for (int q = 0; q < 4; ++q)
@@ -265,48 +275,62 @@ bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, float
   }
 }
 
-// draw = gamma*invstd * (gz - dbeta/n - xhat*dgamma/n)  -> NHWC split-bf16 (and/or fp32) at the conv-output resolution
-__global__ void bn_bwd_apply_kernel(const float* __restrict__ raw, const float* __restrict__ g, int N, int H, int W, int C,
-                                    const float* __restrict__ scale, const float* __restrict__ shift,
-                                    const float* __restrict__ mean, const float* __restrict__ invstd,
-                                    const float* __restrict__ dgamma, const float* __restrict__ dbeta, int pool, int relu,
-                                    float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_hi,
-                                    __nv_bfloat16* __restrict__ out_lo) {
+// draw = gamma*invstd * (gz - dbeta/n - xhat*dgamma/n)  -> NHWC split-bf16 (and/or fp32) at the conv-output resolution.
+// Same thread mapping as bn_apply_kernel: one float4 channel group per thread, its six per-channel constants in registers.
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const float* __restrict__ raw, const float* __restrict__ g, int N, int H, int W, int C,
+                    const float* __restrict__ scale, const float* __restrict__ shift,
+                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                    const float* __restrict__ dgamma, const float* __restrict__ dbeta, int pool, int relu,
+                    float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_hi,
+                    __nv_bfloat16* __restrict__ out_lo) {
   const int Ho = pool ? H / 2 : H, Wo = pool ? W / 2 : W;
   const int C4 = C / 4;
+  const int tpp = C4 < 256 ? C4 : 256;
+  const int ppb = 256 / tpp;
+  const int lane_c = threadIdx.x % tpp, pl = threadIdx.x / tpp;
+  if (pl >= ppb) return;
   const float inv_n = 1.f / (float)((size_t)N * H * W);
-  const size_t total = (size_t)N * Ho * Wo * C4;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c4 = (int)(i % C4);
-    const size_t pix = i / C4;
-    const int ow = (int)(pix % Wo);
-    const int oh = (int)((pix / Wo) % Ho);
-    const int n = (int)(pix / ((size_t)Wo * Ho));
+  const uint32_t npix = (uint32_t)N * Ho * Wo;
+  const size_t row_pitch = (size_t)W * C;
+  const int np = pool ? 4 : 1;
+  for (int c4 = lane_c; c4 < C4; c4 += tpp) {
     const float4 sc = *reinterpret_cast<const float4*>(scale + c4 * 4), sh = *reinterpret_cast<const float4*>(shift + c4 * 4);
     const float4 mn = *reinterpret_cast<const float4*>(mean + c4 * 4), iv = *reinterpret_cast<const float4*>(invstd + c4 * 4);
     const float4 dg = *reinterpret_cast<const float4*>(dgamma + c4 * 4), db = *reinterpret_cast<const float4*>(dbeta + c4 * 4);
-    const float4 gg = *reinterpret_cast<const float4*>(g + pix * C + c4 * 4);
-    BnSrc o;
-    bn_route(raw, H, W, C, n, oh, ow, c4, pool, relu, gg, sc, sh, mn, iv, o);
-    const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, dgv[4] = {dg.x, dg.y, dg.z, dg.w}, dbv[4] = {db.x, db.y, db.z, db.w};
-    const int np = pool ? 4 : 1;
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-      if (q < np) {
-        const int h = pool ? 2 * oh + (q >> 1) : oh, w = pool ? 2 * ow + (q & 1) : ow;
-        float v[4];
-#pragma unroll
-        for (int l = 0; l < 4; ++l) v[l] = scv[l] * (o.gz[q][l] - dbv[l] * inv_n - o.xh[q][l] * dgv[l] * inv_n);
-        const size_t off = (((size_t)n * H + h) * W + w) * C + c4 * 4;
-        if (out_f32) *reinterpret_cast<float4*>(out_f32 + off) = make_float4(v[0], v[1], v[2], v[3]);
-        if (out_hi) {
-          __nv_bfloat16 hh[4], ll[4];
-#pragma unroll
-          for (int l = 0; l < 4; ++l) split_bf16(v[l], hh[l], ll[l]);
-          *reinterpret_cast<uint2*>(out_hi + off) = make_uint2(pack_bf16x2(hh[0], hh[1]), pack_bf16x2(hh[2], hh[3]));
-          if (out_lo) *reinterpret_cast<uint2*>(out_lo + off) = make_uint2(pack_bf16x2(ll[0], ll[1]), pack_bf16x2(ll[2], ll[3]));
-        }
+    const float scv[4] = {sc.x, sc.y, sc.z, sc.w};
+    // v = sc * (gz - db/n - xh * dg/n) = sc*gz - kb - xh*kg
+    const float kb[4] = {sc.x * db.x * inv_n, sc.y * db.y * inv_n, sc.z * db.z * inv_n, sc.w * db.w * inv_n};
+    const float kg[4] = {sc.x * dg.x * inv_n, sc.y * dg.y * inv_n, sc.z * dg.z * inv_n, sc.w * dg.w * inv_n};
+    for (uint32_t pix = blockIdx.x * ppb + pl; pix < npix; pix += gridDim.x * ppb) {
+      size_t off0;
+      if (pool) {
+        const uint32_t ow = pix % Wo, t = pix / Wo, oh = t % Ho, n = t / Ho;
+        off0 = ((size_t)(n * H + 2 * oh) * W + 2 * ow) * C + c4 * 4;
+      } else {
+        off0 = (size_t)pix * C + c4 * 4;
       }
+      const float4 gg = *reinterpret_cast<const float4*>(g + (size_t)pix * C + c4 * 4);
+      BnSrc o;
+      bn_route(raw + off0, row_pitch, C, pool, relu, gg, sc, sh, mn, iv, o);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (q < np) {
+          float4 v;
+          v.x = fmaf(scv[0], o.gz[q][0], -kb[0]) - o.xh[q][0] * kg[0];
+          v.y = fmaf(scv[1], o.gz[q][1], -kb[1]) - o.xh[q][1] * kg[1];
+          v.z = fmaf(scv[2], o.gz[q][2], -kb[2]) - o.xh[q][2] * kg[2];
+          v.w = fmaf(scv[3], o.gz[q][3], -kb[3]) - o.xh[q][3] * kg[3];
+          const size_t off = off0 + (size_t)(q >> 1) * row_pitch + (size_t)(q & 1) * C;
+          if (out_f32) *reinterpret_cast<float4*>(out_f32 + off) = v;
+          if (out_hi) {
+            uint2 hi2, lo2;
+            split_bf16x4(v, hi2, lo2);
+            *reinterpret_cast<uint2*>(out_hi + off) = hi2;
+            if (out_lo) *reinterpret_cast<uint2*>(out_lo + off) = lo2;
+          }
+        }
+    }
   }
 }
 

@@ -75,6 +75,7 @@ struct ConvTcParams {
   __nv_bfloat16* out_lo;      // optional (precise) NHWC bf16
   float* stats;               // optional [gridDim][2][Cout] per-CTA (mean, M2) of the pre-activation (acc + bias)
   float* stats_cnt;           // [gridDim][tiles_n] pixel count behind each per-CTA partial
+  float* colsum;              // optional [Cout]: += column sums of the stored values (bias gradient of the upstream conv)
   long long* prof;            // optional [gridDim][16] cycle counters per role (tools/conv_prof.py); null in production
 };
 
@@ -131,7 +132,7 @@ __device__ __forceinline__ float4 epi_affine(float4 a, const float4& s, const fl
 // tile is drained at ~40 instructions per float4 instead of ~220 in the flag-driven loop.  Layers with a short K loop
 // (K = 9*64 .. 9*128) are bound by exactly this loop, not by the MMAs.
 template <int RED, bool MASK, bool UPS, bool F32, bool SPLIT>
-__device__ __forceinline__ void epi_store(const ConvTcParams& p, const EpiTile& e) {
+__device__ __forceinline__ void epi_store(const ConvTcParams& p, const EpiTile& e, float4& cs) {
   const int obw_mask = (1 << e.obw_log) - 1;
 #pragma unroll 2
   for (int pix = e.pl; pix < e.npix; pix += e.PS) {
@@ -165,6 +166,7 @@ __device__ __forceinline__ void epi_store(const ConvTcParams& p, const EpiTile& 
       if (!(bf16_bits_to_float(mk.y & 0xffffu) > 0.f)) v.z = 0.f;
       if (!(bf16_bits_to_float(mk.y >> 16) > 0.f)) v.w = 0.f;
     }
+    cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;   // column sums (used when p.colsum is set)
     uint2 hi2, lo2;
     if (SPLIT) split_bf16x4(v, hi2, lo2);
     const size_t off = e.out_base + (size_t)(ph * e.out_row + pw * e.out_px);
@@ -466,6 +468,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     const uint32_t stage_s = ptx::smem_u32(stage);
     float* red = stage + (size_t)128 * ldst; // [4][64][3] floats of scratch
     float* run_stats = red + 4 * 64 * 3;     // [Cout][3] running (n, mean, M2) of this CTA (BatchNorm statistics)
+    float* colsum_s = run_stats + (p.stats ? p.Cout * 3 : 0);   // [Cout] column sums of this CTA (bias gradient)
+    if (p.colsum) {
+      for (int i = et; i < p.Cout; i += kEpiThreads) colsum_s[i] = 0.f;
+      ptx::named_bar_sync(1, kEpiThreads);
+    }
     if (p.stats) {
       for (int i = et; i < p.Cout * 3; i += kEpiThreads) run_stats[i] = 0.f;
       ptx::named_bar_sync(1, kEpiThreads);
@@ -546,6 +553,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         }
         ptx::named_bar_sync(1, kEpiThreads);
 
+        float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
         if (it.valid) {
           // -- phase 2: per-tile BatchNorm statistics of (acc + bias): mean and M2 over the tile's valid pixels.
           //    4 threads per column (row quarters), merged with Chan's formula.
@@ -624,13 +632,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
             e.mask_row = mf * mf * Wo * p.Cout; e.mask_px = mf * p.Cout;
             done = true;
             switch (lean_mode) {
-              case 1: epi_store<0, false, false, true, false>(p, e); break;   // fp32 out: train-mode trunk / dgrad into BN
-              case 2: epi_store<0, false, false, false, true>(p, e); break;   // split out: decoder / eval trunk
-              case 3: epi_store<0, false, true, false, true>(p, e); break;    // ... + nearest-2x replicate
-              case 4: epi_store<1, false, false, false, true>(p, e); break;   // ... + 2x2 max-pool
-              case 5: epi_store<0, true, false, false, true>(p, e); break;    // decoder dgrad: ReLU mask
-              case 6: epi_store<2, true, false, false, true>(p, e); break;    // ... + 2x2 sum (grad of Upsample)
-              case 7: epi_store<0, false, false, true, true>(p, e); break;    // both outputs
+              case 1: epi_store<0, false, false, true, false>(p, e, cs); break;   // fp32 out: train-mode trunk / dgrad into BN
+              case 2: epi_store<0, false, false, false, true>(p, e, cs); break;   // split out: decoder / eval trunk
+              case 3: epi_store<0, false, true, false, true>(p, e, cs); break;    // ... + nearest-2x replicate
+              case 4: epi_store<1, false, false, false, true>(p, e, cs); break;   // ... + 2x2 max-pool
+              case 5: epi_store<0, true, false, false, true>(p, e, cs); break;    // decoder dgrad: ReLU mask
+              case 6: epi_store<2, true, false, false, true>(p, e, cs); break;    // ... + 2x2 sum (grad of Upsample)
+              case 7: epi_store<0, false, false, true, true>(p, e, cs); break;    // both outputs
               default: done = false;
             }
           }
@@ -673,6 +681,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                 if (!(bf16_bits_to_float(mk.y & 0xffffu) > 0.f)) v.z = 0.f;
                 if (!(bf16_bits_to_float(mk.y >> 16) > 0.f)) v.w = 0.f;
               }
+              cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
               uint2 hi2 = make_uint2(0, 0), lo2 = make_uint2(0, 0);
               if (p.out_hi) {
                 __nv_bfloat16 h[4], l[4];
@@ -695,6 +704,19 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
             while (pw >= oBW) { pw -= oBW; ++ph; }
           }
         }
+        if (p.colsum && it.valid) {
+          // threads of a warp that share a channel group are gpp lanes apart: fold them, then one smem atomic per channel
+          for (int o = 16; o >= gpp; o >>= 1) {
+            cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o);
+            cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
+            cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o);
+            cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
+          }
+          if (lane < gpp) {
+            float* dst = colsum_s + n0 + g * 4;
+            atomicAdd(dst + 0, cs.x); atomicAdd(dst + 1, cs.y); atomicAdd(dst + 2, cs.z); atomicAdd(dst + 3, cs.w);
+          }
+        }
         ptx::named_bar_sync(1, kEpiThreads);   // staging is free for the next chunk / item
       }
       as ^= 1;
@@ -702,6 +724,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     if (p.prof && et == 0) {
       long long* o = p.prof + (size_t)blockIdx.x * 16;
       o[7] = prof_c[0]; o[8] = clock64() - prof_start; o[9] = (p.num_items - cluster_id + num_clusters - 1) / num_clusters;
+    }
+    if (p.colsum) {
+      for (int c = et; c < p.Cout; c += kEpiThreads) atomicAdd(p.colsum + c, colsum_s[c]);
     }
     if (p.stats) {
       // one (mean, M2, n) partial per CTA and channel; bias shifts the mean only
@@ -791,7 +816,7 @@ extern "C" int egaze_conv3x3_set_prof(void* buf) {
 extern "C" int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, int N, int H, int W,
                                 int Cin_p, int Cout, const float* bias, const float* scale, const float* shift, int relu,
                                 int reduce, int ups, const void* mask, int mask_ups, float* out_f32, void* out_hi,
-                                void* out_lo, float* stats, float* stats_cnt, int precise, void* stream) {
+                                void* out_lo, float* stats, float* stats_cnt, float* colsum, int precise, void* stream) {
   EGAZE_CHECK_ARG(x_hi && w_hi, "conv3x3_tc: null operand");
   EGAZE_CHECK_ARG(!precise || (x_lo && w_lo), "conv3x3_tc: precise mode needs lo planes");
   EGAZE_CHECK_ARG(N > 0 && H > 0 && W > 0, "conv3x3_tc: bad shape %d %d %d", N, H, W);
@@ -832,7 +857,7 @@ extern "C" int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* 
     const double eff_c = (double)H * W / ((double)ceil_div(H, p.BH) * ceil_div(W, p.BW) * 128.0);
     // ring depth the weight boxes would get next to two 180-row windows (see the smem budget below)
     const int bn = conv_pick_bn(Cout, precise), ns = precise ? 2 : 1;
-    const int stage_b = ((128 * ((bn < 64 ? bn : 64) + 4) * 4 + 4 * 64 * 3 * 4 + (stats ? Cout * 3 * 4 : 0) + 1023) / 1024) * 1024;
+    const int stage_b = ((128 * ((bn < 64 ? bn : 64) + 4) * 4 + 4 * 64 * 3 * 4 + (stats ? Cout * 3 * 4 : 0) + (colsum ? Cout * 4 : 0) + 1023) / 1024) * 1024;
     const int sb_w = (222 * 1024 - stage_b - 2 * ns * 23552) / (ns * bn * 128);
     if (eff_w >= eff_c * 0.999 && sb_w >= win_minsb) {
       p.win = 1;
@@ -859,7 +884,7 @@ extern "C" int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* 
   p.a_slot_bytes = ((a_rows * row_bytes + 1023) / 1024) * 1024;
   p.b_slot_bytes = ((p.BN * row_bytes + 1023) / 1024) * 1024;
   const int CW = p.BN < 64 ? p.BN : 64;
-  const int stage_bytes = ((128 * (CW + 4) * 4 + 4 * 64 * 3 * 4 + (stats ? Cout * 3 * 4 : 0) + 1023) / 1024) * 1024;
+  const int stage_bytes = ((128 * (CW + 4) * 4 + 4 * 64 * 3 * 4 + (stats ? Cout * 3 * 4 : 0) + (colsum ? Cout * 4 : 0) + 1023) / 1024) * 1024;
   static int sa_env = -1;
   if (sa_env < 0) {
     const char* e = getenv("EGAZE_CONV_SA");
@@ -905,6 +930,7 @@ extern "C" int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* 
   p.mask_ups = mask_ups;
   p.out_f32 = out_f32; p.out_hi = (__nv_bfloat16*)out_hi; p.out_lo = (__nv_bfloat16*)out_lo;
   p.stats = stats; p.stats_cnt = stats_cnt;
+  p.colsum = colsum;
   p.prof = g_conv_prof;
 
   CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;

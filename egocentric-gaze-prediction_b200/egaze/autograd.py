@@ -34,16 +34,19 @@ class _GradBag(object):
         return self.d.get(id(p))
 
 
-def _conv_param_grads(bag, conv, x_act, gpre_act, bias_grad_is_zero=False):
+def _conv_param_grads(bag, conv, x_act, gpre_act, bias_grad_is_zero=False, bias_grad=None):
     """dW via the tcgen05 wgrad kernel, db via a column sum.  gpre_act: gradient w.r.t. the conv output.
     A conv bias that feeds a training-mode BatchNorm has an exactly-zero gradient (the batch mean removes it; stock
-    PyTorch returns rounding noise ~1e-9 there), so no reduction pass is spent on it."""
+    PyTorch returns rounding noise ~1e-9 there), so no reduction pass is spent on it.  bias_grad: column sums already
+    accumulated by the dgrad epilogue that produced gpre_act (then no pass over gpre_act is needed either)."""
     if _req(conv.weight):
         gw = ops.wgrad3x3(x_act, gpre_act, conv.out_channels, conv.in_channels)
         bag.put(conv.weight, gw)
     if _req(conv.bias):
         if bias_grad_is_zero:
             bag.put(conv.bias, torch.zeros_like(conv.bias))
+        elif bias_grad is not None:
+            bag.put(conv.bias, bias_grad[:conv.out_channels] if bias_grad.numel() != conv.out_channels else bias_grad)
         else:
             bag.put(conv.bias, ops.col_sum(gpre_act, conv.out_channels))
 
@@ -90,13 +93,22 @@ def bn_sequential_backward(specs, saved, g, bag, need_input_grad):
 
 def relu_sequential_backward(specs, saved, gpre, bag, want_input_grad_f32):
     """Backward through a conv+bias+ReLU(+ups) chain.  gpre: split gradient w.r.t. the LAST conv's output
-    (its ReLU mask already applied).  Returns the NHWC fp32 gradient w.r.t. the chain input (or None)."""
+    (its ReLU mask already applied).  Returns the NHWC fp32 gradient w.r.t. the chain input (or None).
+    The dgrad of layer i writes the masked gradient w.r.t. layer i-1's output; its epilogue also accumulates that
+    tensor's column sums, which are layer i-1's bias gradient."""
+    bias_grad = None
     for i in range(len(specs) - 1, -1, -1):
         sp, rec = specs[i], saved[i]
-        _conv_param_grads(bag, sp.conv, rec["x"], gpre)
+        _conv_param_grads(bag, sp.conv, rec["x"], gpre, bias_grad=bias_grad)
+        bias_grad = None
         if i > 0:
             prev = specs[i - 1]
-            gpre, _, _ = _dgrad(sp.conv, gpre, reduce=2 if prev.ups else 0, mask=saved[i - 1]["y"].hi, mask_ups=prev.ups)
+            if _req(prev.conv.bias):
+                cin = sp.conv.in_channels   # == prev.conv.out_channels; the dgrad output carries them padded to 16
+                bias_grad = torch.zeros((ops.pad_channels(cin) if cin % 16 else cin,), dtype=torch.float32,
+                                        device=gpre.hi.device)
+            gpre, _, _ = _dgrad(sp.conv, gpre, reduce=2 if prev.ups else 0, mask=saved[i - 1]["y"].hi, mask_ups=prev.ups,
+                                colsum=bias_grad)
         elif want_input_grad_f32:
             _, g, _ = _dgrad(sp.conv, gpre, want_f32=True, want_split=False)
             return g

@@ -202,8 +202,9 @@ def conv_stats_shape(Cout, precise):
 
 
 def conv3x3(act, wpack, bias=None, scale=None, shift=None, relu=False, reduce=0, ups=False, mask=None,
-            want_f32=False, want_split=True, stats=False, precise=None, mask_ups=False):
+            want_f32=False, want_split=True, stats=False, precise=None, mask_ups=False, colsum=None):
     """3x3/pad-1 conv on the tcgen05 path.  wpack = (w_hi, w_lo, Cout_p, Cin_p) from pack_cache.
+    colsum: optional [Cout] fp32 tensor the kernel ADDS the per-channel sums of the stored values to.
     Returns (out_act | None, out_f32 | None, (stats_partial, stats_cnt) | None)."""
     w_hi, w_lo, Cout, Cin_p = wpack
     if Cin_p != act.Cp:
@@ -226,7 +227,7 @@ def conv3x3(act, wpack, bias=None, scale=None, shift=None, relu=False, reduce=0,
     call("egaze_conv3x3_tc", act.hi, act.lo if precise else None, w_hi, w_lo if precise else None, N, H, W, Cin_p, Cout,
          bias, scale, shift, int(relu), int(reduce), int(ups), mask, int(mask_ups), out_f32,
          out_act.hi if out_act is not None else None, out_act.lo if out_act is not None else None,
-         st[0] if st else None, st[1] if st else None, int(precise), stream_ptr())
+         st[0] if st else None, st[1] if st else None, colsum, int(precise), stream_ptr())
     if _conv_timer["on"]:
         ev1.record()
         _conv_timer["events"].append((ev0, ev1, ("conv", N, H, W, Cin_p, Cout, int(reduce), int(ups), bool(stats))))

@@ -56,11 +56,14 @@ int egaze_conv3x3_set_prof(void* buf);
  *   x_hi/x_lo : [N][H][W][Cin_p] bf16        w_hi/w_lo : [9][Cout][Cin_p] bf16 (egaze_pack_w3x3)
  *   out_f32 / out_hi / out_lo : NHWC [N][Ho][Wo][Cout] (any non-NULL subset is written)
  *   stats / stats_cnt : per-CTA (mean, M2, n) partials of (acc + bias) for BatchNorm batch statistics (egaze_conv3x3_stats_shape)
+ *   colsum : optional [Cout] fp32, ACCUMULATED: += sum over all output pixels of the final (masked) values.  When the
+ *            kernel computes a data gradient this is the bias gradient of the conv that produced the masked activation,
+ *            so no separate reduction pass over the gradient tensor is needed.
  *   precise != 0 : hi*hi + hi*lo + lo*hi (3 MMAs), needs x_lo and w_lo;  0 : single bf16 pass. */
 int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, int N, int H, int W,
                      int Cin_p, int Cout, const float* bias, const float* scale, const float* shift, int relu,
                      int reduce, int ups, const void* mask, int mask_ups, float* out_f32, void* out_hi, void* out_lo,
-                     float* stats, float* stats_cnt, int precise, void* stream);
+                     float* stats, float* stats_cnt, float* colsum, int precise, void* stream);
 /* Weight gradient: dwp[9][Cout][Cin_p] (fp32, ACCUMULATED: zero first) += sum_pixels dY (x) X-window; tcgen05 GEMM with the
  * pixel axis as K, MN-major operands straight from NHWC.  Cin_p % 64 == 0, Cout % 64 == 0.  (loss.backward(): SP.py:136) */
 int egaze_wgrad3x3_tc(const void* x_hi, const void* x_lo, const void* dy_hi, const void* dy_lo, int N, int H, int W,

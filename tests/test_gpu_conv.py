@@ -99,6 +99,17 @@ def test_conv3x3_epilogues(cuda_dev, shape):
     ref = F.avg_pool2d(conv_nb, 2, 2) * 4 * (ops.from_split(ops.Act(mact.hi, None, Cout)) > 0).float()
     assert (ops.nhwc_f32_to_nchw(f) - ref).abs().max().item() <= 4e-4 * 4 * sc
     assert (ops.from_split(a) - ref).abs().max().item() <= 5e-4 * 4 * sc
+    # (d) column sums of the stored values (the bias gradient the dgrad epilogue hands to the upstream conv), both for the
+    #     masked 2x2-sum epilogue and for the plain masked one; accumulated on top of what the buffer already holds
+    for red in (2, 0):
+        m_src = mask_src if red else torch.randn(N, Cout, H, W, generator=g).to(cuda_dev)
+        m_act = ops.to_split(m_src, Cout)
+        cs = torch.full((Cout,), 3.0, device=cuda_dev)
+        a, _, _ = _run(x, w, None, True, reduce=red, mask=m_act.hi, colsum=cs)
+        got = ops.from_split(a)
+        want = got.double().sum((0, 2, 3)) + 3.0
+        tol = 1e-4 * got.abs().double().sum((0, 2, 3)).max().item() + 1e-3
+        assert (cs.double() - want).abs().max().item() <= tol
 
 
 @pytest.mark.parametrize("shape", [(4, 32, 32, 64, 64), (2, 14, 14, 128, 512), (3, 28, 28, 64, 128), (2, 36, 36, 32, 32)])
