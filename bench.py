@@ -1,12 +1,15 @@
 #!/usr/bin/env python
 """bench.py -- the driver's benchmark contract for the egaze-b200 hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload sp_train|sp_fwd|pipeline_fwd] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload sp_train|sp_fwd|pipeline_fwd|full_train|at_seq]
+                    [--impl reference]
 
 Metric (BASELINE.json): SP(+AT+LF) gaze-map frames/s at 224x224, batch 32 per GPU.  One "step" = one pass of the hot
 path over one synthetic batch: `sp_train` = model_SP two-stream forward + floss + backward +
-Adam step (BASELINE configs[1]); `sp_fwd` = eval-mode two-stream forward; `pipeline_fwd` = SP forward -> AT step ->
-LF forward (gaze-map inference).  N > 1 ranks (torchrun) shard frames: weak scaling, B=32 per rank, one NCCL
+Adam step (BASELINE configs[1], the default); `sp_fwd` = eval-mode two-stream forward; `pipeline_fwd` = SP forward -> AT
+step -> LF forward (gaze-map inference); `full_train` = BASELINE configs[3] per rank: SP train step, AT step on the hooked
+conv5_3 map, LF train step on (AT map, SP map) with floss; `at_seq` = BASELINE configs[2]: crop-mean -> 2-layer LSTM ->
+channel-weighted map over 16 feature sequences of 30 steps (a "frame" is one sequence step).  N > 1 ranks (torchrun) shard frames: weak scaling, B=32 per rank, one NCCL
 allreduce of the weight gradients per training step and no collective for inference.
 
 Prints ONE JSON line (rank 0).  `value` = device-resident throughput; `e2e` = same metric through the public module
@@ -35,6 +38,17 @@ UNIT = "frames/s"
 FLOP_SP_FWD = 114.167e9
 FLOP_SP_TRAIN = 341.171e9
 FLOP_LF_FWD = 1.2147e9
+
+
+def load_traffic(workload):
+    """DRAM bytes per launch of the tcgen05 conv kernels (dram__bytes_read.sum + dram__bytes_write.sum averaged over the
+    conv/wgrad launches of one step), from the committed ncu capture of this same command (profiles/*_traffic.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "conv_traffic.json")) as fh:
+            d = json.load(fh)
+        return d.get(workload)
+    except Exception:
+        return None
 
 
 def load_peaks():
@@ -98,9 +112,9 @@ class Workload(object):
         import floss as floss_mod
         self.name, self.B, self.S, self.device, self.world = name, B, S, device, world
         torch.manual_seed(0)  # identical replicas on every rank
-        self.model = model_SP(make_layers(cfg['D'], 3), make_layers(cfg['D'], 20)).to(device)
-        self.crit = floss_mod.floss()
         from egaze.ddp import shard_seed
+        self.model = model_SP(make_layers(cfg['D'], 3), make_layers(cfg['D'], 20)).to(device) if name != "at_seq" else None
+        self.crit = floss_mod.floss()
         x_s, x_t, gt = orc.synth_sp_inputs(B, S, shard_seed(1234, rank))
         self.host = [torch.from_numpy(a).pin_memory() for a in (x_s, x_t, gt)]
         self.dev = [t.to(device) for t in self.host]
@@ -127,14 +141,46 @@ class Workload(object):
             self.gaze = torch.randint(0, S, (B, 2), generator=torch.Generator().manual_seed(5 + rank)).int().to(device)
             self.flop = FLOP_SP_FWD + FLOP_LF_FWD
             self.d2h_bytes = B * S * S * 4
+        elif name == "full_train":
+            # BASELINE configs[3]: SP train step + AT step on the hooked features_s map + LF train step (LF.py:79-105)
+            self.model.train()
+            self.lstm = lstmnet().to(device).eval()
+            self.lf = late_fusion().to(device).train()
+            self.opt = torch.optim.Adam(self.model.parameters(), lr=1e-7)
+            self.opt_lf = torch.optim.Adam(self.lf.parameters(), lr=1e-7)
+            self.feats = []
+            self.model._modules.get('features_s').register_forward_hook(lambda m, i, o: self.feats.append(o))  # AT.py:105
+            self.hidden = (torch.zeros(2, B, 512, device=device), torch.zeros(2, B, 512, device=device))
+            self.gaze = torch.randint(0, S, (B, 2), generator=torch.Generator().manual_seed(5 + rank)).int().to(device)
+            self.flop = FLOP_SP_TRAIN + 3 * FLOP_LF_FWD
+            self.h2d_bytes = sum(t.numel() * 4 for t in self.host)
+            self.d2h_bytes = 8
+            if world > 1:
+                self._make_flat_grads(list(self.model.parameters()) + list(self.lf.parameters()))
+        elif name == "at_seq":
+            # BASELINE configs[2]: 16 feature sequences x 30 steps of 512x14x14 post-ReLU maps
+            self.T, self.NB = 30, 16
+            g = torch.Generator().manual_seed(shard_seed(77, rank))
+            self.model = None
+            self.lstm = lstmnet().to(device).eval()
+            feat = torch.relu(torch.randn(self.T * self.NB, 512, S // 16, S // 16, generator=g))
+            gaze = torch.randint(0, S, (self.T * self.NB, 2), generator=g).int()
+            self.host = [feat.pin_memory(), gaze.pin_memory(), torch.zeros(1).pin_memory()]
+            self.dev = [t.to(device) for t in self.host]
+            self.h2d_bytes = feat.numel() * 4 + gaze.numel() * 4
+            self.d2h_bytes = self.T * self.NB * (S // 16) ** 2 * 4
+            self.flop = 0.0
+            self.B = self.T * self.NB   # "frames" per step = sequence steps
         else:
             raise SystemExit("unknown workload %r" % name)
 
-    def _make_flat_grads(self):
+    def _make_flat_grads(self, params=None):
         """All weight grads live in ONE flat fp32 buffer so the per-step NCCL allreduce needs no pack/copy."""
         from egaze.ddp import FlatGradBucket, broadcast_parameters
         broadcast_parameters(self.model, 0)
-        self.flat = FlatGradBucket(self.model.parameters(), self.device)
+        if params is not None:
+            broadcast_parameters(self.lf, 0)
+        self.flat = FlatGradBucket(self.model.parameters() if params is None else params, self.device)
 
     def step(self, x_s, x_t, gt):
         """One pass of the hot path; returns the tensor a user would read back."""
@@ -151,6 +197,39 @@ class Workload(object):
                 self.flat.allreduce()
             self.opt.step()
             return loss
+        if self.name == "full_train":
+            if self.flat is not None:
+                self.flat.zero()
+            else:
+                self.opt.zero_grad(set_to_none=True)
+                self.opt_lf.zero_grad(set_to_none=True)
+            self.feats.clear()
+            out = self.model(x_s, x_t)                                         # SP.py:132
+            gtv = gt.view(out.size())
+            loss = self.crit(out, gtv)
+            loss.backward()
+            with torch.no_grad():                                              # AT.py:224-252 on the hooked map, batched
+                feat = self.feats[0]
+                vec = ops.crop_mean(feat, self.gaze, 3)
+                w, hidden = self.lstm(vec.unsqueeze(0), self.hidden)
+                self.hidden = tuple(h.detach() for h in hidden)
+                amap = ops.weighted_map(w.squeeze(0), feat)
+                up = ops.bilinear_up(amap.unsqueeze(1), 16, False)
+            fused = self.lf(up, out.detach())                                  # LF.py:90
+            loss_lf = self.crit(fused, gtv)                                    # LF.py:91
+            loss_lf.backward()
+            if self.flat is not None:
+                self.flat.allreduce()
+            self.opt.step()
+            self.opt_lf.step()
+            return torch.stack((loss.detach(), loss_lf.detach()))
+        if self.name == "at_seq":
+            feat, gaze = x_s, x_t
+            with torch.no_grad():
+                vec = ops.crop_mean(feat, gaze, 3)                             # AT.py:236-241, all T*B frames at once
+                hid = (torch.zeros(2, self.NB, 512, device=self.device), torch.zeros(2, self.NB, 512, device=self.device))
+                w, _ = self.lstm(vec.view(self.T, self.NB, 512), hid)          # AT.py:245-246: the recurrence over T
+                return ops.weighted_map(w.reshape(self.T * self.NB, 512), feat)  # AT.py:248 per frame
         with torch.no_grad():
             if self.name == "sp_fwd":
                 return self.model(x_s, x_t)
@@ -179,15 +258,50 @@ def cpu_reference_fps(workload, B, S, steps, warmup, threads):
     torch.manual_seed(0)
     m = ref.ModelSP()
     x_s, x_t, gt = [torch.from_numpy(a) for a in orc.synth_sp_inputs(B, S, 1234)]
-    if workload == "sp_train":
+    if workload == "at_seq":
+        # BASELINE configs[2] the way AT.extract_late walks a video: frame by frame, batch = the 16 sequences
+        T, NB = 30, 16
+        lstm = ref.LSTMNet().eval()
+        g = torch.Generator().manual_seed(77)
+        feat = torch.relu(torch.randn(T, NB, 512, S // 16, S // 16, generator=g)).numpy()
+        gaze = torch.randint(0, S, (T, NB, 2), generator=g).numpy()
+
+        def step():
+            hid = (torch.zeros(2, NB, 512), torch.zeros(2, NB, 512))
+            with torch.no_grad():
+                for t in range(T):
+                    vec = torch.from_numpy(orc.crop_mean(feat[t], gaze[t], 3))
+                    w, hid = lstm(vec.unsqueeze(0), hid)
+                    orc.get_weighted(w.squeeze(0).numpy(), feat[t])
+        B = T * NB
+    elif workload in ("sp_train", "full_train"):
         m.train()
         opt = torch.optim.Adam(m.parameters(), lr=1e-7)
+        full = workload == "full_train"
+        if full:
+            lf, lstm = ref.LateFusion().train(), ref.LSTMNet().eval()
+            opt_lf = torch.optim.Adam(lf.parameters(), lr=1e-7)
 
         def step():
             opt.zero_grad()
-            loss = ref.floss(m(x_s, x_t), gt)
+            blobs = []
+            h = m.features_s.register_forward_hook(lambda mod, i, o: blobs.append(o.detach()))
+            out = m(x_s, x_t)
+            h.remove()
+            loss = ref.floss(out, gt)
             loss.backward()
             opt.step()
+            if full:
+                opt_lf.zero_grad()
+                with torch.no_grad():
+                    feat = blobs[0]
+                    vec = torch.from_numpy(orc.crop_mean(feat.numpy(), [[S // 2, S // 2]] * B, 3))
+                    w, _ = lstm(vec.unsqueeze(0), (torch.zeros(2, B, 512), torch.zeros(2, B, 512)))
+                    amap = torch.from_numpy(orc.get_weighted(w.squeeze(0).numpy(), feat.numpy()))
+                    up = torch.nn.functional.interpolate(amap.unsqueeze(1), scale_factor=16, mode="bilinear", align_corners=False)
+                loss_lf = ref.floss(lf(up, out.detach()), gt)
+                loss_lf.backward()
+                opt_lf.step()
     else:
         m.eval()
         lf = ref.LateFusion().eval() if workload == "pipeline_fwd" else None
@@ -214,7 +328,9 @@ def cpu_reference_fps(workload, B, S, steps, warmup, threads):
     for _ in range(steps):
         step()
     dt = (time.perf_counter() - t0) / steps
-    return B / dt, dt
+    sample = ("at_seq, 16 sequences x 30 steps of 512x%dx%d maps" % (S // 16, S // 16)) if workload == "at_seq" else \
+        "%s, batch %d x %dx%d" % (workload, B, S, S)
+    return B / dt, dt, sample
 
 
 def run_reference(args):
@@ -224,15 +340,15 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     B = args.ref_batch
     steps = max(1, min(args.steps, 3))
-    fps, dt = cpu_reference_fps(args.workload, B, args.size, steps, 1, threads)
+    fps, dt, sample = cpu_reference_fps(args.workload, B, args.size, steps, 1, threads)
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "batch_per_gpu": 32, "size": args.size,
-                       "note": "reference CPU path timed on a bounded sample (batch %d) of the same workload" % B},
+                       "note": "reference CPU path timed on a bounded sample (%s) of the same workload" % sample},
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": "%s, batch %d x %dx%d, %d step(s), torch %s CPU (oneDNN), %d threads" % (
-                                 args.workload, B, args.size, args.size, steps, torch.__version__, threads)},
+                             "sample": "%s, %d step(s), torch %s CPU (oneDNN), %d threads" % (
+                                 sample, steps, torch.__version__, threads)},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -336,34 +452,46 @@ def main():
         return
 
     peaks, peak_src = load_peaks()
-    frames = args.batch * world
+    frames = wl.B * world
     value = frames / ms * 1e3
-    conv_flop_step = (wl.flop - (FLOP_LF_FWD if args.workload == "pipeline_fwd" else 0.0)) * args.batch
+    conv_flop_step = (wl.flop - (FLOP_LF_FWD if args.workload == "pipeline_fwd" else 0.0)
+                      - (3 * FLOP_LF_FWD if args.workload == "full_train" else 0.0)) * args.batch
     conv_tflops = conv_flop_step * K / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     peak_tf = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    traffic = load_traffic(args.workload)
+    if args.workload == "at_seq":
+        # HBM-bound: the 480 x 512 x 14 x 14 fp32 feature stack is read once by the weighted-map kernel
+        alg_bytes = wl.dev[0].numel() * 4 + 17.9e6
+        roofline = {"bound": "hbm", "kernel": "weighted_map_kernel (reads the whole feature stack) + lstm weights",
+                    "achieved": alg_bytes / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": alg_bytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "peak_source": "%s hbm_gbs" % peak_src,
+                    "note": "achieved = algorithmic bytes / whole-step time (the step is 3 C-ABI calls)", "traffic": None}
+    else:
+        roofline = {"bound": "tensor", "kernel": "tcgen05 conv kernels (conv3x3_tc fprop/dgrad + wgrad_tc launches of the step)",
+                    "achieved": conv_tflops, "peak": peak_tf, "unit": "TFLOP/s", "frac": conv_tflops / peak_tf,
+                    "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step)" % peak_src,
+                    "launches_per_step": conv_launches / max(K, 1), "kernel_ms_per_step": conv_ms / max(K, 1),
+                    "step_tflops": wl.flop * args.batch / (ms * 1e-3) / 1e12,
+                    "traffic": traffic}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16x3-split (fp32 accumulate)" if ops.is_precise() else "bf16 (fp32 accumulate)", "data": "synthetic",
-        "config": {"workload": args.workload, "batch_per_gpu": args.batch, "size": args.size, "global_batch": frames,
+        "config": {"workload": args.workload, "batch_per_gpu": wl.B, "size": args.size, "global_batch": frames,
                    "precision_mode": ops.precision(), "parallelism": "dp%d" % world,
                    "l2": "per-step inputs+activations (>1 GB) exceed the 126 MB L2; no explicit flush"},
         "clocks": clocks,
         "e2e": {"value": frames / ms_e2e * 1e3, "unit": UNIT, "h2d_bytes_per_step": wl.h2d_bytes,
                 "d2h_bytes_per_step": wl.d2h_bytes},
         "gpu_launches": launches * K,
-        "roofline": {"bound": "tensor", "kernel": "tcgen05 conv kernels (conv3x3_tc fprop/dgrad + wgrad_tc launches of the step)",
-                     "achieved": conv_tflops, "peak": peak_tf, "unit": "TFLOP/s", "frac": conv_tflops / peak_tf,
-                     "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step)" % peak_src,
-                     "launches_per_step": conv_launches / max(K, 1), "kernel_ms_per_step": conv_ms / max(K, 1),
-                     "step_tflops": wl.flop * args.batch / (ms * 1e-3) / 1e12, "traffic": None},
+        "roofline": roofline,
     }
     if not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1
-        fps, dt = cpu_reference_fps(args.workload, args.ref_batch, args.size, 1, 1, threads)
+        fps, dt, sample = cpu_reference_fps(args.workload, args.ref_batch, args.size, 1, 1, threads)
         line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": "%s, batch %d x %dx%d, 1 warm-up + 1 timed step, torch %s CPU (oneDNN), %d threads"
-                                          % (args.workload, args.ref_batch, args.size, args.size, torch.__version__, threads)}
+                                "sample": "%s, 1 warm-up + 1 timed step, torch %s CPU (oneDNN), %d threads"
+                                          % (sample, torch.__version__, threads)}
     print(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()

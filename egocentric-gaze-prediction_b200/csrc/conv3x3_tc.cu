@@ -55,6 +55,8 @@ struct ConvTcParams {
   int acc_mode;
   int nsum;            // accumulator blocks the epilogue adds (1, 2 or 3)
   int acc_cols;        // TMEM columns of one accumulator stage (power of two >= 32)
+  int pair;            // 1 = CTA-pair MMA (cta_group::2, M = 256): the two CTAs of the cluster each hold HALF of every weight box
+                       //     and rank 0 issues one MMA for both spatial tiles (see the kernel header)
   int win;             // 1 = "window" mode: ONE (BH+2) x (BW+2) activation window per K chunk serves all nine taps
   int win_bo;          // window mode: fill the descriptor's base_offset field with (start >> 7) & 7
   int SA, SB;          // ring depths
@@ -190,18 +192,13 @@ __device__ __forceinline__ void epi_store(const ConvTcParams& p, const EpiTile& 
 // even when the phase completed long ago and the tensor pipe's instruction queue is shallow, so a query sitting between
 // two taps is tensor-pipe idle time; issued here its latency hides behind the (blocking) MMA issue.
 // Returns bit 0: next B slot has landed, bit 1: next A slot has landed.
-#define EGAZE_MMA_PAIR(OFF)                                                                \
+#define EGAZE_MMA_PAIR(CG, OFF)                                                            \
   "add.s64 ah, %2, " #OFF ";\n\t"                                                          \
   "add.s64 al, %3, " #OFF ";\n\t"                                                          \
   "add.s64 bb, %4, " #OFF ";\n\t"                                                          \
-  "tcgen05.mma.cta_group::1.kind::f16 [%1], ah, bb, %5, pt;\n\t"                           \
-  "tcgen05.mma.cta_group::1.kind::f16 [%1], al, bb, %6, pt;\n\t"
-template <int KSTEPS>
-__device__ __forceinline__ uint32_t tap_merged_probe(uint32_t d_tmem, uint64_t ad_hi, uint64_t ad_lo, uint64_t bd,
-                                                     uint32_t idesc2, uint32_t idesc, uint32_t accumulate, uint32_t bar_b,
-                                                     uint32_t par_b, uint32_t bar_a, uint32_t par_a) {
-  uint32_t flags;
-#define EGAZE_TAP_HEAD                                                                     \
+  "tcgen05.mma.cta_group::" #CG ".kind::f16 [%1], ah, bb, %5, pt;\n\t"                     \
+  "tcgen05.mma.cta_group::" #CG ".kind::f16 [%12], al, bb, %6, pt;\n\t"
+#define EGAZE_TAP_HEAD(CG)                                                                 \
   "{\n\t"                                                                                  \
   ".reg .pred pb, pa, pacc, pt;\n\t"                                                       \
   ".reg .b64 ah, al, bb;\n\t"                                                              \
@@ -210,8 +207,8 @@ __device__ __forceinline__ uint32_t tap_merged_probe(uint32_t d_tmem, uint64_t a
   "mbarrier.test_wait.parity.shared::cta.b64 pa, [%10], %11;\n\t"                          \
   "setp.ne.b32 pacc, %7, 0;\n\t"                                                           \
   "setp.eq.b32 pt, %7, %7;\n\t"                                                            \
-  "tcgen05.mma.cta_group::1.kind::f16 [%1], %2, %4, %5, pacc;\n\t"                         \
-  "tcgen05.mma.cta_group::1.kind::f16 [%1], %3, %4, %6, pt;\n\t"
+  "tcgen05.mma.cta_group::" #CG ".kind::f16 [%1], %2, %4, %5, pacc;\n\t"                   \
+  "tcgen05.mma.cta_group::" #CG ".kind::f16 [%12], %3, %4, %6, pt;\n\t"
 #define EGAZE_TAP_TAIL                                                                     \
   "selp.u32 rb, 1, 0, pb;\n\t"                                                             \
   "selp.u32 ra, 2, 0, pa;\n\t"                                                             \
@@ -220,20 +217,34 @@ __device__ __forceinline__ uint32_t tap_merged_probe(uint32_t d_tmem, uint64_t a
 #define EGAZE_TAP_OPERANDS                                                                                            \
   : "=r"(flags)                                                                                                       \
   : "r"(d_tmem), "l"(ad_hi), "l"(ad_lo), "l"(bd), "r"(idesc2), "r"(idesc), "r"(accumulate), "r"(bar_b), "r"(par_b),   \
-    "r"(bar_a), "r"(par_a)                                                                                            \
+    "r"(bar_a), "r"(par_a), "r"(d_tmem2)                                                                              \
   : "memory"
-  if (KSTEPS == 4) {
-    asm volatile(EGAZE_TAP_HEAD EGAZE_MMA_PAIR(2) EGAZE_MMA_PAIR(4) EGAZE_MMA_PAIR(6) EGAZE_TAP_TAIL EGAZE_TAP_OPERANDS);
-  } else if (KSTEPS == 2) {
-    asm volatile(EGAZE_TAP_HEAD EGAZE_MMA_PAIR(2) EGAZE_TAP_TAIL EGAZE_TAP_OPERANDS);
-  } else {
-    asm volatile(EGAZE_TAP_HEAD EGAZE_TAP_TAIL EGAZE_TAP_OPERANDS);
-  }
+#define EGAZE_TAP_ASM(CG)                                                                                             \
+  do {                                                                                                                \
+    if (KSTEPS == 4) {                                                                                                \
+      asm volatile(EGAZE_TAP_HEAD(CG) EGAZE_MMA_PAIR(CG, 2) EGAZE_MMA_PAIR(CG, 4) EGAZE_MMA_PAIR(CG, 6)               \
+                       EGAZE_TAP_TAIL EGAZE_TAP_OPERANDS);                                                            \
+    } else if (KSTEPS == 2) {                                                                                         \
+      asm volatile(EGAZE_TAP_HEAD(CG) EGAZE_MMA_PAIR(CG, 2) EGAZE_TAP_TAIL EGAZE_TAP_OPERANDS);                       \
+    } else {                                                                                                          \
+      asm volatile(EGAZE_TAP_HEAD(CG) EGAZE_TAP_TAIL EGAZE_TAP_OPERANDS);                                             \
+    }                                                                                                                 \
+  } while (0)
+// d_tmem: accumulator of the N = 2*BN MMA; d_tmem2: accumulator of the N = BN MMA (the same block, or shifted by BN/2
+// columns in CTA-pair mode).  PAIR: cta_group::2 (M = 256 across the two CTAs of the cluster).
+template <int KSTEPS, bool PAIR>
+__device__ __forceinline__ uint32_t tap_merged_probe(uint32_t d_tmem, uint32_t d_tmem2, uint64_t ad_hi, uint64_t ad_lo,
+                                                     uint64_t bd, uint32_t idesc2, uint32_t idesc, uint32_t accumulate,
+                                                     uint32_t bar_b, uint32_t par_b, uint32_t bar_a, uint32_t par_a) {
+  uint32_t flags;
+  if (PAIR) EGAZE_TAP_ASM(2);
+  else EGAZE_TAP_ASM(1);
+  return flags;
+}
+#undef EGAZE_TAP_ASM
 #undef EGAZE_TAP_HEAD
 #undef EGAZE_TAP_TAIL
 #undef EGAZE_TAP_OPERANDS
-  return flags;
-}
 #undef EGAZE_MMA_PAIR
 
 template <int NSPLIT, int KSTEPS, int CS>
@@ -261,8 +272,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.SA; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < p.SB; ++i) { ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&b_empty[i], CS); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], kEpiThreads / 32); }
+    // pair mode: only rank 0 issues MMAs / commits (multicast to both CTAs), and rank 0's accumulator-free barrier collects the
+    // epilogue warps of BOTH CTAs
+    for (int i = 0; i < p.SB; ++i) { ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&b_empty[i], p.pair ? 1 : CS); }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&acc_full[i], 1);
+      ptx::mbar_init(&acc_empty[i], (p.pair ? 2 : 1) * (kEpiThreads / 32));
+    }
     ptx::fence_barrier_init();
   }
   if (warp == 0 && lane == 0) {
@@ -272,9 +288,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
   }
   const uint32_t acc_cols = (uint32_t)p.acc_cols;                // columns of one accumulator stage
   const uint32_t tmem_cols = 2 * acc_cols;                       // power of two in [64, 512]
+  const bool pair = CS == 2 && p.pair;
   if (warp == 1) {
-    ptx::tmem_alloc(&tmem_base_smem, tmem_cols);
-    ptx::tmem_relinquish();
+    if (pair) { ptx::tmem_alloc2(&tmem_base_smem, tmem_cols); ptx::tmem_relinquish2(); }
+    else { ptx::tmem_alloc(&tmem_base_smem, tmem_cols); ptx::tmem_relinquish(); }
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -289,7 +306,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
   const int a_loads = p.win ? 1 : 3;                             // windows per K chunk (one per horizontal tap, or one in all)
   const int a_taps = p.win ? 9 : 3;                              // weight boxes consumed per window
   const uint32_t b_box_bytes = (uint32_t)(p.BN * row_bytes);
-  const int b_rows_cta = p.BN / CS;                              // weight rows this CTA fetches (and multicasts)
+  const int b_rows_cta = p.BN / CS;                              // weight rows this CTA fetches (and multicasts / keeps, pair mode)
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -304,19 +321,36 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         for (int kc = 0; kc < chunks; ++kc) {
           for (int al = 0; al < a_loads; ++al) {
             { PROF_T0(p); ptx::mbar_wait(&a_empty[sa], a_par); PROF_ADD(p, prof_c[0]); }
-            ptx::mbar_arrive_expect_tx(&a_full[sa], a_box_bytes * NSPLIT);
             uint8_t* a_dst = a_ring + (size_t)sa * NSPLIT * p.a_slot_bytes;
             const int wx = p.win ? it.w0 - 1 : it.w0 - 1 + al;
-            ptx::tma_load_4d(a_dst, &tmA_hi, &a_full[sa], kc * p.KC, wx, it.h0 - 1, it.img);
-            if (NSPLIT == 2)
-              ptx::tma_load_4d(a_dst + p.a_slot_bytes, &tmA_lo, &a_full[sa], kc * p.KC, wx, it.h0 - 1, it.img);
+            if (pair) {
+              // both CTAs' windows are accounted on rank 0's barrier (its MMA thread consumes both)
+              if (rank == 0) ptx::mbar_arrive_expect_tx(&a_full[sa], 2 * a_box_bytes * NSPLIT);
+              ptx::tma_load_4d_2sm(a_dst, &tmA_hi, &a_full[sa], kc * p.KC, wx, it.h0 - 1, it.img);
+              if (NSPLIT == 2)
+                ptx::tma_load_4d_2sm(a_dst + p.a_slot_bytes, &tmA_lo, &a_full[sa], kc * p.KC, wx, it.h0 - 1, it.img);
+            } else {
+              ptx::mbar_arrive_expect_tx(&a_full[sa], a_box_bytes * NSPLIT);
+              ptx::tma_load_4d(a_dst, &tmA_hi, &a_full[sa], kc * p.KC, wx, it.h0 - 1, it.img);
+              if (NSPLIT == 2)
+                ptx::tma_load_4d(a_dst + p.a_slot_bytes, &tmA_lo, &a_full[sa], kc * p.KC, wx, it.h0 - 1, it.img);
+            }
             if (++sa == p.SA) { sa = 0; a_par ^= 1; }
             for (int t = 0; t < a_taps; ++t) {
               const int s = p.win ? t / 3 : al, r = p.win ? t - 3 * s : t;
               { PROF_T0(p); ptx::mbar_wait(&b_empty[sb], b_par); PROF_ADD(p, prof_c[1]); }   // every CTA of the cluster has drained this slot
+              const int brow = (r * 3 + s) * p.Cout + n0 + rank * b_rows_cta;
+              if (pair) {
+                // this CTA keeps only ITS half of the box (rows rank*BN/2 ..), hi plane then lo plane back to back
+                if (rank == 0) ptx::mbar_arrive_expect_tx(&b_full[sb], b_box_bytes * NSPLIT);
+                uint8_t* b_dst = b_ring + (size_t)sb * NSPLIT * p.b_slot_bytes;
+                ptx::tma_load_2d_2sm(b_dst, &tmB_hi, &b_full[sb], kc * p.KC, brow);
+                if (NSPLIT == 2) ptx::tma_load_2d_2sm(b_dst + p.b_slot_bytes, &tmB_lo, &b_full[sb], kc * p.KC, brow);
+                if (++sb == p.SB) { sb = 0; b_par ^= 1; }
+                continue;
+              }
               ptx::mbar_arrive_expect_tx(&b_full[sb], b_box_bytes * NSPLIT);
               uint8_t* b_dst = b_ring + (size_t)sb * NSPLIT * p.b_slot_bytes + (size_t)rank * b_rows_cta * row_bytes;
-              const int brow = (r * 3 + s) * p.Cout + n0 + rank * b_rows_cta;
               if (CS > 1) {
                 ptx::tma_load_2d_mc(b_dst, &tmB_hi, &b_full[sb], kc * p.KC, brow, kMask);
                 if (NSPLIT == 2) ptx::tma_load_2d_mc(b_dst + p.b_slot_bytes, &tmB_lo, &b_full[sb], kc * p.KC, brow, kMask);
@@ -341,9 +375,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     // loop nest under `if (lane == 0)` every operand of every MMA went through an R2UR move and the single thread
     // needed ~100 cycles per tcgen05.mma -- more than an N <= 128 MMA takes to execute.)
     {
-      const bool leader = ptx::elect_one();
-      const uint32_t idesc = ptx::make_idesc_bf16(128, p.BN, 0, 0);
-      const uint32_t idesc2 = ptx::make_idesc_bf16(128, 2 * p.BN, 0, 0);
+      // CTA-pair mode: rank 0 issues for both CTAs (M = 256); rank 1's MMA warp has nothing to do
+      const bool leader = ptx::elect_one() && !(pair && rank != 0);
+      const int mma_m = pair ? 256 : 128;
+      const uint32_t idesc = ptx::make_idesc_bf16(mma_m, p.BN, 0, 0);
+      const uint32_t idesc2 = ptx::make_idesc_bf16(mma_m, 2 * p.BN, 0, 0);
       const uint32_t sbo = 8u * (uint32_t)row_bytes;
       // window mode: the 8-pixel row segment of tile row th starts (BW+2) window rows after the one of th-1
       const uint32_t sbo_a = p.win ? (uint32_t)AW * (uint32_t)row_bytes : sbo;
@@ -395,9 +431,25 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                 if (!b_ready) { PROF_T0(p); ptx::mbar_wait(&b_full[sb], b_par); PROF_ADD(p, prof_c[2]); }
                 ptx::tc_fence_after();
                 b_ready = false;
-                if (acc_mode == 1) {
-                  const uint32_t fl = tap_merged_probe<KSTEPS>(d_tmem, ad, ad + a_plane16, bd, idesc2, idesc, accumulate, nb_bar,
-                                                               nb_par, na_bar, na_par);
+                if (pair) {
+                  // merged schedule on the CTA pair.  N = 2*BN: each CTA contributes its BN rows [hi half | lo half], so the
+                  // accumulator columns are [hh(c < BN/2) | hl(c < BN/2) | hh(c >= BN/2) | hl(c >= BN/2)]; the N = BN MMA
+                  // (A_lo x B_hi, BN/2 rows per CTA) lands BN/2 columns in, on top of columns of the SAME channels.
+                  if (NSPLIT == 2) {
+                    const uint32_t fl = tap_merged_probe<KSTEPS, true>(d_tmem, d_tmem + (bn >> 1), ad, ad + a_plane16, bd, idesc2,
+                                                                       idesc, accumulate, nb_bar, nb_par, na_bar, na_par);
+                    b_ready = (fl & 1u) != 0;
+                    a_next_ready = (fl & 2u) != 0;
+                  } else {
+#pragma unroll
+                    for (int k = 0; k < KSTEPS; ++k) {
+                      ptx::umma_bf16_2sm(d_tmem, ad + 2 * k, bd + 2 * k, idesc, accumulate);
+                      accumulate = 1;
+                    }
+                  }
+                } else if (acc_mode == 1) {
+                  const uint32_t fl = tap_merged_probe<KSTEPS, false>(d_tmem, d_tmem, ad, ad + a_plane16, bd, idesc2, idesc,
+                                                                      accumulate, nb_bar, nb_par, na_bar, na_par);
                   b_ready = (fl & 1u) != 0;
                   a_next_ready = (fl & 2u) != 0;
                 } else if (acc_mode == 3) {
@@ -434,20 +486,27 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                     for (int k = 0; k < KSTEPS; ++k) ptx::umma_bf16(d_tmem, ad + a_plane16 + 2 * k, bd + 2 * k, idesc, 1);
                   }
                 }
-                if (CS > 1) ptx::umma_commit_mc(&b_empty[sb], kMask);
+                if (pair) ptx::umma_commit_2sm(&b_empty[sb], kMask);
+                else if (CS > 1) ptx::umma_commit_mc(&b_empty[sb], kMask);
                 else ptx::umma_commit(&b_empty[sb]);
               }
               accumulate = 1;
               if (++sb == p.SB) { sb = 0; b_par ^= 1; }
             }
-            if (leader) ptx::umma_commit(&a_empty[sa]);
+            if (leader) {
+              if (pair) ptx::umma_commit_2sm(&a_empty[sa], kMask);
+              else ptx::umma_commit(&a_empty[sa]);
+            }
             a_ready = a_next_ready;   // the probe fused into this slot's last tap
             a_next_ready = false;
             __syncwarp();
             if (++sa == p.SA) { sa = 0; a_par ^= 1; }
           }
         }
-        if (leader) ptx::umma_commit(&acc_full[as]);
+        if (leader) {
+          if (pair) ptx::umma_commit_2sm(&acc_full[as], kMask);
+          else ptx::umma_commit(&acc_full[as]);
+        }
         as ^= 1;
       }
       if (p.prof && leader) {
@@ -523,10 +582,18 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         // -- phase 1: TMEM -> registers -> smem staging [128][CW+4] (raw fp32 accumulators)
         for (int c0 = colsel * 32; c0 < CW; c0 += 64) {
           uint32_t v[32];
-          ptx::tmem_ld_32x32(t_acc + (uint32_t)(cc + c0), v);
+          // accumulator columns of the 32 channels [cc + c0, +32): block 0 and the block(s) the epilogue adds to it
+          uint32_t col0 = (uint32_t)(cc + c0), col1 = (uint32_t)(p.BN + cc + c0);
+          if (pair && NSPLIT == 2) {
+            const uint32_t hb = (uint32_t)p.BN >> 1, cb = (uint32_t)(cc + c0);
+            const uint32_t half = cb >= hb ? 1u : 0u;
+            col0 = half * (uint32_t)p.BN + (cb - half * hb);
+            col1 = col0 + hb;
+          }
+          ptx::tmem_ld_32x32(t_acc + col0, v);
           if (p.nsum >= 2) {
             uint32_t v2[32];
-            ptx::tmem_ld_32x32(t_acc + (uint32_t)(p.BN + cc + c0), v2);
+            ptx::tmem_ld_32x32(t_acc + col1, v2);
             ptx::tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
@@ -549,7 +616,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
           // last chunk read: hand the accumulator stage back to the MMA warp (one arrive per epilogue warp)
           ptx::tc_fence_before();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&acc_empty[as]);
+          if (lane == 0) {
+            if (pair && rank != 0) ptx::mbar_arrive_leader(&acc_empty[as]);   // rank 0's MMA thread waits for both CTAs
+            else ptx::mbar_arrive(&acc_empty[as]);
+          }
         }
         ptx::named_bar_sync(1, kEpiThreads);
 
@@ -741,7 +811,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
 
   __syncthreads();
   if (CS > 1) ptx::cluster_sync_all();   // no CTA exits while a peer may still arrive on its barriers
-  if (warp == 1) ptx::tmem_dealloc(tmem_base, tmem_cols);
+  if (warp == 1) {
+    if (pair) ptx::tmem_dealloc2(tmem_base, tmem_cols);
+    else ptx::tmem_dealloc(tmem_base, tmem_cols);
+  }
 }
 
 // Tile shape for an H x W map: BW % 8 == 0, BH*BW <= 128, maximise useful rows then minimise halo.
@@ -846,9 +919,9 @@ extern "C" int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* 
   static int win_env = -1;
   if (win_env < 0) {
     const char* e = getenv("EGAZE_CONV_WINDOW");
-    win_env = e ? atoi(e) : 0;
+    win_env = e ? atoi(e) : 1;
   }
-  static int win_minsb = 3;
+  static int win_minsb = 2;
   if (win_env > 0 && p.KC == 64) {
     const char* e = getenv("EGAZE_CONV_WINDOW_MINSB");
     if (e) win_minsb = atoi(e);
@@ -882,7 +955,18 @@ extern "C" int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* 
   // window mode: the MMA always walks 16 row groups, (BW+2) window rows apart, from up to 2 rows + 2 pixels in
   if (p.win) a_rows = 17 * (p.BW + 2) + 2 + 8;
   p.a_slot_bytes = ((a_rows * row_bytes + 1023) / 1024) * 1024;
-  p.b_slot_bytes = ((p.BN * row_bytes + 1023) / 1024) * 1024;
+  // CTA-pair MMA (cta_group::2): needs the merged two-plane weight slot (or the single-plane fast mode), 32-column epilogue
+  // blocks that stay inside one channel half (BN >= 64) and N <= 256
+  {
+    static int pair_env = -1;
+    if (pair_env < 0) {
+      const char* e = getenv("EGAZE_CONV_PAIR");
+      pair_env = e ? atoi(e) : 1;
+    }
+    p.pair = (pair_env && CS == 2 && p.BN >= 64 && p.BN <= 128 && (p.BN / 2 * row_bytes) % 1024 == 0) ? 1 : 0;
+  }
+  const int b_plane_rows = p.pair ? p.BN / 2 : p.BN;   // weight rows of one plane kept in THIS CTA's slot
+  p.b_slot_bytes = ((b_plane_rows * row_bytes + 1023) / 1024) * 1024;
   const int CW = p.BN < 64 ? p.BN : 64;
   const int stage_bytes = ((128 * (CW + 4) * 4 + 4 * 64 * 3 * 4 + (stats ? Cout * 3 * 4 : 0) + (colsum ? Cout * 4 : 0) + 1023) / 1024) * 1024;
   static int sa_env = -1;
@@ -906,7 +990,7 @@ extern "C" int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* 
       const char* e = getenv("EGAZE_CONV_ACCMODE");
       mode_env = e ? atoi(e) : -1;
     }
-    const bool can_merge = p.b_slot_bytes == p.BN * row_bytes && 2 * p.BN <= 256;
+    const bool can_merge = p.b_slot_bytes == b_plane_rows * row_bytes && 2 * p.BN <= 256;
     int mode = 0;
     if (precise) {
       // measured (B=32 SP layers): mode 1 beats 2 and 3 -- fewer, larger MMAs win; the extra smem operand reads of mode 3
@@ -915,6 +999,10 @@ extern "C" int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* 
       if (mode_env >= 0) mode = mode_env;
       if ((mode == 1 || mode == 2) && !can_merge) mode = 3;
       if (mode == 2 && p.BN > 64) mode = 1;
+      if (p.pair) {
+        EGAZE_CHECK_ARG(can_merge, "conv3x3_tc: CTA-pair mode needs the merged weight slot");
+        mode = 1;
+      }
     }
     p.acc_mode = mode;
     p.nsum = mode == 0 ? 1 : (mode == 2 ? 3 : 2);

@@ -131,3 +131,54 @@ def test_fast_mode_reported(cuda_dev):
     err = (got - ref).abs().max().item()
     print("fast-mode gaze map max-abs err: %.3e" % err)
     assert err <= 0.25
+
+
+def test_at_sequence_vs_oracle_frame_loop(cuda_dev):
+    """BASELINE configs[2] shape of work (AT over feature sequences): the batched path -- one crop-mean over all T*B frames,
+    one LSTM call over the T steps, one weighted-map over all frames -- against the NumPy oracle walking the sequences frame
+    by frame the way AT.extract_late does (AT.py:224-252)."""
+    import numpy as np
+    import models.LSTMnet as L
+    from egaze import ops
+    from oracle import egaze_oracle as orc
+    T, NB = 6, 3
+    torch.manual_seed(3)
+    net = L.lstmnet().to(cuda_dev).eval()
+    g = torch.Generator().manual_seed(9)
+    feat = torch.relu(torch.randn(T * NB, 512, 14, 14, generator=g))
+    gaze = torch.randint(0, 224, (T * NB, 2), generator=g).int()
+    with torch.no_grad():
+        vec = ops.crop_mean(feat.to(cuda_dev), gaze.to(cuda_dev), 3)
+        hid = (torch.zeros(2, NB, 512, device=cuda_dev), torch.zeros(2, NB, 512, device=cuda_dev))
+        w, _ = net(vec.view(T, NB, 512), hid)
+        got = ops.weighted_map(w.reshape(T * NB, 512), feat.to(cuda_dev)).cpu().numpy()
+    sd = {k: v.detach().cpu().numpy() for k, v in net.state_dict().items()}
+    h = np.zeros((2, NB, 512), np.float32)
+    c = np.zeros((2, NB, 512), np.float32)
+    fn, gn = feat.numpy(), gaze.numpy()
+    for t in range(T):
+        f_t, g_t = fn[t * NB:(t + 1) * NB], gn[t * NB:(t + 1) * NB]
+        v = orc.crop_mean(f_t, g_t, 3)
+        out, h, c = orc.lstmnet_forward(sd, v[None], h, c)
+        for b in range(NB):   # the reference normalises each frame's map on its own (batch 1)
+            ref = orc.get_weighted(out[0, b:b + 1], f_t[b:b + 1])
+            assert np.abs(got[t * NB + b] - ref[0]).max() <= 1e-4
+
+
+def test_full_pipeline_train_step(cuda_dev):
+    """BASELINE configs[3] per rank at a small size: SP train step, AT step on the hooked map, LF train step; the two
+    losses must match stock PyTorch modules fed the same parameters and inputs."""
+    import bench
+    wl = bench.Workload("full_train", 2, 64, 0, 1, cuda_dev)
+    import copy
+    sp_ref, lf_ref = copy.deepcopy(wl.model), copy.deepcopy(wl.lf)
+    lf_before = [p.detach().clone() for p in wl.lf.parameters()]
+    losses = wl.step(*wl.dev).cpu()
+    assert torch.isfinite(losses).all()
+    x_s, x_t, gt = wl.dev
+    ref_out = torch_ref.model_sp_forward(sp_ref, x_s, x_t)
+    ref_loss = torch_ref.floss_loss(ref_out, gt)
+    assert abs(losses[0].item() - ref_loss.item()) <= 1e-3 * abs(ref_loss.item())
+    assert any((p.detach() - q).abs().max().item() > 0 for p, q in zip(wl.lf.parameters(), lf_before))
+    losses2 = wl.step(*wl.dev).cpu()
+    assert torch.isfinite(losses2).all()
