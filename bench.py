@@ -42,11 +42,12 @@ FLOP_LF_FWD = 1.2147e9
 
 def load_traffic(workload):
     """DRAM bytes per launch of the tcgen05 conv kernels (dram__bytes_read.sum + dram__bytes_write.sum averaged over the
-    conv/wgrad launches of one step), from the committed ncu capture of this same command (profiles/*_traffic.json)."""
+    conv/wgrad launches of one step), from the committed ncu capture of this same command (profiles/conv_traffic.json,
+    raw per-launch list beside it)."""
     try:
         with open(os.path.join(ROOT, "profiles", "conv_traffic.json")) as fh:
             d = json.load(fh)
-        return d.get(workload)
+        return float(d[workload]["bytes_per_launch"])
     except Exception:
         return None
 

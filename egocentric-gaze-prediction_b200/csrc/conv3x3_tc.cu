@@ -133,8 +133,11 @@ __device__ __forceinline__ float4 epi_affine(float4 a, const float4& s, const fl
 // Phase 3 of the epilogue with every mode flag resolved at compile time and power-of-two tile widths: the accumulator
 // tile is drained at ~40 instructions per float4 instead of ~220 in the flag-driven loop.  Layers with a short K loop
 // (K = 9*64 .. 9*128) are bound by exactly this loop, not by the MMAs.
-template <int RED, bool MASK, bool UPS, bool F32, bool SPLIT>
-__device__ __forceinline__ void epi_store(const ConvTcParams& p, const EpiTile& e, float4& cs) {
+// STATS: also accumulate the BatchNorm sums of the raw accumulators, shifted by the per-channel reference k4:
+// s1 += a - k, s2 += (a - k)^2.
+template <int RED, bool MASK, bool UPS, bool F32, bool SPLIT, bool STATS = false>
+__device__ __forceinline__ void epi_store(const ConvTcParams& p, const EpiTile& e, float4& cs, float4 k4 = float4(),
+                                          float4* s1 = nullptr, float4* s2 = nullptr) {
   const int obw_mask = (1 << e.obw_log) - 1;
 #pragma unroll 2
   for (int pix = e.pl; pix < e.npix; pix += e.PS) {
@@ -142,7 +145,13 @@ __device__ __forceinline__ void epi_store(const ConvTcParams& p, const EpiTile& 
     if (ph >= e.vh || pw >= e.vw) continue;
     float4 v;
     if (RED == 0) {
-      v = epi_affine(ptx::lds128(e.st_addr + (uint32_t)(pix * e.ldst_b)), e.s4, e.t4, e.lo_clamp);
+      const float4 a = ptx::lds128(e.st_addr + (uint32_t)(pix * e.ldst_b));
+      if (STATS) {
+        const float dx = a.x - k4.x, dy = a.y - k4.y, dz = a.z - k4.z, dw = a.w - k4.w;
+        s1->x += dx; s1->y += dy; s1->z += dz; s1->w += dw;
+        s2->x = fmaf(dx, dx, s2->x); s2->y = fmaf(dy, dy, s2->y); s2->z = fmaf(dz, dz, s2->z); s2->w = fmaf(dw, dw, s2->w);
+      }
+      v = epi_affine(a, e.s4, e.t4, e.lo_clamp);
     } else {
       const uint32_t rb = e.st_addr + (uint32_t)(((2 * ph) * e.BW + 2 * pw) * e.ldst_b);
       const float4 a = epi_affine(ptx::lds128(rb), e.s4, e.t4, e.lo_clamp);
@@ -310,7 +319,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
+    // Like the MMA warp: the whole warp walks the loop nest (warp-uniform control flow keeps the tensor-map pointers, box
+    // coordinates and barrier addresses in uniform registers) and one elected lane waits / issues.  Under `if (lane == 0)`
+    // every UTMALDG operand went through R2UR and the producer needed ~500 cycles per tap -- more than a tap's MMAs take
+    // in the 64-channel layers.
+    {
+      const bool leader = ptx::elect_one();
       int sa = 0, sb = 0;
       long long prof_c[2] = {0, 0};
       const long long prof_start = p.prof ? clock64() : 0;
@@ -320,50 +334,54 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         const int n0 = it.nt * p.BN;
         for (int kc = 0; kc < chunks; ++kc) {
           for (int al = 0; al < a_loads; ++al) {
-            { PROF_T0(p); ptx::mbar_wait(&a_empty[sa], a_par); PROF_ADD(p, prof_c[0]); }
             uint8_t* a_dst = a_ring + (size_t)sa * NSPLIT * p.a_slot_bytes;
             const int wx = p.win ? it.w0 - 1 : it.w0 - 1 + al;
-            if (pair) {
-              // both CTAs' windows are accounted on rank 0's barrier (its MMA thread consumes both)
-              if (rank == 0) ptx::mbar_arrive_expect_tx(&a_full[sa], 2 * a_box_bytes * NSPLIT);
-              ptx::tma_load_4d_2sm(a_dst, &tmA_hi, &a_full[sa], kc * p.KC, wx, it.h0 - 1, it.img);
-              if (NSPLIT == 2)
-                ptx::tma_load_4d_2sm(a_dst + p.a_slot_bytes, &tmA_lo, &a_full[sa], kc * p.KC, wx, it.h0 - 1, it.img);
-            } else {
-              ptx::mbar_arrive_expect_tx(&a_full[sa], a_box_bytes * NSPLIT);
-              ptx::tma_load_4d(a_dst, &tmA_hi, &a_full[sa], kc * p.KC, wx, it.h0 - 1, it.img);
-              if (NSPLIT == 2)
-                ptx::tma_load_4d(a_dst + p.a_slot_bytes, &tmA_lo, &a_full[sa], kc * p.KC, wx, it.h0 - 1, it.img);
+            if (leader) {
+              { PROF_T0(p); ptx::mbar_wait(&a_empty[sa], a_par); PROF_ADD(p, prof_c[0]); }
+              if (pair) {
+                // both CTAs' windows are accounted on rank 0's barrier (its MMA thread consumes both)
+                if (rank == 0) ptx::mbar_arrive_expect_tx(&a_full[sa], 2 * a_box_bytes * NSPLIT);
+                ptx::tma_load_4d_2sm(a_dst, &tmA_hi, &a_full[sa], kc * p.KC, wx, it.h0 - 1, it.img);
+                if (NSPLIT == 2)
+                  ptx::tma_load_4d_2sm(a_dst + p.a_slot_bytes, &tmA_lo, &a_full[sa], kc * p.KC, wx, it.h0 - 1, it.img);
+              } else {
+                ptx::mbar_arrive_expect_tx(&a_full[sa], a_box_bytes * NSPLIT);
+                ptx::tma_load_4d(a_dst, &tmA_hi, &a_full[sa], kc * p.KC, wx, it.h0 - 1, it.img);
+                if (NSPLIT == 2)
+                  ptx::tma_load_4d(a_dst + p.a_slot_bytes, &tmA_lo, &a_full[sa], kc * p.KC, wx, it.h0 - 1, it.img);
+              }
             }
             if (++sa == p.SA) { sa = 0; a_par ^= 1; }
             for (int t = 0; t < a_taps; ++t) {
               const int s = p.win ? t / 3 : al, r = p.win ? t - 3 * s : t;
-              { PROF_T0(p); ptx::mbar_wait(&b_empty[sb], b_par); PROF_ADD(p, prof_c[1]); }   // every CTA of the cluster has drained this slot
               const int brow = (r * 3 + s) * p.Cout + n0 + rank * b_rows_cta;
-              if (pair) {
-                // this CTA keeps only ITS half of the box (rows rank*BN/2 ..), hi plane then lo plane back to back
-                if (rank == 0) ptx::mbar_arrive_expect_tx(&b_full[sb], b_box_bytes * NSPLIT);
-                uint8_t* b_dst = b_ring + (size_t)sb * NSPLIT * p.b_slot_bytes;
-                ptx::tma_load_2d_2sm(b_dst, &tmB_hi, &b_full[sb], kc * p.KC, brow);
-                if (NSPLIT == 2) ptx::tma_load_2d_2sm(b_dst + p.b_slot_bytes, &tmB_lo, &b_full[sb], kc * p.KC, brow);
-                if (++sb == p.SB) { sb = 0; b_par ^= 1; }
-                continue;
-              }
-              ptx::mbar_arrive_expect_tx(&b_full[sb], b_box_bytes * NSPLIT);
-              uint8_t* b_dst = b_ring + (size_t)sb * NSPLIT * p.b_slot_bytes + (size_t)rank * b_rows_cta * row_bytes;
-              if (CS > 1) {
-                ptx::tma_load_2d_mc(b_dst, &tmB_hi, &b_full[sb], kc * p.KC, brow, kMask);
-                if (NSPLIT == 2) ptx::tma_load_2d_mc(b_dst + p.b_slot_bytes, &tmB_lo, &b_full[sb], kc * p.KC, brow, kMask);
-              } else {
-                ptx::tma_load_2d(b_dst, &tmB_hi, &b_full[sb], kc * p.KC, brow);
-                if (NSPLIT == 2) ptx::tma_load_2d(b_dst + p.b_slot_bytes, &tmB_lo, &b_full[sb], kc * p.KC, brow);
+              // pair mode: this CTA keeps only ITS half of the box (rows rank*BN/2 ..), hi plane then lo plane back to back;
+              // multicast mode: it fetches its half and multicasts it into every CTA's full-size slot
+              uint8_t* b_dst = b_ring + (size_t)sb * NSPLIT * p.b_slot_bytes + (pair ? 0 : (size_t)rank * b_rows_cta * row_bytes);
+              if (leader) {
+                { PROF_T0(p); ptx::mbar_wait(&b_empty[sb], b_par); PROF_ADD(p, prof_c[1]); }   // the slot has been drained
+                if (pair) {
+                  if (rank == 0) ptx::mbar_arrive_expect_tx(&b_full[sb], b_box_bytes * NSPLIT);
+                  ptx::tma_load_2d_2sm(b_dst, &tmB_hi, &b_full[sb], kc * p.KC, brow);
+                  if (NSPLIT == 2) ptx::tma_load_2d_2sm(b_dst + p.b_slot_bytes, &tmB_lo, &b_full[sb], kc * p.KC, brow);
+                } else {
+                  ptx::mbar_arrive_expect_tx(&b_full[sb], b_box_bytes * NSPLIT);
+                  if (CS > 1) {
+                    ptx::tma_load_2d_mc(b_dst, &tmB_hi, &b_full[sb], kc * p.KC, brow, kMask);
+                    if (NSPLIT == 2) ptx::tma_load_2d_mc(b_dst + p.b_slot_bytes, &tmB_lo, &b_full[sb], kc * p.KC, brow, kMask);
+                  } else {
+                    ptx::tma_load_2d(b_dst, &tmB_hi, &b_full[sb], kc * p.KC, brow);
+                    if (NSPLIT == 2) ptx::tma_load_2d(b_dst + p.b_slot_bytes, &tmB_lo, &b_full[sb], kc * p.KC, brow);
+                  }
+                }
               }
               if (++sb == p.SB) { sb = 0; b_par ^= 1; }
             }
+            __syncwarp();
           }
         }
       }
-      if (p.prof) {
+      if (p.prof && leader) {
         long long* o = p.prof + (size_t)blockIdx.x * 16;
         o[0] = prof_c[0]; o[1] = prof_c[1]; o[2] = clock64() - prof_start;
       }
@@ -525,8 +543,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     const int CW = p.BN < 64 ? p.BN : 64;    // staged column chunk (power of two)
     const int ldst = CW + 4;                 // padded staging row (floats)
     const uint32_t stage_s = ptx::smem_u32(stage);
-    float* red = stage + (size_t)128 * ldst; // [4][64][3] floats of scratch
-    float* run_stats = red + 4 * 64 * 3;     // [Cout][3] running (n, mean, M2) of this CTA (BatchNorm statistics)
+    float* red = stage + (size_t)128 * ldst; // scratch: [tiles_n] pixel counts behind the BatchNorm sums
+    // BatchNorm statistics of this CTA, per output channel: reference value k (the first accumulator the CTA saw for the
+    // channel), s1 = sum(a - k), s2 = sum((a - k)^2) over every pixel it stored.  Shifting by k keeps both sums small, so
+    // mean = k + s1/n and M2 = s2 - s1^2/n lose nothing to cancellation.
+    float* run_stats = red + 4 * 64 * 3;     // [3][Cout]: k, s1, s2
+    float* st_k = run_stats;
+    float* st_s1 = run_stats + p.Cout;
+    float* st_s2 = run_stats + 2 * p.Cout;
+    unsigned long long st_seen = 0;          // bit per CW-channel block: k has been chosen (uniform across the epilogue threads)
     float* colsum_s = run_stats + (p.stats ? p.Cout * 3 : 0);   // [Cout] column sums of this CTA (bias gradient)
     if (p.colsum) {
       for (int i = et; i < p.Cout; i += kEpiThreads) colsum_s[i] = 0.f;
@@ -534,6 +559,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     }
     if (p.stats) {
       for (int i = et; i < p.Cout * 3; i += kEpiThreads) run_stats[i] = 0.f;
+      for (int i = et; i < p.tiles_n; i += kEpiThreads) red[i] = 0.f;
       ptx::named_bar_sync(1, kEpiThreads);
     }
     const int gpp = CW >> 2;                 // float4 channel groups per pixel (power of two)
@@ -624,51 +650,19 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         ptx::named_bar_sync(1, kEpiThreads);
 
         float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 k4 = cs, s1v = cs, s2v = cs;
         if (it.valid) {
-          // -- phase 2: per-tile BatchNorm statistics of (acc + bias): mean and M2 over the tile's valid pixels.
-          //    4 threads per column (row quarters), merged with Chan's formula.
+          // -- phase 2: BatchNorm statistics are accumulated inside the store loop below (shifted sums, see st_k).  The first
+          //    time the CTA meets a channel block it fixes the block's reference values: row 0 of the staged tile.
           if (p.stats) {
-            const int vh = min(p.BH, p.H - h0), vw = min(p.BW, p.W - w0);   // valid extent of this tile
-            const int c = et & 63, q = et >> 6;
-            const int r0 = (q * vh) >> 2, r1 = ((q + 1) * vh) >> 2;
-            const int n_loc = (r1 - r0) * vw;
-            float sum = 0.f, mean = 0.f, m2 = 0.f;
-            if (c < CW && n_loc > 0) {
-              for (int th = r0; th < r1; ++th) {
-                const uint32_t rowp = stage_s + (uint32_t)(((th * p.BW) * ldst + c) * 4);
-                for (int tw = 0; tw < vw; ++tw) sum += ptx::lds32(rowp + (uint32_t)(tw * ldst * 4));
-              }
-              mean = sum / (float)n_loc;
-              for (int th = r0; th < r1; ++th) {
-                const uint32_t rowp = stage_s + (uint32_t)(((th * p.BW) * ldst + c) * 4);
-                for (int tw = 0; tw < vw; ++tw) {
-                  const float d = ptx::lds32(rowp + (uint32_t)(tw * ldst * 4)) - mean;
-                  m2 = fmaf(d, d, m2);
-                }
-              }
+            const int blk = n0 / CW;
+            if (!((st_seen >> blk) & 1ull)) {
+              if (et < CW) st_k[n0 + et] = stage[et];
+              ptx::named_bar_sync(2, kEpiThreads);
+              st_seen |= 1ull << blk;
             }
-            if (c < CW) {
-              float* rp = red + (size_t)(q * 64 + c) * 3;
-              rp[0] = mean; rp[1] = m2; rp[2] = (float)n_loc;
-            }
-            ptx::named_bar_sync(2, kEpiThreads);
-            if (q == 0 && c < CW) {
-              // merge the four row quarters, then fold the tile into this CTA's running (n, mean, M2) of the column
-              float* run = run_stats + (size_t)(it.nt * p.BN + cc + c) * 3;
-              float na = run[0], ma = run[1], m2a = run[2];
-#pragma unroll
-              for (int qq = 0; qq < 4; ++qq) {
-                const float* rp = red + (size_t)(qq * 64 + c) * 3;
-                const float nb = rp[2];
-                if (nb > 0.f) {
-                  const float nn = na + nb, d = rp[0] - ma;
-                  ma += d * nb / nn;
-                  m2a += rp[1] + d * d * na * nb / nn;
-                  na = nn;
-                }
-              }
-              run[0] = na; run[1] = ma; run[2] = m2a;
-            }
+            k4 = *reinterpret_cast<const float4*>(st_k + n0 + g * 4);
+            if (cc == 0 && et == 0) red[it.nt] += (float)(min(p.BH, p.H - h0) * min(p.BW, p.W - w0));
           }
 
           // -- phase 3: (+bias, *scale+shift, relu) -> 2x2 max/sum -> mask -> coalesced NHWC stores.
@@ -701,8 +695,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
             e.mask_base = ((size_t)(img * mf * Ho + mf * oh0) * (mf * Wo) + (size_t)(mf * ow0)) * p.Cout + ch;
             e.mask_row = mf * mf * Wo * p.Cout; e.mask_px = mf * p.Cout;
             done = true;
-            switch (lean_mode) {
-              case 1: epi_store<0, false, false, true, false>(p, e, cs); break;   // fp32 out: train-mode trunk / dgrad into BN
+            switch (p.stats && lean_mode != 1 ? 0 : lean_mode) {
+              case 1:                                                              // fp32 out: train-mode trunk / dgrad into BN
+                if (p.stats) epi_store<0, false, false, true, false, true>(p, e, cs, k4, &s1v, &s2v);
+                else epi_store<0, false, false, true, false>(p, e, cs);
+                break;
               case 2: epi_store<0, false, false, false, true>(p, e, cs); break;   // split out: decoder / eval trunk
               case 3: epi_store<0, false, true, false, true>(p, e, cs); break;    // ... + nearest-2x replicate
               case 4: epi_store<1, false, false, false, true>(p, e, cs); break;   // ... + 2x2 max-pool
@@ -727,6 +724,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
               };
               if (p.reduce == 0) {
                 v = fetch(ph * p.BW + pw);
+                if (p.stats) {
+                  const float4 a = *reinterpret_cast<const float4*>(stage + (size_t)(ph * p.BW + pw) * ldst + g * 4);
+                  const float dx = a.x - k4.x, dy = a.y - k4.y, dz = a.z - k4.z, dw = a.w - k4.w;
+                  s1v.x += dx; s1v.y += dy; s1v.z += dz; s1v.w += dw;
+                  s2v.x = fmaf(dx, dx, s2v.x); s2v.y = fmaf(dy, dy, s2v.y); s2v.z = fmaf(dz, dz, s2v.z); s2v.w = fmaf(dw, dw, s2v.w);
+                }
               } else {
                 const int rb = (2 * ph) * p.BW + 2 * pw;
                 const float4 a = fetch(rb), b = fetch(rb + 1), c = fetch(rb + p.BW), d = fetch(rb + p.BW + 1);
@@ -774,6 +777,20 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
             while (pw >= oBW) { pw -= oBW; ++ph; }
           }
         }
+        if (p.stats && it.valid) {
+          for (int o = 16; o >= gpp; o >>= 1) {
+            s1v.x += __shfl_xor_sync(0xffffffffu, s1v.x, o); s1v.y += __shfl_xor_sync(0xffffffffu, s1v.y, o);
+            s1v.z += __shfl_xor_sync(0xffffffffu, s1v.z, o); s1v.w += __shfl_xor_sync(0xffffffffu, s1v.w, o);
+            s2v.x += __shfl_xor_sync(0xffffffffu, s2v.x, o); s2v.y += __shfl_xor_sync(0xffffffffu, s2v.y, o);
+            s2v.z += __shfl_xor_sync(0xffffffffu, s2v.z, o); s2v.w += __shfl_xor_sync(0xffffffffu, s2v.w, o);
+          }
+          if (lane < gpp) {
+            float* d1 = st_s1 + n0 + g * 4;
+            float* d2 = st_s2 + n0 + g * 4;
+            atomicAdd(d1 + 0, s1v.x); atomicAdd(d1 + 1, s1v.y); atomicAdd(d1 + 2, s1v.z); atomicAdd(d1 + 3, s1v.w);
+            atomicAdd(d2 + 0, s2v.x); atomicAdd(d2 + 1, s2v.y); atomicAdd(d2 + 2, s2v.z); atomicAdd(d2 + 3, s2v.w);
+          }
+        }
         if (p.colsum && it.valid) {
           // threads of a warp that share a channel group are gpp lanes apart: fold them, then one smem atomic per channel
           for (int o = 16; o >= gpp; o >>= 1) {
@@ -800,11 +817,18 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     }
     if (p.stats) {
       // one (mean, M2, n) partial per CTA and channel; bias shifts the mean only
+      ptx::named_bar_sync(1, kEpiThreads);
       for (int c = et; c < p.Cout; c += kEpiThreads) {
-        const float* run = run_stats + (size_t)c * 3;
-        p.stats[((size_t)blockIdx.x * 2 + 0) * p.Cout + c] = run[1] + (p.bias ? __ldg(p.bias + c) : 0.f);
-        p.stats[((size_t)blockIdx.x * 2 + 1) * p.Cout + c] = run[2];
-        if (c % p.BN == 0) p.stats_cnt[(size_t)blockIdx.x * p.tiles_n + c / p.BN] = run[0];
+        const float n = red[c / p.BN];
+        float mean = 0.f, m2 = 0.f;
+        if (n > 0.f) {
+          const float s1 = st_s1[c];
+          mean = st_k[c] + s1 / n;
+          m2 = fmaxf(st_s2[c] - s1 * s1 / n, 0.f);
+        }
+        p.stats[((size_t)blockIdx.x * 2 + 0) * p.Cout + c] = mean + (p.bias ? __ldg(p.bias + c) : 0.f);
+        p.stats[((size_t)blockIdx.x * 2 + 1) * p.Cout + c] = m2;
+        if (c % p.BN == 0) p.stats_cnt[(size_t)blockIdx.x * p.tiles_n + c / p.BN] = n;
       }
     }
   }

@@ -106,16 +106,19 @@ __global__ void pack_w3x3_kernel(const float* __restrict__ w, int Co, int Ci, in
   }
 }
 
-// dwp: [9][Co][Ci_p] fp32 (wgrad accumulator)  ->  gw: OIHW [Co][Ci][3][3]  (gw = beta*gw + dwp)
-__global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, int Co, int Ci, int Ci_p, float beta,
+// dwp: [9][Co_p][Ci_p] fp32 (wgrad accumulator)  ->  gw: OIHW [Co][Ci][3][3]  (gw = beta*gw + dwp).
+// clear != 0: the accumulator is zeroed on the way out, so a persistent buffer is ready for the next accumulation.
+__global__ void unpack_wgrad_kernel(float* __restrict__ dwp, int Co, int Ci, int Co_p, int Ci_p, float beta, int clear,
                                     float* __restrict__ gw) {
-  const size_t total = (size_t)Co * Ci * 9;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int tap = (int)(i % 9);
-    const int ci = (int)((i / 9) % Ci);
-    const int co = (int)(i / ((size_t)9 * Ci));
-    const float v = dwp[((size_t)tap * Co + co) * Ci_p + ci];
-    gw[i] = beta == 0.f ? v : fmaf(beta, gw[i], v);
+  const uint32_t total = (uint32_t)9 * Co_p * Ci_p;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const uint32_t ci = i % Ci_p, t = i / Ci_p, co = t % Co_p, tap = t / Co_p;
+    const float v = dwp[i];
+    if (clear) dwp[i] = 0.f;
+    if (co < (uint32_t)Co && ci < (uint32_t)Ci) {
+      float* dst = gw + ((size_t)co * Ci + ci) * 9 + tap;
+      *dst = beta == 0.f ? v : fmaf(beta, *dst, v);
+    }
   }
 }
 
@@ -176,13 +179,13 @@ extern "C" int egaze_pack_w3x3(const float* w_oihw, int Cout, int Cin, int cols_
   return EGAZE_OK;
 }
 
-extern "C" int egaze_unpack_wgrad(const float* dwp, int Cout, int Cin, int Cin_p, float beta, float* gw_oihw,
+extern "C" int egaze_unpack_wgrad(float* dwp, int Cout, int Cin, int Cout_p, int Cin_p, float beta, int clear, float* gw_oihw,
                                   void* stream) {
-  EGAZE_CHECK_ARG(dwp && gw_oihw, "unpack_wgrad: bad args");
-  const size_t total = (size_t)Cout * Cin * 9;
+  EGAZE_CHECK_ARG(dwp && gw_oihw && Cout_p >= Cout && Cin_p >= Cin, "unpack_wgrad: bad args");
+  const size_t total = (size_t)9 * Cout_p * Cin_p;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  unpack_wgrad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dwp, Cout, Cin, Cin_p, beta, gw_oihw);
+  unpack_wgrad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dwp, Cout, Cin, Cout_p, Cin_p, beta, clear, gw_oihw);
   EGAZE_LAUNCH_CHECK();
   return EGAZE_OK;
 }

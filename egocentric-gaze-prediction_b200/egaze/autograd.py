@@ -59,6 +59,12 @@ def _dgrad(conv, gpre_act, **kw):
     return ops.conv3x3(gpre_act, wpack, **kw)
 
 
+def _first_cp(conv):
+    """Channel padding of a trunk's input.  When the first conv's weight is trained the input is laid out with the 64-channel
+    stride its weight-gradient GEMM needs, instead of being re-padded (two extra copies per plane) in the backward."""
+    return 64 if (_req(conv.weight) and conv.in_channels <= 64) else ops.pad_channels(conv.in_channels)
+
+
 def _any_req(mods):
     return any(p.requires_grad for m in mods for p in m.parameters())
 
@@ -132,8 +138,8 @@ class _ModelSPFn(torch.autograd.Function):
         saved_s, saved_t, saved_tail = [], [], []
         specs_s, _ = engine.parse_sequential(model.features_s)
         specs_t, _ = engine.parse_sequential(model.features_t)
-        a_s = ops.to_split(x_s, ops.pad_channels(specs_s[0].conv.in_channels))
-        a_t = ops.to_split(x_t, ops.pad_channels(specs_t[0].conv.in_channels))
+        a_s = ops.to_split(x_s, _first_cp(specs_s[0].conv))
+        a_t = ops.to_split(x_t, _first_cp(specs_t[0].conv))
         for sp in specs_s:
             a_s = engine.run_conv_spec(a_s, sp, saved_s)
         for sp in specs_t:
@@ -208,7 +214,7 @@ class _SequentialFn(torch.autograd.Function):
         if tail is not None or any(sp.bn is None for sp in specs):
             raise NotImplementedError("egaze: stand-alone training is implemented for conv+BN+ReLU trunks")
         saved = []
-        act = ops.to_split(x, ops.pad_channels(specs[0].conv.in_channels))
+        act = ops.to_split(x, _first_cp(specs[0].conv))
         for sp in specs:
             act = engine.run_conv_spec(act, sp, saved)
         ctx.seq, ctx.rec, ctx.need_x = seq, (specs, saved), x.requires_grad
@@ -239,7 +245,7 @@ class _VGGFn(torch.autograd.Function):
     def forward(ctx, model, x, *params):
         specs, _ = engine.parse_sequential(model.features)
         saved_f, saved_d = [], []
-        act = ops.to_split(x, ops.pad_channels(specs[0].conv.in_channels))
+        act = ops.to_split(x, _first_cp(specs[0].conv))
         for sp in specs:
             act = engine.run_conv_spec(act, sp, saved_f)
         feat_act = act

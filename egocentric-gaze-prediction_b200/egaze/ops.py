@@ -315,7 +315,11 @@ def wgrad3x3(x_act, dy_act, Cout, Cin, precise=None):
     dy_act = repad(dy_act, (dy_act.Cp + 63) // 64 * 64)
     N, H, W = x_act.N, x_act.H, x_act.W
     dev = x_act.hi.device
-    dwp = torch.zeros((9, dy_act.Cp, x_act.Cp), dtype=F32, device=dev)
+    # persistent accumulator per shape: allocated zeroed once, left zeroed again by egaze_unpack_wgrad (clear=1)
+    key = (dy_act.Cp, x_act.Cp, dev)
+    dwp = _dwp_cache.get(key)
+    if dwp is None:
+        dwp = _dwp_cache[key] = torch.zeros((9, dy_act.Cp, x_act.Cp), dtype=F32, device=dev)
     if _conv_timer["on"]:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
@@ -325,12 +329,11 @@ def wgrad3x3(x_act, dy_act, Cout, Cin, precise=None):
         ev1.record()
         _conv_timer["events"].append((ev0, ev1, ("wgrad", N, H, W, x_act.Cp, dy_act.Cp, 0, 0, False)))
     gw = torch.empty((Cout, Cin, 3, 3), dtype=F32, device=dev)
-    if dy_act.Cp != Cout:
-        dwp = dwp[:, :Cout].contiguous()
-    call("egaze_unpack_wgrad", dwp, Cout, Cin, x_act.Cp, 0.0, gw, stream_ptr())
+    call("egaze_unpack_wgrad", dwp, Cout, Cin, dy_act.Cp, x_act.Cp, 0.0, 1, gw, stream_ptr())
     return gw
 
 
+_dwp_cache = {}
 _bn_bwd_nblk = [None]
 
 

@@ -38,8 +38,8 @@ int egaze_f32_to_split(const float* x, long long n, void* hi, void* lo, void* st
 /* nn.Conv2d weight OIHW fp32 -> packed split bf16.  mode 0 (fprop): [9][Cout][cols_p>=Cin];
  * mode 1 (dgrad): taps flipped, [9][Cin][cols_p>=Cout].  (weights of utils.py:70, model_SP.py:10,13-30, late_fusion.py:10-12) */
 int egaze_pack_w3x3(const float* w_oihw, int Cout, int Cin, int cols_p, int mode, void* hi, void* lo, void* stream);
-/* wgrad accumulator [9][Cout][Cin_p] fp32 -> OIHW grad, gw = beta*gw + dw */
-int egaze_unpack_wgrad(const float* dwp, int Cout, int Cin, int Cin_p, float beta, float* gw_oihw, void* stream);
+/* wgrad accumulator [9][Cout_p][Cin_p] fp32 -> OIHW grad, gw = beta*gw + dw; clear != 0 zeroes the accumulator afterwards */
+int egaze_unpack_wgrad(float* dwp, int Cout, int Cin, int Cout_p, int Cin_p, float beta, int clear, float* gw_oihw, void* stream);
 
 /* ---- 3x3 convolution, tcgen05 implicit GEMM (replaces nn.Conv2d(k=3,p=1): utils.py:70, model_SP.py:10,13-30) - */
 /* Tile geometry the kernel will use for an (N,H,W) map; num_tiles sizes the BN-statistics workspace. */

@@ -42,8 +42,12 @@ for name, N, H, W, Ci, Co, kw in LAYERS:
     call("egaze_conv3x3_set_prof", None)
     p = prof[prof[:, 9] > 0].double()
     items = p[:, 9].mean().item()
-    tot = p[:, 6].mean().item()
-    f = lambda c, d: 100.0 * (p[:, c] / p[:, d]).mean().item()
+    pm = p[p[:, 6] > 0]          # CTAs whose MMA warp issued (rank 0 of every pair in CTA-pair mode)
+    tot = pm[:, 6].mean().item()
+
+    def f(c, d):
+        q = p[p[:, d] > 0]
+        return 100.0 * (q[:, c] / q[:, d]).mean().item()
     fl = 2.0 * N * H * W * Co * Ci * 9
     print("%-32s %.3f ms %6.1f TF/s | %5.1f items/CTA %7.0f clk/item | producer waits A-free %4.1f%% B-free %4.1f%% | "
           "MMA waits acc-free %4.1f%% A-landed %4.1f%% B-landed %4.1f%% | epilogue waits acc-ready %4.1f%%"
