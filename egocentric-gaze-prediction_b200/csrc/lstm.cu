@@ -15,11 +15,22 @@ __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.f / (1.f + exp
 //  x    : [B][512] layer input (if apply_tanh, tanh is applied on load: layer 0 input)
 //  h,c  : [B][512] previous state;  h_out,c_out : [B][512]
 //  gates_out (optional, training): [B][4][512] post-activation gates i,f,g,o
+struct CellArgs {
+  const float* x; int apply_tanh;
+  const float* h; const float* c;
+  const float* w_ih; const float* w_hh; const float* b_ih; const float* b_hh;
+  float* h_out; float* c_out; float* gates_out;
+};
+// gridDim.z = 2 runs two independent cells in one launch: layer 0 at step t and layer 1 at step t-1 (the wavefront of the
+// two-layer recurrence), which halves the number of dependent launches of a sequence.
 __global__ void __launch_bounds__(256)
-lstm_cell_kernel(const float* __restrict__ x, int apply_tanh, const float* __restrict__ h, const float* __restrict__ c,
-                 const float* __restrict__ w_ih, const float* __restrict__ w_hh, const float* __restrict__ b_ih,
-                 const float* __restrict__ b_hh, int B, float* __restrict__ h_out, float* __restrict__ c_out,
-                 float* __restrict__ gates_out) {
+lstm_cell_kernel(const CellArgs a0, const CellArgs a1, int B) {
+  const CellArgs& a = blockIdx.z == 0 ? a0 : a1;
+  const float* __restrict__ x = a.x; const int apply_tanh = a.apply_tanh;
+  const float* __restrict__ h = a.h; const float* __restrict__ c = a.c;
+  const float* __restrict__ w_ih = a.w_ih; const float* __restrict__ w_hh = a.w_hh;
+  const float* __restrict__ b_ih = a.b_ih; const float* __restrict__ b_hh = a.b_hh;
+  float* __restrict__ h_out = a.h_out; float* __restrict__ c_out = a.c_out; float* __restrict__ gates_out = a.gates_out;
   __shared__ float xs[BT][HID];
   __shared__ float hs[BT][HID];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -89,15 +100,19 @@ lstm_cell_kernel(const float* __restrict__ x, int apply_tanh, const float* __res
 }
 
 // y[r][j] = act(sum_k x[r][k] * W[j][k] + b[j]),  K = 512;  act: 0 none, 1 relu
+// Input rows come in groups of `grp` consecutive rows, `grp_stride` floats apart (grp_stride == grp*512: dense).
 __global__ void __launch_bounds__(256)
 linear512_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, int rows, int J,
-                 int act, float* __restrict__ y) {
+                 int act, float* __restrict__ y, int grp, long long grp_stride) {
   __shared__ float xs[BT][HID];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int j = blockIdx.x * 8 + warp;
   const int r0 = blockIdx.y * BT;
   const int nr = min(BT, rows - r0);
-  for (int i = threadIdx.x; i < nr * HID; i += blockDim.x) xs[i / HID][i % HID] = x[(size_t)(r0 + i / HID) * HID + i % HID];
+  for (int i = threadIdx.x; i < nr * HID; i += blockDim.x) {
+    const int r = r0 + i / HID;
+    xs[i / HID][i % HID] = x[(size_t)(r / grp) * grp_stride + (size_t)(r % grp) * HID + i % HID];
+  }
   __syncthreads();
   if (j >= J) return;
   float acc[BT];
@@ -225,26 +240,32 @@ extern "C" int egaze_lstm_seq_fwd(const float* x, const float* h0, const float* 
   EGAZE_CHECK_ARG(T > 0 && B > 0, "lstm_seq_fwd: bad T=%d B=%d", T, B);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t sl = (size_t)B * HID;
-  dim3 grid(HID / 8, ceil_div(B, BT));
-  for (int t = 0; t < T; ++t) {
-    for (int l = 0; l < 2; ++l) {
-      const float* xin = l == 0 ? x + (size_t)t * sl : ws_h + ((size_t)t * 2 + 0) * sl;
-      const float* hp = t == 0 ? h0 + l * sl : ws_h + ((size_t)(t - 1) * 2 + l) * sl;
-      const float* cp = t == 0 ? c0 + l * sl : ws_c + ((size_t)(t - 1) * 2 + l) * sl;
-      float* ho = ws_h + ((size_t)t * 2 + l) * sl;
-      float* co = ws_c + ((size_t)t * 2 + l) * sl;
-      float* go = ws_gates ? ws_gates + ((size_t)t * 2 + l) * sl * 4 : nullptr;
-      lstm_cell_kernel<<<grid, 256, 0, st>>>(xin, l == 0, hp, cp, w_ih[l], w_hh[l], b_ih[l], b_hh[l], B, ho, co, go);
-      EGAZE_LAUNCH_CHECK();
-    }
-  }
-  // top-layer hidden states of all steps -> Linear + ReLU.  Gather rows (t, layer 1) with a strided view:
-  // rows are [T][B], row stride 2*sl between steps -> run per step to keep the kernel simple.
-  dim3 lgrid(HID / 8, ceil_div(B, BT));
-  for (int t = 0; t < T; ++t) {
-    linear512_kernel<<<lgrid, 256, 0, st>>>(ws_h + ((size_t)t * 2 + 1) * sl, lin_w, lin_b, B, HID, 1, out + (size_t)t * sl);
+  // Wavefront over the two layers: launch t runs layer 0 at step t and layer 1 at step t-1 (both only depend on launch t-1),
+  // so a sequence is T+1 dependent launches instead of 2T.
+  auto cell = [&](int l, int t) {
+    CellArgs a;
+    a.x = l == 0 ? x + (size_t)t * sl : ws_h + ((size_t)t * 2 + 0) * sl;
+    a.apply_tanh = l == 0;
+    a.h = t == 0 ? h0 + l * sl : ws_h + ((size_t)(t - 1) * 2 + l) * sl;
+    a.c = t == 0 ? c0 + l * sl : ws_c + ((size_t)(t - 1) * 2 + l) * sl;
+    a.w_ih = w_ih[l]; a.w_hh = w_hh[l]; a.b_ih = b_ih[l]; a.b_hh = b_hh[l];
+    a.h_out = ws_h + ((size_t)t * 2 + l) * sl;
+    a.c_out = ws_c + ((size_t)t * 2 + l) * sl;
+    a.gates_out = ws_gates ? ws_gates + ((size_t)t * 2 + l) * sl * 4 : nullptr;
+    return a;
+  };
+  for (int t = 0; t <= T; ++t) {
+    const bool has0 = t < T, has1 = t >= 1;
+    const CellArgs a0 = has0 ? cell(0, t) : cell(1, t - 1);
+    const CellArgs a1 = has1 ? cell(1, t - 1) : a0;
+    dim3 grid(HID / 8, ceil_div(B, BT), (has0 && has1) ? 2 : 1);
+    lstm_cell_kernel<<<grid, 256, 0, st>>>(a0, a1, B);
     EGAZE_LAUNCH_CHECK();
   }
+  // top-layer hidden states of all steps -> Linear + ReLU in ONE launch: rows (t, b) live B at a time, 2*sl floats apart
+  dim3 lgrid(HID / 8, ceil_div(T * B, BT));
+  linear512_kernel<<<lgrid, 256, 0, st>>>(ws_h + sl, lin_w, lin_b, T * B, HID, 1, out, B, (long long)(2 * sl));
+  EGAZE_LAUNCH_CHECK();
   EGAZE_CUDA(cudaMemcpyAsync(hn, ws_h + ((size_t)(T - 1) * 2) * sl, 2 * sl * sizeof(float), cudaMemcpyDeviceToDevice, st));
   EGAZE_CUDA(cudaMemcpyAsync(cn, ws_c + ((size_t)(T - 1) * 2) * sl, 2 * sl * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return EGAZE_OK;

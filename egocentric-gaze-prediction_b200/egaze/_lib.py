@@ -98,7 +98,7 @@ def call(name, *args):
     fn = getattr(lib(), name)
     rc = fn(*[_arg(a) for a in args])
     if name == "egaze_lstm_seq_fwd":
-        _launch_count += 3 * int(args[9])  # 2 cell kernels + 1 linear per time step
+        _launch_count += int(args[9]) + 2  # T+1 wavefront launches (layer 0 at t | layer 1 at t-1) + one Linear over all steps
     elif name == "egaze_lstm_seq_bwd":
         _launch_count += 6 * int(args[6]) + 16  # per step: 2 x (gate grad + 2 small GEMMs); + Linear / weight-grad passes
     else:
