@@ -33,6 +33,7 @@ namespace {
 constexpr int kThreads = 320;      // TMA warp + MMA warp + 8 epilogue warps
 constexpr int kEpiThreads = 256;
 constexpr int kMaxSA = 4, kMaxSB = 8;
+constexpr int kEpiScratch = 32 + 8 * 3 * 64;   // floats of epilogue scratch behind the staging tile
 
 struct ConvTcParams {
   int N, H, W;         // conv output == input spatial size
@@ -139,37 +140,8 @@ template <int RED, bool MASK, bool UPS, bool F32, bool SPLIT, bool STATS = false
 __device__ __forceinline__ void epi_store(const ConvTcParams& p, const EpiTile& e, float4& cs, float4 k4 = float4(),
                                           float4* s1 = nullptr, float4* s2 = nullptr) {
   const int obw_mask = (1 << e.obw_log) - 1;
-#pragma unroll 2
-  for (int pix = e.pl; pix < e.npix; pix += e.PS) {
-    const int ph = pix >> e.obw_log, pw = pix & obw_mask;
-    if (ph >= e.vh || pw >= e.vw) continue;
-    float4 v;
-    if (RED == 0) {
-      const float4 a = ptx::lds128(e.st_addr + (uint32_t)(pix * e.ldst_b));
-      if (STATS) {
-        const float dx = a.x - k4.x, dy = a.y - k4.y, dz = a.z - k4.z, dw = a.w - k4.w;
-        s1->x += dx; s1->y += dy; s1->z += dz; s1->w += dw;
-        s2->x = fmaf(dx, dx, s2->x); s2->y = fmaf(dy, dy, s2->y); s2->z = fmaf(dz, dz, s2->z); s2->w = fmaf(dw, dw, s2->w);
-      }
-      v = epi_affine(a, e.s4, e.t4, e.lo_clamp);
-    } else {
-      const uint32_t rb = e.st_addr + (uint32_t)(((2 * ph) * e.BW + 2 * pw) * e.ldst_b);
-      const float4 a = epi_affine(ptx::lds128(rb), e.s4, e.t4, e.lo_clamp);
-      const float4 b = epi_affine(ptx::lds128(rb + (uint32_t)e.ldst_b), e.s4, e.t4, e.lo_clamp);
-      const float4 c = epi_affine(ptx::lds128(rb + (uint32_t)(e.BW * e.ldst_b)), e.s4, e.t4, e.lo_clamp);
-      const float4 d = epi_affine(ptx::lds128(rb + (uint32_t)((e.BW + 1) * e.ldst_b)), e.s4, e.t4, e.lo_clamp);
-      if (RED == 1) {
-        v.x = fmaxf(fmaxf(a.x, b.x), fmaxf(c.x, d.x));
-        v.y = fmaxf(fmaxf(a.y, b.y), fmaxf(c.y, d.y));
-        v.z = fmaxf(fmaxf(a.z, b.z), fmaxf(c.z, d.z));
-        v.w = fmaxf(fmaxf(a.w, b.w), fmaxf(c.w, d.w));
-      } else {
-        v.x = (a.x + b.x) + (c.x + d.x);
-        v.y = (a.y + b.y) + (c.y + d.y);
-        v.z = (a.z + b.z) + (c.z + d.z);
-        v.w = (a.w + b.w) + (c.w + d.w);
-      }
-    }
+  // everything after the staged value(s) of output pixel `pix` are in registers
+  auto finish = [&](int pix, int ph, int pw, float4 v) {
     if (MASK) {
       const uint2 mk = __ldg(reinterpret_cast<const uint2*>(p.mask + e.mask_base + (size_t)(ph * e.mask_row + pw * e.mask_px)));
       if (!(bf16_bits_to_float(mk.x & 0xffffu) > 0.f)) v.x = 0.f;
@@ -192,6 +164,54 @@ __device__ __forceinline__ void epi_store(const ConvTcParams& p, const EpiTile& 
           *reinterpret_cast<uint2*>(p.out_lo + o) = lo2;
         }
       }
+  };
+  if (RED == 0) {
+    // four pixels per trip: the four staged float4 are loaded up front so their latency overlaps
+    constexpr int U = 4;
+    for (int pix0 = e.pl; pix0 < e.npix; pix0 += U * e.PS) {
+      float4 a[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int pix = pix0 + u * e.PS;
+        a[u] = pix < e.npix ? ptx::lds128(e.st_addr + (uint32_t)(pix * e.ldst_b)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int pix = pix0 + u * e.PS;
+        const int ph = pix >> e.obw_log, pw = pix & obw_mask;
+        if (pix >= e.npix || ph >= e.vh || pw >= e.vw) continue;
+        if (STATS) {
+          const float dx = a[u].x - k4.x, dy = a[u].y - k4.y, dz = a[u].z - k4.z, dw = a[u].w - k4.w;
+          s1->x += dx; s1->y += dy; s1->z += dz; s1->w += dw;
+          s2->x = fmaf(dx, dx, s2->x); s2->y = fmaf(dy, dy, s2->y); s2->z = fmaf(dz, dz, s2->z); s2->w = fmaf(dw, dw, s2->w);
+        }
+        finish(pix, ph, pw, epi_affine(a[u], e.s4, e.t4, e.lo_clamp));
+      }
+    }
+  } else {
+#pragma unroll 2
+    for (int pix = e.pl; pix < e.npix; pix += e.PS) {
+      const int ph = pix >> e.obw_log, pw = pix & obw_mask;
+      if (ph >= e.vh || pw >= e.vw) continue;
+      const uint32_t rb = e.st_addr + (uint32_t)(((2 * ph) * e.BW + 2 * pw) * e.ldst_b);
+      const float4 a = epi_affine(ptx::lds128(rb), e.s4, e.t4, e.lo_clamp);
+      const float4 b = epi_affine(ptx::lds128(rb + (uint32_t)e.ldst_b), e.s4, e.t4, e.lo_clamp);
+      const float4 c = epi_affine(ptx::lds128(rb + (uint32_t)(e.BW * e.ldst_b)), e.s4, e.t4, e.lo_clamp);
+      const float4 d = epi_affine(ptx::lds128(rb + (uint32_t)((e.BW + 1) * e.ldst_b)), e.s4, e.t4, e.lo_clamp);
+      float4 v;
+      if (RED == 1) {
+        v.x = fmaxf(fmaxf(a.x, b.x), fmaxf(c.x, d.x));
+        v.y = fmaxf(fmaxf(a.y, b.y), fmaxf(c.y, d.y));
+        v.z = fmaxf(fmaxf(a.z, b.z), fmaxf(c.z, d.z));
+        v.w = fmaxf(fmaxf(a.w, b.w), fmaxf(c.w, d.w));
+      } else {
+        v.x = (a.x + b.x) + (c.x + d.x);
+        v.y = (a.y + b.y) + (c.y + d.y);
+        v.z = (a.z + b.z) + (c.z + d.z);
+        v.w = (a.w + b.w) + (c.w + d.w);
+      }
+      finish(pix, ph, pw, v);
+    }
   }
 }
 
@@ -543,11 +563,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     const int CW = p.BN < 64 ? p.BN : 64;    // staged column chunk (power of two)
     const int ldst = CW + 4;                 // padded staging row (floats)
     const uint32_t stage_s = ptx::smem_u32(stage);
-    float* red = stage + (size_t)128 * ldst; // scratch: [tiles_n] pixel counts behind the BatchNorm sums
+    float* red = stage + (size_t)128 * ldst; // scratch: [32] pixel counts behind the BatchNorm sums, then
+    float* part = red + 32;                  //          [8 warps][3][64]: per-warp partial (s1, s2, column sum) of a chunk
     // BatchNorm statistics of this CTA, per output channel: reference value k (the first accumulator the CTA saw for the
     // channel), s1 = sum(a - k), s2 = sum((a - k)^2) over every pixel it stored.  Shifting by k keeps both sums small, so
     // mean = k + s1/n and M2 = s2 - s1^2/n lose nothing to cancellation.
-    float* run_stats = red + 4 * 64 * 3;     // [3][Cout]: k, s1, s2
+    float* run_stats = red + kEpiScratch;    // [3][Cout]: k, s1, s2
     float* st_k = run_stats;
     float* st_s1 = run_stats + p.Cout;
     float* st_s2 = run_stats + 2 * p.Cout;
@@ -594,6 +615,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     int as = 0;
     uint32_t full_par[2] = {0, 0};
     long long prof_c[2] = {0, 0};
+    long long prof_e[5] = {0, 0, 0, 0, 0};   // phase 1 | barrier | store loop | reductions | barrier
     const long long prof_start = p.prof ? clock64() : 0;
     for (int w = cluster_id; w < p.num_items; w += num_clusters) {
       const Item it = decode_item(p, w, CS, rank);
@@ -605,6 +627,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
 
       for (int cc = 0; cc < p.BN; cc += CW) {
         const int n0 = it.nt * p.BN + cc;   // first output channel of this chunk
+        const long long tp0 = p.prof ? clock64() : 0;
         // -- phase 1: TMEM -> registers -> smem staging [128][CW+4] (raw fp32 accumulators)
         for (int c0 = colsel * 32; c0 < CW; c0 += 64) {
           uint32_t v[32];
@@ -647,7 +670,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
             else ptx::mbar_arrive(&acc_empty[as]);
           }
         }
+        const long long tp1 = p.prof ? clock64() : 0;
         ptx::named_bar_sync(1, kEpiThreads);
+        const long long tp2 = p.prof ? clock64() : 0;
 
         float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
         float4 k4 = cs, s1v = cs, s2v = cs;
@@ -777,40 +802,57 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
             while (pw >= oBW) { pw -= oBW; ++ph; }
           }
         }
-        if (p.stats && it.valid) {
+        const long long tp3 = p.prof ? clock64() : 0;
+        // Fold the per-thread sums: lanes of a warp that share a channel group are gpp lanes apart (shuffles), then every
+        // warp parks its partials in its own scratch row; after the chunk's closing barrier one thread per channel adds
+        // the eight rows into the CTA's running sums.  (Shared-memory float atomics are CAS loops: 2k cycles per chunk.)
+        const bool fold = (p.stats || p.colsum) && it.valid;
+        if (fold) {
           for (int o = 16; o >= gpp; o >>= 1) {
-            s1v.x += __shfl_xor_sync(0xffffffffu, s1v.x, o); s1v.y += __shfl_xor_sync(0xffffffffu, s1v.y, o);
-            s1v.z += __shfl_xor_sync(0xffffffffu, s1v.z, o); s1v.w += __shfl_xor_sync(0xffffffffu, s1v.w, o);
-            s2v.x += __shfl_xor_sync(0xffffffffu, s2v.x, o); s2v.y += __shfl_xor_sync(0xffffffffu, s2v.y, o);
-            s2v.z += __shfl_xor_sync(0xffffffffu, s2v.z, o); s2v.w += __shfl_xor_sync(0xffffffffu, s2v.w, o);
+            if (p.stats) {
+              s1v.x += __shfl_xor_sync(0xffffffffu, s1v.x, o); s1v.y += __shfl_xor_sync(0xffffffffu, s1v.y, o);
+              s1v.z += __shfl_xor_sync(0xffffffffu, s1v.z, o); s1v.w += __shfl_xor_sync(0xffffffffu, s1v.w, o);
+              s2v.x += __shfl_xor_sync(0xffffffffu, s2v.x, o); s2v.y += __shfl_xor_sync(0xffffffffu, s2v.y, o);
+              s2v.z += __shfl_xor_sync(0xffffffffu, s2v.z, o); s2v.w += __shfl_xor_sync(0xffffffffu, s2v.w, o);
+            }
+            if (p.colsum) {
+              cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
+              cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
+            }
           }
           if (lane < gpp) {
-            float* d1 = st_s1 + n0 + g * 4;
-            float* d2 = st_s2 + n0 + g * 4;
-            atomicAdd(d1 + 0, s1v.x); atomicAdd(d1 + 1, s1v.y); atomicAdd(d1 + 2, s1v.z); atomicAdd(d1 + 3, s1v.w);
-            atomicAdd(d2 + 0, s2v.x); atomicAdd(d2 + 1, s2v.y); atomicAdd(d2 + 2, s2v.z); atomicAdd(d2 + 3, s2v.w);
+            float* row = part + (size_t)ew * 3 * 64 + g * 4;
+            if (p.stats) {
+              *reinterpret_cast<float4*>(row) = s1v;
+              *reinterpret_cast<float4*>(row + 64) = s2v;
+            }
+            if (p.colsum) *reinterpret_cast<float4*>(row + 128) = cs;
           }
         }
-        if (p.colsum && it.valid) {
-          // threads of a warp that share a channel group are gpp lanes apart: fold them, then one smem atomic per channel
-          for (int o = 16; o >= gpp; o >>= 1) {
-            cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o);
-            cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
-            cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o);
-            cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
-          }
-          if (lane < gpp) {
-            float* dst = colsum_s + n0 + g * 4;
-            atomicAdd(dst + 0, cs.x); atomicAdd(dst + 1, cs.y); atomicAdd(dst + 2, cs.z); atomicAdd(dst + 3, cs.w);
-          }
-        }
+        const long long tp4 = p.prof ? clock64() : 0;
         ptx::named_bar_sync(1, kEpiThreads);   // staging is free for the next chunk / item
+        if (fold && et < 3 * 64) {
+          // et -> (which sum, channel); the next write to `part` is two barriers away
+          const int which = et >> 6, c = et & 63;
+          if (c < CW && (which < 2 ? p.stats != nullptr : p.colsum != nullptr)) {
+            float v = 0.f;
+#pragma unroll
+            for (int wv = 0; wv < 8; ++wv) v += part[(size_t)wv * 3 * 64 + which * 64 + c];
+            float* dst = which == 0 ? st_s1 : (which == 1 ? st_s2 : colsum_s);
+            dst[n0 + c] += v;
+          }
+        }
+        if (p.prof) {
+          const long long tp5 = clock64();
+          prof_e[0] += tp1 - tp0; prof_e[1] += tp2 - tp1; prof_e[2] += tp3 - tp2; prof_e[3] += tp4 - tp3; prof_e[4] += tp5 - tp4;
+        }
       }
       as ^= 1;
     }
     if (p.prof && et == 0) {
       long long* o = p.prof + (size_t)blockIdx.x * 16;
       o[7] = prof_c[0]; o[8] = clock64() - prof_start; o[9] = (p.num_items - cluster_id + num_clusters - 1) / num_clusters;
+      for (int i = 0; i < 5; ++i) o[10 + i] = prof_e[i];
     }
     if (p.colsum) {
       for (int c = et; c < p.Cout; c += kEpiThreads) atomicAdd(p.colsum + c, colsum_s[c]);
@@ -954,7 +996,7 @@ extern "C" int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* 
     const double eff_c = (double)H * W / ((double)ceil_div(H, p.BH) * ceil_div(W, p.BW) * 128.0);
     // ring depth the weight boxes would get next to two 180-row windows (see the smem budget below)
     const int bn = conv_pick_bn(Cout, precise), ns = precise ? 2 : 1;
-    const int stage_b = ((128 * ((bn < 64 ? bn : 64) + 4) * 4 + 4 * 64 * 3 * 4 + (stats ? Cout * 3 * 4 : 0) + (colsum ? Cout * 4 : 0) + 1023) / 1024) * 1024;
+    const int stage_b = ((128 * ((bn < 64 ? bn : 64) + 4) * 4 + kEpiScratch * 4 + (stats ? Cout * 3 * 4 : 0) + (colsum ? Cout * 4 : 0) + 1023) / 1024) * 1024;
     const int sb_w = (222 * 1024 - stage_b - 2 * ns * 23552) / (ns * bn * 128);
     if (eff_w >= eff_c * 0.999 && sb_w >= win_minsb) {
       p.win = 1;
@@ -992,7 +1034,7 @@ extern "C" int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* 
   const int b_plane_rows = p.pair ? p.BN / 2 : p.BN;   // weight rows of one plane kept in THIS CTA's slot
   p.b_slot_bytes = ((b_plane_rows * row_bytes + 1023) / 1024) * 1024;
   const int CW = p.BN < 64 ? p.BN : 64;
-  const int stage_bytes = ((128 * (CW + 4) * 4 + 4 * 64 * 3 * 4 + (stats ? Cout * 3 * 4 : 0) + (colsum ? Cout * 4 : 0) + 1023) / 1024) * 1024;
+  const int stage_bytes = ((128 * (CW + 4) * 4 + kEpiScratch * 4 + (stats ? Cout * 3 * 4 : 0) + (colsum ? Cout * 4 : 0) + 1023) / 1024) * 1024;
   static int sa_env = -1;
   if (sa_env < 0) {
     const char* e = getenv("EGAZE_CONV_SA");

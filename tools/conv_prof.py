@@ -52,3 +52,6 @@ for name, N, H, W, Ci, Co, kw in LAYERS:
     print("%-32s %.3f ms %6.1f TF/s | %5.1f items/CTA %7.0f clk/item | producer waits A-free %4.1f%% B-free %4.1f%% | "
           "MMA waits acc-free %4.1f%% A-landed %4.1f%% B-landed %4.1f%% | epilogue waits acc-ready %4.1f%%"
           % (name, ms, fl / ms / 1e9, items, tot / items, f(0, 2), f(1, 2), f(3, 6), f(4, 6), f(5, 6), f(7, 8)))
+    ep = [(p[:, 10 + i] / p[:, 9]).mean().item() for i in range(5)]
+    print("    epilogue (thread 0) cycles per item: TMEM->smem %.0f | barrier %.0f | store loop %.0f | reductions %.0f | barrier %.0f"
+          % tuple(ep))
