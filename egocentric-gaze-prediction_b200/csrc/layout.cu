@@ -106,6 +106,31 @@ __global__ void pack_w3x3_kernel(const float* __restrict__ w, int Co, int Ci, in
   }
 }
 
+// The same for MANY weights in one launch (after an optimiser step every packed copy is stale): blockIdx.y = job.
+struct PackJob {
+  const float* w;
+  __nv_bfloat16* hi;
+  __nv_bfloat16* lo;
+  int Co, Ci, rows, cols_p, mode, pad;
+};
+__global__ void pack_w3x3_multi_kernel(const PackJob* __restrict__ jobs) {
+  const PackJob j = jobs[blockIdx.y];
+  const uint32_t total = (uint32_t)9 * j.rows * j.cols_p;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const uint32_t col = i % j.cols_p, t = i / j.cols_p, row = t % j.rows, tap = t / j.rows;
+    float v = 0.f;
+    if (j.mode == 0) {
+      if (col < (uint32_t)j.Ci) v = j.w[((size_t)row * j.Ci + col) * 9 + tap];
+    } else {
+      if (col < (uint32_t)j.Co) v = j.w[((size_t)col * j.Ci + row) * 9 + (8 - tap)];
+    }
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    j.hi[i] = h;
+    if (j.lo) j.lo[i] = l;
+  }
+}
+
 // dwp: [9][Co_p][Ci_p] fp32 (wgrad accumulator)  ->  gw: OIHW [Co][Ci][3][3]  (gw = beta*gw + dwp).
 // clear != 0: the accumulator is zeroed on the way out, so a persistent buffer is ready for the next accumulation.
 __global__ void unpack_wgrad_kernel(float* __restrict__ dwp, int Co, int Ci, int Co_p, int Ci_p, float beta, int clear,
@@ -175,6 +200,16 @@ extern "C" int egaze_pack_w3x3(const float* w_oihw, int Cout, int Cin, int cols_
   if (blocks > 148 * 16) blocks = 148 * 16;
   pack_w3x3_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w_oihw, Cout, Cin, rows, cols_p, mode, (__nv_bfloat16*)hi,
                                                              (__nv_bfloat16*)lo);
+  EGAZE_LAUNCH_CHECK();
+  return EGAZE_OK;
+}
+
+// jobs: device array of njobs records {const float* w; void* hi; void* lo; int Cout, Cin, rows, cols_p, mode, pad;}
+// (48 bytes each, the fields of egaze_pack_w3x3).
+extern "C" int egaze_pack_w3x3_multi(const void* jobs, int njobs, void* stream) {
+  EGAZE_CHECK_ARG(jobs && njobs > 0, "pack_w3x3_multi: bad args");
+  dim3 grid(64, (unsigned)njobs);
+  pack_w3x3_multi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const PackJob*)jobs);
   EGAZE_LAUNCH_CHECK();
   return EGAZE_OK;
 }

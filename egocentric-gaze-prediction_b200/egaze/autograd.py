@@ -135,6 +135,7 @@ def _ret_grads(bag, params):
 class _ModelSPFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, x_s, x_t, *params):
+        ops.pack_cache.refresh()   # one launch re-packs every weight copy the optimiser step made stale
         saved_s, saved_t, saved_tail = [], [], []
         specs_s, _ = engine.parse_sequential(model.features_s)
         specs_t, _ = engine.parse_sequential(model.features_t)
@@ -210,6 +211,7 @@ def model_sp_with_grad(model, x_s, x_t):
 class _SequentialFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, seq, x, *params):
+        ops.pack_cache.refresh()   # one launch re-packs every weight copy the optimiser step made stale
         specs, tail = engine.parse_sequential(seq)
         if tail is not None or any(sp.bn is None for sp in specs):
             raise NotImplementedError("egaze: stand-alone training is implemented for conv+BN+ReLU trunks")
@@ -243,6 +245,7 @@ def sequential_with_grad(seq, x):
 class _VGGFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, x, *params):
+        ops.pack_cache.refresh()   # one launch re-packs every weight copy the optimiser step made stale
         specs, _ = engine.parse_sequential(model.features)
         saved_f, saved_d = [], []
         act = ops.to_split(x, _first_cp(specs[0].conv))
@@ -286,6 +289,7 @@ def vgg_with_grad(model, x):
 class _LateFusionFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, f, g, *params):
+        ops.pack_cache.refresh()   # one launch re-packs every weight copy the optimiser step made stale
         x = torch.cat((f, g), dim=1)
         specs, head = engine.parse_sequential(model.fusion)
         saved = []

@@ -120,20 +120,24 @@ def f32_to_split(x_nhwc, C=None):
 class _PackCache(object):
     def __init__(self):
         self._d = {}
+        self._tables = {}
+
+    @staticmethod
+    def _dims(w, mode, rows_p, cols_p):
+        Co, Ci = int(w.shape[0]), int(w.shape[1])
+        rows = Co if mode == 0 else Ci
+        cols = Ci if mode == 0 else Co
+        return Co, Ci, rows, (rows if rows_p is None else rows_p), (pad_channels(cols) if cols_p is None else cols_p)
 
     def get(self, w, mode, rows_p=None, cols_p=None):
         """w: nn.Conv2d weight [Co, Ci, 3, 3] (or Conv3d [Co, Ci, 1, 3, 3]).  Returns (hi, lo, rows, cols_p)."""
-        key = (id(w), mode, rows_p, cols_p)
+        Co, Ci, rows, rp, cp = self._dims(w, mode, rows_p, cols_p)
+        key = (id(w), mode, rp, cp)
         ent = self._d.get(key)
         ver = w._version
         if ent is not None and ent[0]() is w and ent[1] == ver and ent[2] == w.data_ptr():
             return ent[3]
-        Co, Ci = int(w.shape[0]), int(w.shape[1])
         w4 = w.detach().reshape(Co, Ci, 3, 3).contiguous().float()
-        rows = Co if mode == 0 else Ci
-        cols = Ci if mode == 0 else Co
-        cp = pad_channels(cols) if cols_p is None else cols_p
-        rp = rows if rows_p is None else rows_p
         if rp == rows:
             # the pack kernel writes every element (padding columns included): reuse the previous buffers when possible
             if ent is not None and ent[3][0].shape == (9, rp, cp) and ent[3][0].device == w.device:
@@ -154,6 +158,35 @@ class _PackCache(object):
         val = (hi, lo, rp, cp)
         self._d[key] = (weakref.ref(w), ver, w.data_ptr(), val)
         return val
+
+    def refresh(self):
+        """Re-pack, in ONE launch, every cached copy whose weight changed since it was packed (after an optimiser step that is
+        all of them: 76 small launches per SP training step otherwise).  Copies of dead or re-allocated weights are dropped."""
+        stale = []
+        for key, ent in list(self._d.items()):
+            w = ent[0]()
+            if w is None or ent[2] != w.data_ptr():
+                del self._d[key]
+                continue
+            _, mode, rp, cp = key
+            Co, Ci, rows, _, _ = self._dims(w, mode, rp, cp)
+            if ent[1] != w._version and rp == rows and w.is_contiguous() and w.dtype == F32:
+                stale.append((key, ent, w, Co, Ci, rows))
+        if len(stale) < 2:
+            return
+        tkey = tuple((k, e[2], e[3][0].data_ptr()) for k, e, _, _, _, _ in stale)
+        table = self._tables.get(tkey)
+        if table is None:
+            import numpy as np
+            rec = np.zeros((len(stale), 6), dtype=np.int64)
+            for i, (key, ent, w, Co, Ci, rows) in enumerate(stale):
+                hi, lo, rp, cp = ent[3]
+                rec[i] = (w.data_ptr(), hi.data_ptr(), lo.data_ptr(), Co | (Ci << 32), rows | (cp << 32), key[1])
+            self._tables.clear()
+            table = self._tables[tkey] = torch.from_numpy(rec).to(stale[0][2].device)
+        call("egaze_pack_w3x3_multi", table, len(stale), stream_ptr())
+        for key, ent, w, _, _, _ in stale:
+            self._d[key] = (ent[0], w._version, ent[2], ent[3])
 
 
 pack_cache = _PackCache()
@@ -453,6 +486,36 @@ def bilinear_up(x, scale=16, align_corners=False):
     out = torch.empty((xb.shape[0], h * scale, w * scale), dtype=F32, device=x.device)
     call("egaze_bilinear_up", xb, xb.shape[0], h, w, int(scale), int(align_corners), out, stream_ptr())
     return out.reshape(tuple(shp[:-2]) + (h * scale, w * scale))
+
+
+# ---- validation metric ---------------------------------------------------------------------------------------------
+def aae_auc(output, target):
+    """utils.computeAAEAUC on the device: output / target [B,(1,)224,224] CUDA tensors -> [B,4] fp64 tensor of
+    (AAE in degrees, AUC, gaze row, gaze column) per sample.  Only this small tensor needs to travel to the host."""
+    _lib.check_device(output.device)
+    o = output.detach().contiguous().float().reshape(-1, output.shape[-2], output.shape[-1])
+    t = target.detach().contiguous().float().reshape(-1, target.shape[-2], target.shape[-1])
+    if o.shape != t.shape:
+        raise RuntimeError("egaze: aae_auc shape mismatch %s vs %s" % (tuple(o.shape), tuple(t.shape)))
+    res = torch.empty((o.shape[0], 4), dtype=torch.float64, device=o.device)
+    call("egaze_aae_auc", o, t, o.shape[0], o.shape[1], o.shape[2], _gauss14(o.device), res, stream_ptr())
+    return res
+
+
+_gauss14_cache = {}
+
+
+def _gauss14(device):
+    """scipy.ndimage._filters._gaussian_kernel1d(sigma=14, order=0, radius=int(4*14+0.5)), restated with NumPy so that the
+    device multiplies bit-identical weights (utils.py:117 calls gaussian_filter(z, 14))."""
+    w = _gauss14_cache.get(device)
+    if w is None:
+        import numpy as np
+        sigma, radius = 14.0, 56
+        x = np.arange(-radius, radius + 1)
+        phi = np.exp(-0.5 / (sigma * sigma) * x ** 2)
+        w = _gauss14_cache[device] = torch.from_numpy(phi / phi.sum()).to(device)
+    return w
 
 
 # ---- LSTM ----------------------------------------------------------------------------------------------------------

@@ -114,7 +114,21 @@ def _aae_auc_single(out_sq, tar_sq):
 
 
 def computeAAEAUC(output, target):
-    """Host-side validation metric (reference utils.py:96-140; CPU/scipy, out of the hot path -- SURVEY 8f #1)."""
+    """Validation metric (reference utils.py:96-140).  NumPy arrays -- what the reference's loops pass after `.cpu()` -- take
+    the scipy path like the reference; CUDA tensors are scored on the device (egaze_aae_auc) and only four numbers per
+    sample come back, so a validation loop no longer has to ship both maps to the host (SURVEY 8f #1)."""
+    try:
+        import torch
+        if isinstance(output, torch.Tensor) and output.is_cuda:
+            from egaze import ops
+            res = ops.aae_auc(output, target if isinstance(target, torch.Tensor) else torch.as_tensor(target, device=output.device))
+            r = res.cpu().numpy()
+            gp = [[int(a), int(b)] for a, b in r[:, 2:4]]
+            if r.shape[0] == 1 and output.dim() == 2:
+                return float(r[0, 0]), float(r[0, 1]), gp
+            return float(np.mean(r[:, 0])), float(np.mean(r[:, 1])), gp
+    except ImportError:
+        pass
     if output.ndim == 3:
         res = [_aae_auc_single(output[b].squeeze(), target[b].squeeze()) for b in range(output.shape[0])]
         return np.mean([r[0] for r in res]), np.mean([r[1] for r in res]), [r[2] for r in res]

@@ -38,6 +38,9 @@ int egaze_f32_to_split(const float* x, long long n, void* hi, void* lo, void* st
 /* nn.Conv2d weight OIHW fp32 -> packed split bf16.  mode 0 (fprop): [9][Cout][cols_p>=Cin];
  * mode 1 (dgrad): taps flipped, [9][Cin][cols_p>=Cout].  (weights of utils.py:70, model_SP.py:10,13-30, late_fusion.py:10-12) */
 int egaze_pack_w3x3(const float* w_oihw, int Cout, int Cin, int cols_p, int mode, void* hi, void* lo, void* stream);
+/* egaze_pack_w3x3 for many weights in ONE launch.  jobs: device array of njobs 48-byte records
+ * {const float* w; void* hi; void* lo; int Cout, Cin, rows, cols_p, mode, pad;} (rows = Cout for mode 0, Cin for mode 1). */
+int egaze_pack_w3x3_multi(const void* jobs, int njobs, void* stream);
 /* wgrad accumulator [9][Cout_p][Cin_p] fp32 -> OIHW grad, gw = beta*gw + dw; clear != 0 zeroes the accumulator afterwards */
 int egaze_unpack_wgrad(float* dwp, int Cout, int Cin, int Cout_p, int Cin_p, float beta, int clear, float* gw_oihw, void* stream);
 
@@ -132,6 +135,11 @@ int egaze_lstm_seq_bwd(const float* x, const float* h0, const float* c0, const f
                        float* xt, float* dz, float* dgates, float* dh_top, float* tmp_x, float* dh_next, float* dc_next,
                        float* dx0, float* const* dw_ih, float* const* dw_hh, float* const* db, float* dlin_w,
                        float* dlin_b, float* dinput, float* dh0, float* dc0, void* stream);
+
+/* ---- validation metric on the device (replaces utils.computeAAEAUC, utils.py:96-140: scipy centre of mass + Gaussian
+ * filter + AUC count per sample on the host).  out / tgt: [B][224][224] fp32; weights: [113] fp64 = scipy's sigma-14 Gaussian
+ * kernel built on the host; res: [B][4] fp64 = (AAE deg, AUC, gaze row, col) */
+int egaze_aae_auc(const float* out, const float* tgt, int B, int H, int W, const double* weights, double* res, void* stream);
 
 #ifdef __cplusplus
 }

@@ -261,6 +261,42 @@ def get_weighted(chn_weight, feature):
     return np.stack(out).astype(np.float32)
 
 
+def aae_auc(output, target):
+    """utils.computeAAEAUC (utils.py:96-140) for one 224x224 prediction / target pair -> (AAE degrees, AUC, [i, j]).
+    scipy does the centre of mass and the sigma-14 Gaussian filter exactly as the reference does."""
+    from scipy import ndimage
+    predicted = ndimage.center_of_mass(output)
+    i, j = np.unravel_index(target.argmax(), target.shape)
+    d = 112 / math.tan(math.pi / 6)
+    r1 = np.array([predicted[0] - 112, predicted[1] - 112, d])
+    r2 = np.array([i - 112, j - 112, d])
+    angle = math.degrees(math.atan2(np.linalg.norm(np.cross(r1, r2)), np.dot(r1, r2)))
+    z = np.zeros((224, 224))
+    z[int(predicted[0])][int(predicted[1])] = 1
+    z = ndimage.gaussian_filter(z, 14)
+    z = z - np.min(z)
+    z = z / np.max(z)
+    auc = 1 - float((z > z[i][j]).sum()) / (output.shape[0] * output.shape[1])
+    return angle, auc, [int(i), int(j)]
+
+
+def synth_metric_inputs(B, seed=21):
+    """Seeded (prediction, target) pairs for the metric tests: smooth blobs whose centres sweep the image, including the
+    borders (the Gaussian filter reflects there), plus quantised targets with arg-max plateaus."""
+    rng = np.random.RandomState(seed)
+    ys, xs = np.mgrid[0:224, 0:224].astype(np.float64)
+    outs, tgts = [], []
+    for b in range(B):
+        cy, cx = rng.uniform(0, 223, 2) if b % 3 else rng.choice([2.0, 221.0, 30.0, 200.0], 2)
+        o = np.exp(-((ys - cy) ** 2 + (xs - cx) ** 2) / (2 * rng.uniform(4, 40) ** 2)) + 0.02 * rng.rand(224, 224)
+        ty, tx = rng.uniform(0, 223, 2)
+        t = np.exp(-((ys - ty) ** 2 / (2 * 16.3 ** 2) + (xs - tx) ** 2 / (2 * 12.25 ** 2)))
+        t = np.round(255 * (t - t.min()) / (t.max() - t.min())) / 255
+        outs.append(o.astype(np.float32))
+        tgts.append(t.astype(np.float32))
+    return np.stack(outs), np.stack(tgts)
+
+
 def bilinear_upsample(x, scale, align_corners=False):
     """F.upsample(mode='bilinear') == align_corners=False (run_spatialstream.py:136); upsample_bilinear == True (AT.py:46)."""
     x = np.asarray(x, np.float32)

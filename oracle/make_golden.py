@@ -199,6 +199,13 @@ def main():
             warnings.simplefilter("ignore")
             ca = ref_at.crop_align_feature(t(feats[b:b + 1]), [list(gazes[b])], 3).contiguous()
         avecs.append(torch.mean(ca.view(1, 512, -1), 2).numpy())
+    # ---- validation metric (utils.computeAAEAUC) on seeded prediction / target pairs
+    mo, mt = orc.synth_metric_inputs(12, 21)
+    rows = [ref_utils.computeAAEAUC(mo[b], mt[b]) for b in range(mo.shape[0])]
+    batch = ref_utils.computeAAEAUC(mo, mt)
+    np.savez_compressed(os.path.join(OUT, "metric_aae_auc.npz"), seed=21, B=12, aae=np.array([r[0] for r in rows]),
+                        auc=np.array([r[1] for r in rows]), gp=np.array([r[2][0] for r in rows]),
+                        batch_aae=np.float64(batch[0]), batch_auc=np.float64(batch[1]))
     np.savez_compressed(os.path.join(OUT, "at_glue.npz"), seed=9, gazes=gazes, vec=np.concatenate(vecs), map=np.concatenate(maps),
                         align_vec=np.concatenate(avecs))
     print("golden fixtures written to", OUT)

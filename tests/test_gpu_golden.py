@@ -149,3 +149,23 @@ def test_at_glue_vs_reference_golden(cuda_dev):
     assert np.abs(wm.cpu().numpy() - g["map"]).max() <= 2e-5
     av = ops.crop_align_mean(feats, g["gazes"].tolist(), 3)
     assert np.abs(av.cpu().numpy() - g["align_vec"]).max() <= 1e-5
+
+
+def test_metric_aae_auc_vs_reference_golden(cuda_dev):
+    """Device computeAAEAUC (egaze_aae_auc) against the reference's scipy implementation run on the same seeded maps:
+    gaze point exact, AAE within 1e-4 degrees, AUC within 2 pixels of 50176 (float32 vs float64 centre-of-mass sums can move
+    int(predicted) across an integer boundary only in contrived cases; none here)."""
+    from egaze import ops
+    import utils as egaze_utils
+    g = np.load(os.path.join(GOLD, "metric_aae_auc.npz"))
+    mo, mt = orc.synth_metric_inputs(int(g["B"]), int(g["seed"]))
+    o, t = torch.from_numpy(mo).to(cuda_dev), torch.from_numpy(mt).to(cuda_dev)
+    res = ops.aae_auc(o, t).cpu().numpy()
+    assert np.array_equal(res[:, 2:4].astype(np.int64), g["gp"])
+    assert np.abs(res[:, 0] - g["aae"]).max() <= 1e-4
+    assert np.abs(res[:, 1] - g["auc"]).max() <= 2.0 / (224 * 224)
+    aae, auc, gp = egaze_utils.computeAAEAUC(o, t)          # the drop-in entry point with CUDA tensors
+    assert abs(aae - float(g["batch_aae"])) <= 1e-4 and abs(auc - float(g["batch_auc"])) <= 2.0 / (224 * 224)
+    assert gp == [list(map(int, r)) for r in g["gp"]]
+    aae_h, auc_h, _ = egaze_utils.computeAAEAUC(mo, mt)     # NumPy arrays keep the reference's host path
+    assert abs(aae_h - float(g["batch_aae"])) <= 1e-9 and abs(auc_h - float(g["batch_auc"])) <= 1e-12

@@ -182,3 +182,34 @@ def test_full_pipeline_train_step(cuda_dev):
     assert any((p.detach() - q).abs().max().item() > 0 for p, q in zip(wl.lf.parameters(), lf_before))
     losses2 = wl.step(*wl.dev).cpu()
     assert torch.isfinite(losses2).all()
+
+
+def test_at_step_fixation_saccade_vs_oracle(cuda_dev):
+    """egaze.at.at_sequence (B videos advancing together, fixation frames keep their crop weights and LSTM state) against the
+    NumPy oracle running every video on its own through the reference's loop body (AT.py:236-248)."""
+    import numpy as np
+    import models.LSTMnet as L
+    from egaze import at
+    from oracle import egaze_oracle as orc
+    T, B = 7, 3
+    torch.manual_seed(4)
+    net = L.lstmnet().to(cuda_dev).eval()
+    g = torch.Generator().manual_seed(10)
+    feats = torch.relu(torch.randn(T, B, 512, 14, 14, generator=g))
+    gazes = torch.randint(0, 224, (T, B, 2), generator=g).int()
+    fixsac = (torch.rand(T, B, generator=g) < 0.4).int()
+    maps, _ = at.at_sequence(feats.to(cuda_dev), gazes.to(cuda_dev), fixsac.to(cuda_dev), net)
+    maps = maps.cpu().numpy()
+    sd = {k: v.detach().cpu().numpy() for k, v in net.state_dict().items()}
+    fn, gn, fs = feats.numpy(), gazes.numpy(), fixsac.numpy()
+    for b in range(B):
+        h = np.zeros((2, 1, 512), np.float32)
+        c = np.zeros((2, 1, 512), np.float32)
+        for t in range(T):
+            f = fn[t, b:b + 1]
+            w = orc.crop_mean(f, gn[t, b:b + 1], 3)
+            if fs[t, b] != 1:
+                out, h, c = orc.lstmnet_forward(sd, w[None], h, c)
+                w = out[0]
+            ref = orc.get_weighted(w, f)[0]
+            assert np.abs(maps[t, b] - ref).max() <= 1e-4, (t, b)
