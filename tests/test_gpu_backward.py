@@ -229,3 +229,41 @@ def test_vgg_single_stream_train_step(cuda_dev):
             assert p.grad is None
         else:
             assert rel_l2(p.grad, q.grad) <= 5e-2, k
+
+
+@pytest.mark.parametrize("shape", [(32, 224, 224, 64, 64), (32, 56, 56, 256, 256), (32, 14, 14, 512, 512)])
+def test_full_size_adjoint_and_linearity(cuda_dev, shape):
+    """BASELINE-size properties that need no oracle (the NumPy oracle cannot finish a B=32, 224x224 layer in seconds):
+      * linearity:  conv(x1 + 2*x2) == conv(x1) + 2*conv(x2)
+      * adjoint identities of the three tcgen05 kernels on the same operands:
+            <conv(x; w), dy> == <x, dgrad(dy; w)> == <w, wgrad(x, dy)>
+    all at the batch-32 layer sizes the headline benchmark runs (fp64 dot products of the fp32 outputs).  The operands are
+    first rounded to what the kernels see (hi+lo split), so the identities hold to accumulation-order rounding."""
+    from egaze import ops
+    N, H, W, Cin, Cout = shape
+    g = torch.Generator().manual_seed(12)
+    rnd = lambda *s: ops.from_split(ops.to_split(torch.randn(*s, generator=g).to(cuda_dev)))
+    x1, x2, dy = rnd(N, Cin, H, W), rnd(N, Cin, H, W), rnd(N, Cout, H, W)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) * 0.05).to(cuda_dev)
+    w = w.bfloat16().float() + (w - w.bfloat16().float()).bfloat16().float()     # hi + lo exactly
+
+    def conv(x):
+        a = ops.to_split(x)
+        _, y, _ = ops.conv3x3(a, ops.pack_cache.get(w, 0, cols_p=a.Cp), want_f32=True, want_split=False)
+        return ops.nhwc_f32_to_nchw(y, Cout)
+
+    y1, y2 = conv(x1), conv(x2)
+    y12 = conv(ops.from_split(ops.to_split(x1 + 2 * x2)))
+    x12 = ops.from_split(ops.to_split(x1 + 2 * x2))
+    lin_ref = y1 + 2 * y2 + conv(x12 - (x1 + 2 * x2))      # the split of the sum may round: account for that exactly
+    assert rel_l2(y12, lin_ref) <= 2e-5, rel_l2(y12, lin_ref)
+
+    dya = ops.to_split(dy)
+    _, dx, _ = ops.conv3x3(dya, ops.pack_cache.get(w, 1, cols_p=dya.Cp), want_f32=True, want_split=False)
+    dx = ops.nhwc_f32_to_nchw(dx, Cin)
+    gw = ops.wgrad3x3(ops.to_split(x1), dya, Cout, Cin)
+    a = (y1.double() * dy.double()).sum().item()
+    b = (x1.double() * dx.double()).sum().item()
+    c = (w.double() * gw.double()).sum().item()
+    scale = (y1.double().norm() * dy.double().norm()).item()
+    assert abs(a - b) <= 2e-6 * scale and abs(a - c) <= 2e-6 * scale, (a, b, c, scale)
