@@ -1,8 +1,10 @@
 """Data-parallel plumbing: frames shard across ranks, ONE all-reduce per optimiser step.
 
-The reference is single-GPU (gaze_full.py:37); this is the only multi-GPU mechanism the path needs.  Every trainable
-parameter's .grad is a view into one flat fp32 buffer, so the backward kernels' outputs are accumulated in place and
-the NCCL all-reduce (AVG) over NVLink needs no pack / unpack copies.  BatchNorm statistics stay per replica.
+The reference is single-GPU (gaze_full.py:37); this is the only multi-GPU mechanism the path needs.  After the
+backward the gradients are gathered into ONE flat fp32 buffer with a single multi-tensor copy, averaged with one NCCL
+all-reduce over NVLink, and every .grad is re-pointed at its slice of the buffer (the optimiser reads the averaged values
+in place, no scatter).  Letting autograd ACCUMULATE into pre-set .grad views instead costs one small add kernel per
+parameter (215 for model_SP) every step.  BatchNorm statistics stay per replica.
 """
 import torch
 import torch.distributed as dist
@@ -23,20 +25,33 @@ class FlatGradBucket(object):
             off += p.numel()
 
     def zero(self):
-        """Zero the bucket and make sure every .grad still aliases it (zero_grad(set_to_none=True) would detach them)."""
-        self.flat.zero_()
-        for p, v in zip(self.params, self.views):
-            if p.grad is None or p.grad.data_ptr() != v.data_ptr():
-                p.grad = v
+        """Drop the gradients (the next backward assigns fresh tensors instead of adding into the bucket)."""
+        for p in self.params:
+            p.grad = None
 
     def allreduce(self, group=None):
-        """Average the gradients over all ranks (no-op for a single process)."""
+        """Gather every parameter's gradient into the flat buffer (one multi-tensor copy; parameters without a gradient
+        contribute zeros), average over all ranks (no-op for a single process) and alias .grad to the buffer."""
+        src, dst, missing = [], [], []
+        for p, v in zip(self.params, self.views):
+            g = p.grad
+            if g is None:
+                missing.append(v)
+            elif g.data_ptr() != v.data_ptr():
+                src.append(g.reshape(v.shape))
+                dst.append(v)
+        if dst:
+            torch._foreach_copy_(dst, src)
+        if missing:
+            torch._foreach_zero_(missing)
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             if dist.get_backend(group) == "nccl":
                 dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group)
             else:  # gloo (CPU tests) has no AVG
                 dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
                 self.flat.div_(dist.get_world_size(group))
+        for p, v in zip(self.params, self.views):
+            p.grad = v
         return self.flat
 
 

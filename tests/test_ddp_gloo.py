@@ -35,13 +35,13 @@ def _worker(rank, world, port, out):
         x = torch.randn(8, 3, 16, 16, generator=g)
         t = torch.rand(8, 1, 16, 16, generator=g)
         xs, ts = x[rank * 4:(rank + 1) * 4], t[rank * 4:(rank + 1) * 4]
-        for step in range(2):  # second step checks that zero() re-aliases and does not accumulate
+        for step in range(2):  # second step checks that zero() drops the old gradients (no accumulation)
             bucket.zero()
             loss = torch.nn.functional.binary_cross_entropy(m(xs), ts)
             loss.backward()
-            for p, v in zip(bucket.params, bucket.views):
-                assert p.grad.data_ptr() == v.data_ptr()
             flat = bucket.allreduce().clone()
+            for p, v in zip(bucket.params, bucket.views):   # the optimiser reads the averaged values through .grad
+                assert p.grad.data_ptr() == v.data_ptr()
         if rank == 0:
             torch.save({"flat": flat, "seeds": [shard_seed(1234, r) for r in range(world)]}, out)
     finally:
