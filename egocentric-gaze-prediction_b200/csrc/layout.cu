@@ -86,24 +86,33 @@ __global__ void f32_to_split_kernel(const float* __restrict__ x, size_t n, __nv_
 // w: OIHW fp32 [Co][Ci][3][3].
 //  mode 0 (fprop) : out[(r*3+s)][co][ci]            rows = Co, cols = Ci_p  (ci >= Ci zero)
 //  mode 1 (dgrad) : out[((2-r)*3+(2-s))][ci][co]    rows = Ci, cols = Co_p  (co >= Co zero)
+// One thread per (row, col): it reads the nine taps of its weight (36 contiguous bytes; in mode 0 adjacent threads read
+// adjacent runs) and writes one element of each tap plane (adjacent threads write adjacent bf16).
+__device__ __forceinline__ void pack_w3x3_body(const float* __restrict__ w, int Co, int Ci, int rows, int cols_p, int mode,
+                                               __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                               uint32_t first, uint32_t stride) {
+  const uint32_t total = (uint32_t)rows * cols_p;
+  const size_t plane = (size_t)rows * cols_p;
+  for (uint32_t i = first; i < total; i += stride) {
+    const uint32_t col = i % cols_p, row = i / cols_p;
+    float v[9];
+    const bool live = mode == 0 ? col < (uint32_t)Ci : col < (uint32_t)Co;
+    const float* src = mode == 0 ? w + ((size_t)row * Ci + col) * 9 : w + ((size_t)col * Ci + row) * 9;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) v[t] = live ? src[t] : 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      __nv_bfloat16 h, l;
+      split_bf16(v[mode == 0 ? t : 8 - t], h, l);
+      hi[(size_t)t * plane + i] = h;
+      if (lo) lo[(size_t)t * plane + i] = l;
+    }
+  }
+}
+
 __global__ void pack_w3x3_kernel(const float* __restrict__ w, int Co, int Ci, int rows, int cols_p, int mode,
                                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
-  const size_t total = (size_t)9 * rows * cols_p;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int col = (int)(i % cols_p);
-    const int row = (int)((i / cols_p) % rows);
-    const int tap = (int)(i / ((size_t)cols_p * rows));
-    float v = 0.f;
-    if (mode == 0) {
-      if (col < Ci) v = w[((size_t)row * Ci + col) * 9 + tap];
-    } else {
-      if (col < Co) v = w[((size_t)col * Ci + row) * 9 + (8 - tap)];
-    }
-    __nv_bfloat16 h, l;
-    split_bf16(v, h, l);
-    hi[i] = h;
-    if (lo) lo[i] = l;
-  }
+  pack_w3x3_body(w, Co, Ci, rows, cols_p, mode, hi, lo, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
 
 // The same for MANY weights in one launch (after an optimiser step every packed copy is stale): blockIdx.y = job.
@@ -115,34 +124,24 @@ struct PackJob {
 };
 __global__ void pack_w3x3_multi_kernel(const PackJob* __restrict__ jobs) {
   const PackJob j = jobs[blockIdx.y];
-  const uint32_t total = (uint32_t)9 * j.rows * j.cols_p;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const uint32_t col = i % j.cols_p, t = i / j.cols_p, row = t % j.rows, tap = t / j.rows;
-    float v = 0.f;
-    if (j.mode == 0) {
-      if (col < (uint32_t)j.Ci) v = j.w[((size_t)row * j.Ci + col) * 9 + tap];
-    } else {
-      if (col < (uint32_t)j.Co) v = j.w[((size_t)col * j.Ci + row) * 9 + (8 - tap)];
-    }
-    __nv_bfloat16 h, l;
-    split_bf16(v, h, l);
-    j.hi[i] = h;
-    if (j.lo) j.lo[i] = l;
-  }
+  pack_w3x3_body(j.w, j.Co, j.Ci, j.rows, j.cols_p, j.mode, j.hi, j.lo, blockIdx.x * blockDim.x + threadIdx.x,
+                 gridDim.x * blockDim.x);
 }
 
 // dwp: [9][Co_p][Ci_p] fp32 (wgrad accumulator)  ->  gw: OIHW [Co][Ci][3][3]  (gw = beta*gw + dwp).
-// clear != 0: the accumulator is zeroed on the way out, so a persistent buffer is ready for the next accumulation.
-__global__ void unpack_wgrad_kernel(float* __restrict__ dwp, int Co, int Ci, int Co_p, int Ci_p, float beta, int clear,
+// One thread per (co, ci): nine strided reads, one 36-byte contiguous store (adjacent threads store adjacent 36-byte runs).
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, int Co, int Ci, int Co_p, int Ci_p, float beta,
                                     float* __restrict__ gw) {
-  const uint32_t total = (uint32_t)9 * Co_p * Ci_p;
+  const uint32_t total = (uint32_t)Co * Ci;
+  const size_t tap_stride = (size_t)Co_p * Ci_p;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const uint32_t ci = i % Ci_p, t = i / Ci_p, co = t % Co_p, tap = t / Co_p;
-    const float v = dwp[i];
-    if (clear) dwp[i] = 0.f;
-    if (co < (uint32_t)Co && ci < (uint32_t)Ci) {
-      float* dst = gw + ((size_t)co * Ci + ci) * 9 + tap;
-      *dst = beta == 0.f ? v : fmaf(beta, *dst, v);
+    const uint32_t ci = i % Ci, co = i / Ci;
+    const float* src = dwp + (size_t)co * Ci_p + ci;
+    float* dst = gw + (size_t)i * 9;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const float v = src[tap * tap_stride];
+      dst[tap] = beta == 0.f ? v : fmaf(beta, dst[tap], v);
     }
   }
 }
@@ -195,7 +194,7 @@ extern "C" int egaze_pack_w3x3(const float* w_oihw, int Cout, int Cin, int cols_
   EGAZE_CHECK_ARG(w_oihw && hi, "pack_w3x3: bad args");
   const int rows = mode == 0 ? Cout : Cin;
   EGAZE_CHECK_ARG(cols_p >= (mode == 0 ? Cin : Cout), "pack_w3x3: cols_p too small");
-  const size_t total = (size_t)9 * rows * cols_p;
+  const size_t total = (size_t)rows * cols_p;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   pack_w3x3_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w_oihw, Cout, Cin, rows, cols_p, mode, (__nv_bfloat16*)hi,
@@ -217,10 +216,12 @@ extern "C" int egaze_pack_w3x3_multi(const void* jobs, int njobs, void* stream) 
 extern "C" int egaze_unpack_wgrad(float* dwp, int Cout, int Cin, int Cout_p, int Cin_p, float beta, int clear, float* gw_oihw,
                                   void* stream) {
   EGAZE_CHECK_ARG(dwp && gw_oihw && Cout_p >= Cout && Cin_p >= Cin, "unpack_wgrad: bad args");
-  const size_t total = (size_t)9 * Cout_p * Cin_p;
+  const size_t total = (size_t)Cout * Cin;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  unpack_wgrad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dwp, Cout, Cin, Cout_p, Cin_p, beta, clear, gw_oihw);
+  unpack_wgrad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dwp, Cout, Cin, Cout_p, Cin_p, beta, gw_oihw);
   EGAZE_LAUNCH_CHECK();
+  // clear != 0: leave the (persistent) accumulator zeroed for the next accumulation -- a stream-ordered fill at full bandwidth
+  if (clear) EGAZE_CUDA(cudaMemsetAsync(dwp, 0, (size_t)9 * Cout_p * Cin_p * sizeof(float), (cudaStream_t)stream));
   return EGAZE_OK;
 }
