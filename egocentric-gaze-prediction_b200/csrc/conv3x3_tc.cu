@@ -149,7 +149,7 @@ __device__ __forceinline__ void epi_store(const ConvTcParams& p, const EpiTile& 
       if (!(bf16_bits_to_float(mk.y & 0xffffu) > 0.f)) v.z = 0.f;
       if (!(bf16_bits_to_float(mk.y >> 16) > 0.f)) v.w = 0.f;
     }
-    cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;   // column sums (used when p.colsum is set)
+    if (MASK) { cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w; }   // column sums = bias gradient (masked dgrad modes only)
     uint2 hi2, lo2;
     if (SPLIT) split_bf16x4(v, hi2, lo2);
     const size_t off = e.out_base + (size_t)(ph * e.out_row + pw * e.out_px);
@@ -720,7 +720,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
             e.mask_base = ((size_t)(img * mf * Ho + mf * oh0) * (mf * Wo) + (size_t)(mf * ow0)) * p.Cout + ch;
             e.mask_row = mf * mf * Wo * p.Cout; e.mask_px = mf * p.Cout;
             done = true;
-            switch (p.stats && lean_mode != 1 ? 0 : lean_mode) {
+            // statistics ride on mode 1 only, column sums on the masked modes only; anything else takes the generic loop
+            switch ((p.stats && lean_mode != 1) || (p.colsum && lean_mode != 5 && lean_mode != 6) ? 0 : lean_mode) {
               case 1:                                                              // fp32 out: train-mode trunk / dgrad into BN
                 if (p.stats) epi_store<0, false, false, true, false, true>(p, e, cs, k4, &s1v, &s2v);
                 else epi_store<0, false, false, true, false>(p, e, cs);

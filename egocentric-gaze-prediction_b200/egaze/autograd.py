@@ -10,6 +10,8 @@ Backward schedule per layer (reverse order):
   conv+ReLU(+ups)    : dgrad of the NEXT layer already applied this layer's ReLU mask (and the 2x2 sum that is the
                        gradient of nn.Upsample) in its epilogue -> wgrad + col_sum + dgrad
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -18,6 +20,41 @@ from . import engine, ops
 
 def _req(p):
     return p is not None and p.requires_grad
+
+
+# ---- weight gradients on a side stream ------------------------------------------------------------------------------
+# dW of a layer feeds nothing downstream in the backward, so its tcgen05 GEMM is enqueued on a second stream: it overlaps
+# the HBM-bound BatchNorm-backward passes of the next layers (different SM resources: tensor pipe vs DRAM), which the
+# main stream would otherwise run with the tensor pipe idle.  EGAZE_WGRAD_STREAM=0 keeps everything on one stream.
+_side_streams = {}
+
+
+def _use_side_stream():
+    return os.environ.get("EGAZE_WGRAD_STREAM", "1") != "0"
+
+
+def _wgrad(x_act, dy_act, cout, cin):
+    if not _use_side_stream():
+        return ops.wgrad3x3(x_act, dy_act, cout, cin)
+    dev = x_act.hi.device
+    side = _side_streams.get(dev)
+    if side is None:
+        side = _side_streams[dev] = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream(dev)
+    side.wait_stream(main)                      # the operands were produced on the main stream
+    with torch.cuda.stream(side):
+        gw = ops.wgrad3x3(x_act, dy_act, cout, cin)
+    for t in (x_act.hi, x_act.lo, dy_act.hi, dy_act.lo):
+        if t is not None:
+            t.record_stream(side)               # the caching allocator must not recycle them while the side stream reads
+    gw.record_stream(main)
+    return gw
+
+
+def _join_side_stream():
+    """Called once at the end of a backward: the returned gradients are consumed on the main stream."""
+    for dev, side in _side_streams.items():
+        torch.cuda.current_stream(dev).wait_stream(side)
 
 
 class _GradBag(object):
@@ -40,7 +77,7 @@ def _conv_param_grads(bag, conv, x_act, gpre_act, bias_grad_is_zero=False, bias_
     PyTorch returns rounding noise ~1e-9 there), so no reduction pass is spent on it.  bias_grad: column sums already
     accumulated by the dgrad epilogue that produced gpre_act (then no pass over gpre_act is needed either)."""
     if _req(conv.weight):
-        gw = ops.wgrad3x3(x_act, gpre_act, conv.out_channels, conv.in_channels)
+        gw = _wgrad(x_act, gpre_act, conv.out_channels, conv.in_channels)
         bag.put(conv.weight, gw)
     if _req(conv.bias):
         if bias_grad_is_zero:
@@ -181,7 +218,7 @@ class _ModelSPFn(torch.autograd.Function):
             d2 = ops.pairmax_bwd(tail["raw2"], dmx)  # [2B,14,14,512] split: gradient routed to the arg-max stream
             fus = model.fusion
             if _req(fus.weight):
-                bag.put(fus.weight, ops.wgrad3x3(tail["cat"], d2, fus.out_channels, fus.in_channels))
+                bag.put(fus.weight, _wgrad(tail["cat"], d2, fus.out_channels, fus.in_channels))
             if _req(fus.bias):
                 bag.put(fus.bias, torch.zeros_like(fus.bias))  # feeds model_SP.bn in batch-stat mode: exactly zero
             if trunk_need:
@@ -198,6 +235,7 @@ class _ModelSPFn(torch.autograd.Function):
         gx_s = ops.nhwc_f32_to_nchw(gx_s, specs_s[0].conv.in_channels) if (gx_s is not None and ctx.need_x[0]) else None
         gx_t = ops.nhwc_f32_to_nchw(gx_t, specs_t[0].conv.in_channels) if (gx_t is not None and ctx.need_x[1]) else None
         ctx.rec = None
+        _join_side_stream()
         return (None, gx_s, gx_t) + _ret_grads(bag, _params(model))
 
 
@@ -232,6 +270,7 @@ class _SequentialFn(torch.autograd.Function):
         gx = bn_sequential_backward(specs, saved, g, bag, ctx.need_x)
         gx = ops.nhwc_f32_to_nchw(gx, specs[0].conv.in_channels) if (gx is not None and ctx.need_x) else None
         ctx.rec = None
+        _join_side_stream()
         return (None, gx) + _ret_grads(bag, _params(ctx.seq))
 
 
@@ -276,6 +315,7 @@ class _VGGFn(torch.autograd.Function):
         gx = bn_sequential_backward(specs, saved_f, g, bag, ctx.need_x) if trunk_need else None
         gx = ops.nhwc_f32_to_nchw(gx, specs[0].conv.in_channels) if (gx is not None and ctx.need_x) else None
         ctx.rec = None
+        _join_side_stream()
         return (None, gx) + _ret_grads(bag, _params(model))
 
 
@@ -320,6 +360,7 @@ class _LateFusionFn(torch.autograd.Function):
             gf = gx[:, 0:1].contiguous() if ctx.need_x[0] else None
             gg = gx[:, 1:2].contiguous() if ctx.need_x[1] else None
         ctx.rec = None
+        _join_side_stream()
         return (None, gf, gg) + _ret_grads(bag, _params(model))
 
 
