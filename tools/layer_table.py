@@ -1,5 +1,6 @@
 """Per-launch timing table of the tcgen05 conv kernels for one SP train step (B=32, 224x224)."""
 import os, sys
+os.environ["EGAZE_WGRAD_STREAM"] = "0"   # per-kernel durations: keep every launch on one stream (no overlap)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "egocentric-gaze-prediction_b200")); sys.path.insert(0, ROOT)
 import torch
@@ -7,7 +8,7 @@ from egaze import ops
 from bench import Workload
 B = int(os.environ.get("B", 32))
 wl = Workload(os.environ.get("WL", "sp_train"), B, 224, 0, 1, torch.device("cuda"))
-for _ in range(2): wl.step(*wl.dev)
+for _ in range(3): wl.step(*wl.dev)
 torch.cuda.synchronize()
 ops.conv_timer_reset(True)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
