@@ -106,16 +106,18 @@ def _any_req(mods):
     return any(p.requires_grad for m in mods for p in m.parameters())
 
 
-def bn_sequential_backward(specs, saved, g, bag, need_input_grad):
-    """Backward through a conv+BN+ReLU(+pool) chain.  g: NHWC fp32 gradient w.r.t. the chain output.
-    Returns the NHWC fp32 gradient w.r.t. the chain input (or None)."""
+def _bn_chain_steps(specs, saved, g, bag, need_input_grad, result):
+    """Generator: one conv+BN+ReLU(+pool) layer of the backward chain per step (so that two independent chains -- the two
+    trunks of model_SP -- can be enqueued alternately on two streams).  result[0] receives the gradient w.r.t. the chain
+    input (or None)."""
     first_needed = None
     for i, sp in enumerate(specs):
         if _any_req([sp.conv, sp.bn]):
             first_needed = i
             break
     if first_needed is None and not need_input_grad:
-        return None
+        result[0] = None
+        return
     stop = 0 if need_input_grad else first_needed
     for i in range(len(specs) - 1, stop - 1, -1):
         sp, rec = specs[i], saved[i]
@@ -131,7 +133,46 @@ def bn_sequential_backward(specs, saved, g, bag, need_input_grad):
             _, g, _ = _dgrad(sp.conv, draw, want_f32=True, want_split=False)
         else:
             g = None
-    return g
+        result[0] = g
+        yield
+
+
+def bn_sequential_backward(specs, saved, g, bag, need_input_grad):
+    """Backward through a conv+BN+ReLU(+pool) chain.  g: NHWC fp32 gradient w.r.t. the chain output.
+    Returns the NHWC fp32 gradient w.r.t. the chain input (or None)."""
+    result = [None]
+    for _ in _bn_chain_steps(specs, saved, g, bag, need_input_grad, result):
+        pass
+    return result[0]
+
+
+# ---- the two trunks of model_SP on two streams --------------------------------------------------------------------------
+# features_s and features_t are independent until the fusion layer.  Enqueued alternately on two streams, the HBM-bound
+# BatchNorm passes of one trunk run under the tensor-bound convolutions of the other.  EGAZE_TRUNK_STREAM=0 disables it.
+_trunk_streams = {}
+
+
+def _trunk_stream(dev):
+    if os.environ.get("EGAZE_TRUNK_STREAM", "1") == "0":
+        return None
+    st = _trunk_streams.get(dev)
+    if st is None:
+        st = _trunk_streams[dev] = torch.cuda.Stream(device=dev)
+    return st
+
+
+def _alternate(gen_a, gen_b, stream_b):
+    """Drive two generators to exhaustion, one step each in turn; gen_b runs with stream_b current."""
+    live_a, live_b = True, True
+    while live_a or live_b:
+        if live_a:
+            live_a = next(gen_a, _DONE) is not _DONE
+        if live_b:
+            with torch.cuda.stream(stream_b):
+                live_b = next(gen_b, _DONE) is not _DONE
+
+
+_DONE = object()
 
 
 def relu_sequential_backward(specs, saved, gpre, bag, want_input_grad_f32):
@@ -163,7 +204,15 @@ def _params(module):
 
 
 def _ret_grads(bag, params):
-    return tuple(bag.get(p) for p in params)
+    """Gradients in parameter order.  Some were produced on the weight-gradient / trunk streams: tell the caching allocator
+    that the main stream (optimiser, all-reduce) uses them too."""
+    out = []
+    for p in params:
+        g = bag.get(p)
+        if g is not None and g.is_cuda:
+            g.record_stream(torch.cuda.current_stream(g.device))
+        out.append(g)
+    return tuple(out)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -176,12 +225,32 @@ class _ModelSPFn(torch.autograd.Function):
         saved_s, saved_t, saved_tail = [], [], []
         specs_s, _ = engine.parse_sequential(model.features_s)
         specs_t, _ = engine.parse_sequential(model.features_t)
-        a_s = ops.to_split(x_s, _first_cp(specs_s[0].conv))
-        a_t = ops.to_split(x_t, _first_cp(specs_t[0].conv))
-        for sp in specs_s:
-            a_s = engine.run_conv_spec(a_s, sp, saved_s)
-        for sp in specs_t:
-            a_t = engine.run_conv_spec(a_t, sp, saved_t)
+        ts = _trunk_stream(x_s.device)
+        if ts is None:
+            a_s = ops.to_split(x_s, _first_cp(specs_s[0].conv))
+            a_t = ops.to_split(x_t, _first_cp(specs_t[0].conv))
+            for sp in specs_s:
+                a_s = engine.run_conv_spec(a_s, sp, saved_s)
+            for sp in specs_t:
+                a_t = engine.run_conv_spec(a_t, sp, saved_t)
+        else:
+            main = torch.cuda.current_stream(x_s.device)
+            ts.wait_stream(main)                       # inputs and re-packed weights were produced on the main stream
+            box_s, box_t = [None], [None]
+
+            def trunk(x, specs, saved, box):
+                box[0] = ops.to_split(x, _first_cp(specs[0].conv))
+                yield
+                for sp in specs:
+                    box[0] = engine.run_conv_spec(box[0], sp, saved)
+                    yield
+
+            _alternate(trunk(x_s, specs_s, saved_s, box_s), trunk(x_t, specs_t, saved_t, box_t), ts)
+            a_s, a_t = box_s[0], box_t[0]
+            x_t.record_stream(ts)
+            main.wait_stream(ts)                       # the fusion layer reads both trunks
+            for t in (a_t.hi, a_t.lo):
+                t.record_stream(main)
         # forward hooks registered on the trunks (AT.py:105 idiom) still fire, with detached NCHW views
         for mod, act in ((model.features_s, a_s), (model.features_t, a_t)):
             if mod._forward_hooks:
@@ -226,8 +295,21 @@ class _ModelSPFn(torch.autograd.Function):
                 _, gf, _ = ops.conv3x3(d2, wpack, want_f32=True, want_split=False)
                 B = gf.shape[0] // 2
                 g_s, g_t = gf[:B], gf[B:]
-                gx_s = bn_sequential_backward(specs_s, saved_s, g_s, bag, ctx.need_x[0])
-                gx_t = bn_sequential_backward(specs_t, saved_t, g_t, bag, ctx.need_x[1])
+                ts = _trunk_stream(gf.device)
+                if ts is None:
+                    gx_s = bn_sequential_backward(specs_s, saved_s, g_s, bag, ctx.need_x[0])
+                    gx_t = bn_sequential_backward(specs_t, saved_t, g_t, bag, ctx.need_x[1])
+                else:
+                    main = torch.cuda.current_stream(gf.device)
+                    ts.wait_stream(main)               # g_t comes from the fusion dgrad on the main stream
+                    gf.record_stream(ts)
+                    res_s, res_t = [None], [None]
+                    _alternate(_bn_chain_steps(specs_s, saved_s, g_s, bag, ctx.need_x[0], res_s),
+                               _bn_chain_steps(specs_t, saved_t, g_t, bag, ctx.need_x[1], res_t), ts)
+                    main.wait_stream(ts)
+                    gx_s, gx_t = res_s[0], res_t[0]
+                    if gx_t is not None:
+                        gx_t.record_stream(main)
             else:
                 gx_s = gx_t = None
         else:
