@@ -277,7 +277,7 @@ __device__ __forceinline__ uint32_t tap_merged_probe(uint32_t d_tmem, uint32_t d
 #undef EGAZE_MMA_PAIR
 
 template <int NSPLIT, int KSTEPS, int CS>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __maxnreg__(128)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                   const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                   const ConvTcParams p) {
@@ -855,12 +855,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
       o[7] = prof_c[0]; o[8] = clock64() - prof_start; o[9] = (p.num_items - cluster_id + num_clusters - 1) / num_clusters;
       for (int i = 0; i < 5; ++i) o[10 + i] = prof_e[i];
     }
+    // the last chunk's per-warp partials are folded into the CTA sums AFTER its closing barrier: wait for those adds
+    if (p.colsum || p.stats) ptx::named_bar_sync(1, kEpiThreads);
     if (p.colsum) {
       for (int c = et; c < p.Cout; c += kEpiThreads) atomicAdd(p.colsum + c, colsum_s[c]);
     }
     if (p.stats) {
       // one (mean, M2, n) partial per CTA and channel; bias shifts the mean only
-      ptx::named_bar_sync(1, kEpiThreads);
       for (int c = et; c < p.Cout; c += kEpiThreads) {
         const float n = red[c / p.BN];
         float mean = 0.f, m2 = 0.f;
