@@ -433,21 +433,24 @@ def main():
     # ---- roofline pass: duration of every tcgen05 conv / wgrad launch ------------------------------------------------------
     # Same workload, same process, right after the timed region, with a CUDA-event pair around every launch on the stream
     # it is launched on.  The weight-gradient GEMMs normally run on a second stream and overlap other kernels (their event
-    # intervals then overlap too and the sum double-counts time), so this pass keeps everything on one stream: each number is
-    # the kernel's own duration inside a long step.
+    # intervals then overlap too and the sum double-counts time), and so do the two trunks; this pass keeps everything on one
+    # stream: each number is the kernel's own duration inside a long step.
     R = max(1, min(K, 5))
-    prev = os.environ.get("EGAZE_WGRAD_STREAM")
-    os.environ["EGAZE_WGRAD_STREAM"] = "0"
+    knobs = ("EGAZE_WGRAD_STREAM", "EGAZE_TRUNK_STREAM")
+    prev = {k: os.environ.get(k) for k in knobs}
+    for k in knobs:
+        os.environ[k] = "0"
     wl.step(*wl.dev)
     ops.conv_timer_reset(True)
     for _ in range(R):
         wl.step(*wl.dev)
     conv_ms, conv_launches = ops.conv_timer_read()   # summed over the R steps
     ops.conv_timer_reset(False)
-    if prev is None:
-        os.environ.pop("EGAZE_WGRAD_STREAM", None)
-    else:
-        os.environ["EGAZE_WGRAD_STREAM"] = prev
+    for k in knobs:
+        if prev[k] is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = prev[k]
     barrier()
 
     # ---- end to end: host (pinned) inputs in, result read back, every step -----------------------------------------------

@@ -1,6 +1,7 @@
 """Per-launch timing table of the tcgen05 conv kernels for one SP train step (B=32, 224x224)."""
 import os, sys
 os.environ["EGAZE_WGRAD_STREAM"] = "0"   # per-kernel durations: keep every launch on one stream (no overlap)
+os.environ["EGAZE_TRUNK_STREAM"] = "0"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "egocentric-gaze-prediction_b200")); sys.path.insert(0, ROOT)
 import torch

@@ -37,6 +37,7 @@ for S in [int(v) for v in args.sizes.split(",")]:
             ms = e0.elapsed_time(e1) / args.steps
             # kernel durations in a second pass on one stream (see bench.py: overlapping event intervals double-count)
             os.environ["EGAZE_WGRAD_STREAM"] = "0"
+            os.environ["EGAZE_TRUNK_STREAM"] = "0"
             wl.step(*wl.dev)
             ops.conv_timer_reset(True)
             for _ in range(args.steps):
@@ -44,6 +45,7 @@ for S in [int(v) for v in args.sizes.split(",")]:
             conv_ms, _ = ops.conv_timer_read()
             ops.conv_timer_reset(False)
             os.environ.pop("EGAZE_WGRAD_STREAM", None)
+            os.environ.pop("EGAZE_TRUNK_STREAM", None)
             fl = FLOP[S][0 if name == "sp_fwd" else 1] * B
             row[name] = {"ms_per_step": round(ms, 3), "fps": round(B / ms * 1e3, 1),
                          "conv_tflops": round(fl * args.steps / (conv_ms * 1e-3) / 1e12, 1),
