@@ -16,6 +16,7 @@ Prints ONE JSON line (rank 0).  `value` = device-resident throughput; `e2e` = sa
 API with HOST (pinned) inputs and a host read of the result inside the timed region.
 """
 import argparse
+import contextlib
 import json
 import os
 import subprocess
@@ -172,6 +173,7 @@ class Workload(object):
             self.lf = late_fusion().to(device).train()
             self.opt = torch.optim.Adam(self.model.parameters(), lr=1e-7)
             self.opt_lf = torch.optim.Adam(self.lf.parameters(), lr=1e-7)
+            self.lf_stream = torch.cuda.Stream(device=device)
             self.feats = []
             self.model._modules.get('features_s').register_forward_hook(lambda m, i, o: self.feats.append(o))  # AT.py:105
             self.hidden = (torch.zeros(2, B, 512, device=device), torch.zeros(2, B, 512, device=device))
@@ -231,17 +233,34 @@ class Workload(object):
             out = self.model(x_s, x_t)                                         # SP.py:132
             gtv = gt.view(out.size())
             loss = self.crit(out, gtv)
-            loss.backward()
-            with torch.no_grad():                                              # AT.py:224-252 on the hooked map, batched
-                feat = self.feats[0]
-                vec = ops.crop_mean(feat, self.gaze, 3)
-                w, hidden = self.lstm(vec.unsqueeze(0), self.hidden)
-                self.hidden = tuple(h.detach() for h in hidden)
-                amap = ops.weighted_map(w.squeeze(0), feat)
-                up = ops.bilinear_up(amap.unsqueeze(1), 16, False)
-            fused = self.lf(up, out.detach())                                  # LF.py:90
-            loss_lf = self.crit(fused, gtv)                                    # LF.py:91
-            loss_lf.backward()
+            # The AT step and the LF train step only need the SP forward's outputs: they are enqueued on a second stream and
+            # run (small, HBM / latency-bound kernels) under the tensor-bound SP backward.  EGAZE_BENCH_LF_STREAM=0: serial.
+            lf_stream = self.lf_stream if os.environ.get("EGAZE_BENCH_LF_STREAM", "1") != "0" else None
+            main = torch.cuda.current_stream(self.device)
+            if lf_stream is None:
+                loss.backward()
+            else:
+                lf_stream.wait_stream(main)
+            with torch.cuda.stream(lf_stream) if lf_stream is not None else contextlib.nullcontext():
+                with torch.no_grad():                                          # AT.py:224-252 on the hooked map, batched
+                    feat = self.feats[0]
+                    vec = ops.crop_mean(feat, self.gaze, 3)
+                    w, hidden = self.lstm(vec.unsqueeze(0), self.hidden)
+                    self.hidden = tuple(h.detach() for h in hidden)
+                    amap = ops.weighted_map(w.squeeze(0), feat)
+                    up = ops.bilinear_up(amap.unsqueeze(1), 16, False)
+                fused = self.lf(up, out.detach())                              # LF.py:90
+                loss_lf = self.crit(fused, gtv)                                # LF.py:91
+                loss_lf.backward()
+            if lf_stream is not None:
+                for t in (feat, out, gtv):
+                    t.record_stream(lf_stream)
+                loss.backward()                                                # SP backward on the main stream, concurrently
+                main.wait_stream(lf_stream)
+                for p_ in self.lf.parameters():
+                    if p_.grad is not None:
+                        p_.grad.record_stream(main)
+                loss_lf.record_stream(main)
             if self.flat is not None:
                 self.flat.allreduce()
             self.opt.step()
