@@ -267,3 +267,31 @@ def test_full_size_adjoint_and_linearity(cuda_dev, shape):
     c = (w.double() * gw.double()).sum().item()
     scale = (y1.double().norm() * dy.double().norm()).item()
     assert abs(a - b) <= 2e-6 * scale and abs(a - c) <= 2e-6 * scale, (a, b, c, scale)
+
+
+def test_multi_stream_schedule_matches_single_stream(cuda_dev):
+    """The default schedule runs the weight-gradient GEMMs and the temporal trunk on their own CUDA streams.  A training
+    step must give the same forward (bit for bit: the forward kernels are deterministic) and the same gradients (weight
+    gradients are summed with fp32 atomics, so to rounding) as the single-stream schedule; repeated to catch ordering bugs."""
+    import floss as floss_mod
+
+    def run(streams):
+        os.environ["EGAZE_WGRAD_STREAM"] = os.environ["EGAZE_TRUNK_STREAM"] = "1" if streams else "0"
+        try:
+            m, _ = _sp_pair(cuda_dev, 0, 0.8)
+            x_s, x_t, gt = [torch.from_numpy(a).to(cuda_dev) for a in orc.synth_sp_inputs(4, 64, 5)]
+            out = m(x_s, x_t)
+            loss = floss_mod.floss()(out, gt)
+            loss.backward()
+            torch.cuda.synchronize()
+            return out.detach().clone(), [p.grad.detach().clone() for p in m.parameters()]
+        finally:
+            os.environ.pop("EGAZE_WGRAD_STREAM", None)
+            os.environ.pop("EGAZE_TRUNK_STREAM", None)
+
+    ref_out, ref_grads = run(False)
+    for _ in range(3):
+        out, grads = run(True)
+        assert torch.equal(out, ref_out)
+        for g, r in zip(grads, ref_grads):
+            assert rel_l2(g, r) <= 1e-5 or (g - r).abs().max().item() <= 1e-9
