@@ -9,23 +9,33 @@
 //   weights      : packed [tap = r*3+s][Cout][Cin_p] bf16 (K-major rows of Cin_p), hi/lo planes alike.
 //   output       : NHWC fp32 and/or NHWC split-bf16, after the fused epilogue below.
 //
-// Tiling: one work item = one spatial tile of BH x BW output pixels (BH*BW <= 128 GEMM rows) x BN output
-// channels.  For each 64/32/16-channel chunk of Cin and each horizontal tap s, TMA loads ONE
-// (BH+2) x BW x KC input window whose origin is shifted by s-1 pixels (OOB rows/cols zero-filled by
-// the TMA unit = the conv padding).  The three vertical taps r read that same window at a row offset
-// of r*BW rows, which is a whole number of 8-row swizzle atoms because BW % 8 == 0 -- so the A operand
-// is fetched 3x (+halo) instead of 9x.  Weights stream through their own ring, one [BN x KC] box per tap.
-// precise mode issues hi*hi + hi*lo + lo*hi into the same fp32 TMEM accumulator.
+// Tiling: one work item = one spatial tile of BH x BW output pixels (BH*BW <= 128 GEMM rows) x BN output channels; K runs
+// over 64/32/16-channel chunks of Cin and the nine taps.  Two ways of feeding the activation operand:
+//   classic : per chunk and HORIZONTAL tap s, TMA loads one (BH+2) x BW x KC window whose origin is shifted by s-1 pixels
+//             (out-of-bounds rows / columns zero-filled by the TMA unit = the conv padding); the three vertical taps read
+//             that window at a row offset of r*BW rows, a whole number of 8-row swizzle atoms because BW % 8 == 0.
+//   window  : (KC == 64, BW == 8) ONE (BH+2) x (BW+2) x 64 window per chunk serves all nine taps: tap (r, s) is the same
+//             SWIZZLE_128B tile read through a descriptor that starts (r*(BW+2) + s) * 128 bytes further and steps its 8-row
+//             groups by (BW+2) * 128 bytes.  Legal because the tensor core swizzles on absolute shared-memory address bits
+//             (tools/probe_swizzle_shift.cu); the descriptor's base_offset field must stay 0.
+// Weights stream through their own ring, one box per tap.  precise mode issues, per K step, A_hi x [B_hi | B_lo] as ONE
+// MMA of N = 2*BN plus A_lo x B_hi; the accumulator blocks are added in the epilogue.
 //
-// Schedule: PERSISTENT CTAs (one per SM), launched as thread-block clusters of CS (1 or 2).  The CTAs of a cluster
-// work on adjacent spatial tiles of the SAME output-channel tile in lockstep, so the weight box of every tap is
-// fetched from L2 once per cluster: each CTA loads 1/CS of it and TMA-multicasts it into all CTAs' rings
-// (weight traffic is the dominant L2->SM stream of this kernel).  Two TMEM accumulator stages let the epilogue of
-// item i overlap the MMAs of item i+1.
+// Schedule: PERSISTENT CTAs (one per SM), launched as thread-block clusters of CS (1 or 2) whose CTAs work on adjacent
+// spatial tiles of the SAME output-channel tile.
+//   pair mode (default for BN >= 64): tcgen05.mma.cta_group::2 with M = 256.  Each CTA loads its own activation window and
+//             only HALF of every weight box into its own shared memory (cp.async.bulk.tensor .cta_group::2, completion
+//             accounted on rank 0's mbarrier); rank 0's MMA warp issues one MMA for both tiles and multicasts the commits.
+//             Per CTA this cuts the shared-memory operand traffic by a third, which is what bounded the kernel before.
+//   multicast mode: every CTA keeps the full weight box; each loads 1/CS of it and TMA-multicasts it to its peers.
+// Two TMEM accumulator stages let the epilogue of item i overlap the MMAs of item i+1.
 //
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (one elected lane),
-// warps 2..9 = epilogue (TMEM -> regs -> smem staging in 64-column chunks -> coalesced NHWC stores, BN batch
-// statistics, 2x2 max/sum reduction, ReLU/mask, nearest-2x replicate).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..9 = epilogue.  Producer
+// and issuer walk their loop nests with the WHOLE warp (uniform control flow keeps descriptors in uniform registers) and
+// one elected lane issues; the next slot's barrier query is fused into the MMA asm block.  The epilogue stages the
+// accumulator tile through shared memory (64-column chunks) and drains it with compile-time-specialised store loops:
+// bias / folded-BN affine / ReLU, 2x2 max or sum, ReLU-backward mask, nearest-2x replicate, packed bf16 split, coalesced
+// NHWC stores -- with BatchNorm batch statistics (shifted sums) and bias-gradient column sums accumulated in the same pass.
 #include "common.cuh"
 
 namespace {
