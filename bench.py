@@ -208,6 +208,46 @@ class Workload(object):
             broadcast_parameters(self.lf, 0)
         self.flat = FlatGradBucket(self.model.parameters() if params is None else params, self.device)
 
+    def capture(self):
+        """Capture one whole training step (forward, floss, backward on all three streams, Adam) on the resident inputs into a
+        CUDA graph; `replay()` then runs a step with no host work at all.  Only used for the device-resident throughput
+        loop of single-GPU `sp_train` (EGAZE_BENCH_GRAPH=0 turns it off); returns False -- and the caller stays on the eager
+        path -- if anything in the capture fails."""
+        try:
+            self.opt = torch.optim.Adam(self.model.parameters(), lr=1e-7, capturable=True)
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):                      # warm-up on a side stream, as torch.cuda.graph requires
+                for _ in range(3):
+                    self.step(*self.dev)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.graph_out = self.step(*self.dev)
+            self.graph = g
+            torch.cuda.synchronize(self.device)
+            return True
+        except Exception as exc:  # noqa: BLE001 -- any capture problem means: stay eager
+            sys.stderr.write("bench: CUDA-graph capture failed (%s: %s); staying on the eager path\n" % (type(exc).__name__, exc))
+            self.graph = None
+            try:
+                torch.cuda.synchronize(self.device)
+            except Exception:
+                pass
+            self.opt = torch.optim.Adam(self.model.parameters(), lr=1e-7)
+            return False
+
+    def replay(self):
+        self.graph.replay()
+        return self.graph_out
+
+    def release(self):
+        """Back to the eager path (the roofline and end-to-end passes launch kernel by kernel through the module API)."""
+        self.graph = None
+        self.graph_out = None
+        self.opt = torch.optim.Adam(self.model.parameters(), lr=1e-7)
+
     def step(self, x_s, x_t, gt):
         """One pass of the hot path; returns the tensor a user would read back."""
         from egaze import ops
@@ -437,6 +477,10 @@ def main():
     for _ in range(W):
         wl.step(*wl.dev)
     launches = count_launches(lambda: wl.step(*wl.dev))
+    graphed = False
+    if os.environ.get("EGAZE_BENCH_GRAPH", "1") == "1" and args.workload == "sp_train" and world == 1:
+        graphed = wl.capture()
+    run_step = (lambda: wl.replay()) if graphed else (lambda: wl.step(*wl.dev))
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -445,12 +489,14 @@ def main():
     e0.record()
     t_host = time.perf_counter()
     for _ in range(K):
-        wl.step(*wl.dev)
+        run_step()
     host_ms = (time.perf_counter() - t_host) * 1e3 / K   # time the host needs to ENQUEUE a step (no synchronisation inside)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1) / K
     clocks = sampler.finish() if sampler else None
+    if graphed:
+        wl.release()
 
     # ---- roofline pass: duration of every tcgen05 conv / wgrad launch ------------------------------------------------------
     # Same workload, same process, right after the timed region, with a CUDA-event pair around every launch on the stream
@@ -490,17 +536,33 @@ def main():
                 b.copy_(h, non_blocking=True)
             ready[i % 2].record(copy_stream)
 
+    # Every step's result is read back to the host inside the timed region -- one step LATE (the copy of step i's result is
+    # enqueued right behind it and the host waits for it after enqueueing step i+1; the last one before the timer stops),
+    # the way a training loop logs its loss without stalling the launch queue.
+    host_res = [None, None]
+    res_ready = [torch.cuda.Event() for _ in range(2)]
+
     def e2e_run(n):
         for ev in freed:
             ev.record()
         prefetch(0)
+        got = 0
         for i in range(n):
             torch.cuda.current_stream().wait_event(ready[i % 2])
             if i + 1 < n:
                 prefetch(i + 1)
-            res = wl.step(*bufs[i % 2])
+            res = wl.step(*bufs[i % 2]).detach()
             freed[i % 2].record()
-            res.detach().to("cpu", non_blocking=False)
+            if host_res[i % 2] is None or host_res[i % 2].shape != res.shape:
+                host_res[i % 2] = torch.empty(res.shape, dtype=res.dtype, pin_memory=True)
+            host_res[i % 2].copy_(res, non_blocking=True)
+            res_ready[i % 2].record()
+            if i > 0:
+                res_ready[(i - 1) % 2].synchronize()      # the host now holds step i-1's result
+                got += 1
+        res_ready[(n - 1) % 2].synchronize()
+        return got + 1
+
     e2e_run(2)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -548,10 +610,13 @@ def main():
         "dtype": "bf16x3-split (fp32 accumulate)" if ops.is_precise() else "bf16 (fp32 accumulate)", "data": "synthetic",
         "config": {"workload": args.workload, "batch_per_gpu": wl.B, "size": args.size, "global_batch": frames,
                    "precision_mode": ops.precision(), "parallelism": "dp%d" % world,
+                   "device_loop": "CUDA graph replay of the whole step" if graphed else "eager launches",
                    "l2": "per-step inputs+activations (>1 GB) exceed the 126 MB L2; no explicit flush"},
         "clocks": clocks,
         "e2e": {"value": frames / ms_e2e * 1e3, "unit": UNIT, "h2d_bytes_per_step": wl.h2d_bytes,
-                "d2h_bytes_per_step": wl.d2h_bytes},
+                "d2h_bytes_per_step": wl.d2h_bytes,
+                "note": "pinned host inputs prefetched one step ahead on a copy stream; every step's result copied to pinned "
+                        "host memory and awaited by the host one step later (the last one inside the timed region)"},
         "gpu_launches": launches * K, "host_enqueue_ms_per_step": host_ms,
         "roofline": roofline,
     }
