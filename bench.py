@@ -210,8 +210,8 @@ class Workload(object):
 
     def capture(self):
         """Capture one whole training step (forward, floss, backward on all three streams, Adam) on the resident inputs into a
-        CUDA graph; `replay()` then runs a step with no host work at all.  Only used for the device-resident throughput
-        loop of single-GPU `sp_train` (EGAZE_BENCH_GRAPH=0 turns it off); returns False -- and the caller stays on the eager
+        CUDA graph (under torchrun the NCCL gradient all-reduce is captured with it); `replay()` then runs a step with no host
+        work at all.  Only used for the device-resident throughput loop of `sp_train` (EGAZE_BENCH_GRAPH=0 turns it off); returns False -- and the caller stays on the eager
         path -- if anything in the capture fails."""
         try:
             self.opt = torch.optim.Adam(self.model.parameters(), lr=1e-7, capturable=True)
@@ -478,7 +478,7 @@ def main():
         wl.step(*wl.dev)
     launches = count_launches(lambda: wl.step(*wl.dev))
     graphed = False
-    if os.environ.get("EGAZE_BENCH_GRAPH", "1") == "1" and args.workload == "sp_train" and world == 1:
+    if os.environ.get("EGAZE_BENCH_GRAPH", "1") == "1" and args.workload == "sp_train":
         graphed = wl.capture()
     run_step = (lambda: wl.replay()) if graphed else (lambda: wl.step(*wl.dev))
     sampler = ClockSampler(local) if rank == 0 else None
