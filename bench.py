@@ -209,24 +209,14 @@ class Workload(object):
         self.flat = FlatGradBucket(self.model.parameters() if params is None else params, self.device)
 
     def capture(self):
-        """Capture one whole training step (forward, floss, backward on all three streams, Adam) on the resident inputs into a
-        CUDA graph (under torchrun the NCCL gradient all-reduce is captured with it); `replay()` then runs a step with no host
-        work at all.  Only used for the device-resident throughput loop of `sp_train` (EGAZE_BENCH_GRAPH=0 turns it off); returns False -- and the caller stays on the eager
-        path -- if anything in the capture fails."""
+        """Capture one whole training step (forward, floss, backward on all three streams, the NCCL gradient all-reduce
+        under torchrun, Adam) on the resident inputs into a CUDA graph (egaze.graph.GraphedStep); `replay()` then runs a
+        step with no host work at all.  Only used for the device-resident throughput loop of `sp_train`
+        (EGAZE_BENCH_GRAPH=0 turns it off); returns False -- and the caller stays on the eager path -- if the capture fails."""
+        from egaze.graph import GraphedStep
         try:
             self.opt = torch.optim.Adam(self.model.parameters(), lr=1e-7, capturable=True)
-            side = torch.cuda.Stream(device=self.device)
-            side.wait_stream(torch.cuda.current_stream(self.device))
-            with torch.cuda.stream(side):                      # warm-up on a side stream, as torch.cuda.graph requires
-                for _ in range(3):
-                    self.step(*self.dev)
-            torch.cuda.current_stream(self.device).wait_stream(side)
-            torch.cuda.synchronize(self.device)
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self.graph_out = self.step(*self.dev)
-            self.graph = g
-            torch.cuda.synchronize(self.device)
+            self.graph = GraphedStep(self.step, self.dev, optimizers=[self.opt], own_inputs=True, restore=False)
             return True
         except Exception as exc:  # noqa: BLE001 -- any capture problem means: stay eager
             sys.stderr.write("bench: CUDA-graph capture failed (%s: %s); staying on the eager path\n" % (type(exc).__name__, exc))
@@ -239,13 +229,11 @@ class Workload(object):
             return False
 
     def replay(self):
-        self.graph.replay()
-        return self.graph_out
+        return self.graph.replay()
 
     def release(self):
         """Back to the eager path (the roofline and end-to-end passes launch kernel by kernel through the module API)."""
         self.graph = None
-        self.graph_out = None
         self.opt = torch.optim.Adam(self.model.parameters(), lr=1e-7)
 
     def step(self, x_s, x_t, gt):

@@ -159,6 +159,12 @@ class _PackCache(object):
         self._d[key] = (weakref.ref(w), ver, w.data_ptr(), val)
         return val
 
+    def mark_stale(self):
+        """Forget that any packed copy is current: the next get() / refresh() re-packs it.  For weights that change without
+        their tensor version changing (an optimiser step replayed inside a CUDA graph, egaze/graph.py)."""
+        for key, ent in list(self._d.items()):
+            self._d[key] = (ent[0], -1, ent[2], ent[3])
+
     def refresh(self):
         """Re-pack, in ONE launch, every cached copy whose weight changed since it was packed (after an optimiser step that is
         all of them: 76 small launches per SP training step otherwise).  Copies of dead or re-allocated weights are dropped."""
