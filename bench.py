@@ -211,8 +211,8 @@ class Workload(object):
     def capture(self):
         """Capture one whole training step (forward, floss, backward on all three streams, the NCCL gradient all-reduce
         under torchrun, Adam) on the resident inputs into a CUDA graph (egaze.graph.GraphedStep); `replay()` then runs a
-        step with no host work at all.  Only used for the device-resident throughput loop of `sp_train`
-        (EGAZE_BENCH_GRAPH=0 turns it off); returns False -- and the caller stays on the eager path -- if the capture fails."""
+        step with no host work at all.  Used for the device-resident and the end-to-end loop of `sp_train`
+        (EGAZE_BENCH_GRAPH=0 turns it off: eager module calls in both); returns False -- and the caller stays on the eager path -- if the capture fails."""
         from egaze.graph import GraphedStep
         try:
             self.opt = torch.optim.Adam(self.model.parameters(), lr=1e-7, capturable=True)
@@ -230,11 +230,6 @@ class Workload(object):
 
     def replay(self):
         return self.graph.replay()
-
-    def release(self):
-        """Back to the eager path (the roofline and end-to-end passes launch kernel by kernel through the module API)."""
-        self.graph = None
-        self.opt = torch.optim.Adam(self.model.parameters(), lr=1e-7)
 
     def step(self, x_s, x_t, gt):
         """One pass of the hot path; returns the tensor a user would read back."""
@@ -483,8 +478,6 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1) / K
     clocks = sampler.finish() if sampler else None
-    if graphed:
-        wl.release()
 
     # ---- roofline pass: duration of every tcgen05 conv / wgrad launch ------------------------------------------------------
     # Same workload, same process, right after the timed region, with a CUDA-event pair around every launch on the stream
@@ -539,7 +532,8 @@ def main():
             torch.cuda.current_stream().wait_event(ready[i % 2])
             if i + 1 < n:
                 prefetch(i + 1)
-            res = wl.step(*bufs[i % 2]).detach()
+            # graphed: egaze.graph.GraphedStep.__call__ copies the batch into the graph's static inputs and replays the step
+            res = (wl.graph(*bufs[i % 2]) if graphed else wl.step(*bufs[i % 2])).detach()
             freed[i % 2].record()
             if host_res[i % 2] is None or host_res[i % 2].shape != res.shape:
                 host_res[i % 2] = torch.empty(res.shape, dtype=res.dtype, pin_memory=True)
@@ -603,6 +597,7 @@ def main():
         "clocks": clocks,
         "e2e": {"value": frames / ms_e2e * 1e3, "unit": UNIT, "h2d_bytes_per_step": wl.h2d_bytes,
                 "d2h_bytes_per_step": wl.d2h_bytes,
+                "call": "egaze.graph.GraphedStep (whole step replayed as one CUDA graph)" if graphed else "eager module calls",
                 "note": "pinned host inputs prefetched one step ahead on a copy stream; every step's result copied to pinned "
                         "host memory and awaited by the host one step later (the last one inside the timed region)"},
         "gpu_launches": launches * K, "host_enqueue_ms_per_step": host_ms,
