@@ -212,7 +212,8 @@ class Workload(object):
         """Capture one whole training step (forward, floss, backward on all three streams, the NCCL gradient all-reduce
         under torchrun, Adam) on the resident inputs into a CUDA graph (egaze.graph.GraphedStep); `replay()` then runs a
         step with no host work at all.  Used for the device-resident and the end-to-end loop of `sp_train`
-        (EGAZE_BENCH_GRAPH=0 turns it off: eager module calls in both); returns False -- and the caller stays on the eager path -- if the capture fails."""
+        (EGAZE_BENCH_GRAPH=0 turns it off: eager module calls in both); returns False -- and the caller stays on the eager
+        path -- if the capture fails."""
         from egaze.graph import GraphedStep
         try:
             self.opt = torch.optim.Adam(self.model.parameters(), lr=1e-7, capturable=True)
@@ -230,6 +231,19 @@ class Workload(object):
 
     def replay(self):
         return self.graph.replay()
+
+    def drop_graph(self):
+        """Destroy the captured graph (and its memory pool) and go back to the eager optimiser."""
+        import gc
+        torch.cuda.synchronize(self.device)
+        try:
+            self.graph.release()
+        except Exception as exc:  # noqa: BLE001 -- the measurements are taken; a failed clean-up must not lose them
+            sys.stderr.write("bench: releasing the CUDA graph failed (%s: %s)\n" % (type(exc).__name__, exc))
+        self.graph = None
+        self.opt = torch.optim.Adam(self.model.parameters(), lr=1e-7)
+        gc.collect()
+        torch.cuda.synchronize(self.device)
 
     def step(self, x_s, x_t, gt):
         """One pass of the hot path; returns the tensor a user would read back."""
@@ -399,10 +413,52 @@ def cpu_reference_fps(workload, B, S, steps, warmup, threads):
     return B / dt, dt, sample
 
 
+_json_out = [None]
+
+
+def claim_stdout():
+    """stdout carries the ONE JSON line and nothing else: keep a private handle on the real stdout and point fd 1 at
+    stderr, so whatever a library prints (NCCL's version banner, oneDNN / OpenMP chatter) cannot land next to the line."""
+    if _json_out[0] is None:
+        sys.stdout.flush()
+        real = os.dup(1)
+        os.dup2(2, 1)
+        _json_out[0] = os.fdopen(real, "w")
+    return _json_out[0]
+
+
+def emit(line):
+    out = claim_stdout()
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
+def finish(world):
+    """Tear the process group down without ever hanging the launcher: the line is out by now, so a teardown that does not
+    return within 30 s (an NCCL communicator that still has work or graphs attached) ends in a hard exit with status 0."""
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if world <= 1:
+        return
+    guard = threading.Timer(30.0, os._exit, (0,))
+    guard.daemon = True
+    guard.start()
+    try:
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        if torch.distributed.is_initialized():
+            torch.distributed.destroy_process_group()
+    except Exception as exc:  # noqa: BLE001
+        sys.stderr.write("bench: destroy_process_group: %s\n" % exc)
+    sys.stderr.flush()
+    os._exit(0)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    claim_stdout()
     threads = os.cpu_count() or 1
     B = args.ref_batch
     steps = max(1, min(args.steps, 3))
@@ -416,7 +472,7 @@ def run_reference(args):
                              "sample": "%s, %d step(s), torch %s CPU (oneDNN), %d threads" % (
                                  sample, steps, torch.__version__, threads)},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -437,14 +493,12 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    claim_stdout()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: the egaze path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
-        # keep stdout to the ONE JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
         torch.distributed.init_process_group("nccl", device_id=device)
     from egaze import _lib, ops
     W = max(args.warmup, 3)
@@ -553,15 +607,16 @@ def main():
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1) / K
+    if graphed:
+        wl.drop_graph()   # before any teardown: the graph holds the captured all-reduce of the NCCL communicator
+        barrier()
 
     t = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     ms, ms_e2e = t.tolist()
     if rank != 0:
-        if world > 1:
-            torch.distributed.destroy_process_group()
-        return
+        return finish(world)
 
     peaks, peak_src = load_peaks()
     frames = wl.B * world
@@ -609,9 +664,8 @@ def main():
         line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": "%s, 1 warm-up + 1 timed step, torch %s CPU (oneDNN), %d threads"
                                           % (sample, torch.__version__, threads)}
-    print(json.dumps(line))
-    if world > 1:
-        torch.distributed.destroy_process_group()
+    emit(line)
+    finish(world)
 
 
 if __name__ == "__main__":

@@ -105,8 +105,20 @@ class GraphedStep(object):
             s.copy_(t, non_blocking=True)
         return self.replay()
 
+    def release(self):
+        """Destroy the graph and give its memory pool back.  Do this before `destroy_process_group()` when the step contains
+        an NCCL collective: a communicator is not torn down while a graph that captured its work exists."""
+        if self.graph is not None:
+            torch.cuda.synchronize(self.device)
+            self.graph.reset()
+        self.graph = None
+        self.outputs = None
+        self.fn = None
+
     def replay(self):
         """Run the step on whatever the static inputs hold."""
+        if self.graph is None:
+            raise RuntimeError("GraphedStep: released")
         self.graph.replay()
         # the replayed optimiser changed the weights without touching their tensor versions: eager calls of the modules
         # after this must re-pack (the graph itself always does)

@@ -1,0 +1,55 @@
+"""bench.py's output contract on CPU: stdout carries exactly ONE JSON line (whatever libraries write to file descriptor 1
+goes to stderr), under torchrun only rank 0 prints, and the teardown ends with status 0."""
+import json
+import os
+import subprocess
+import sys
+import textwrap
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+_SCRIPT = textwrap.dedent('''
+    import os, sys
+    sys.path.insert(0, %r)
+    import torch, torch.distributed as dist
+    import bench
+    bench.claim_stdout()
+    os.write(1, b"library banner written straight to fd 1\\n")     # what NCCL's version banner does
+    print("python-level chatter")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        dist.init_process_group("gloo")
+        t = torch.ones(1) * (int(os.environ["RANK"]) + 1)
+        dist.all_reduce(t)
+    else:
+        t = torch.ones(1)
+    if int(os.environ.get("RANK", "0")) == 0:
+        bench.emit({"metric": "m", "value": float(t.item()), "n_gpus": world})
+    bench.finish(world)
+''') % ROOT
+
+
+def _run(cmd, tmp_path):
+    script = tmp_path / "emit.py"
+    script.write_text(_SCRIPT)
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    return subprocess.run(cmd + [str(script)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env, timeout=300, text=True)
+
+
+def test_single_process_stdout_is_one_json_line(tmp_path):
+    r = _run([sys.executable], tmp_path)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = r.stdout.splitlines()
+    assert len(lines) == 1, r.stdout
+    assert json.loads(lines[0]) == {"metric": "m", "value": 1.0, "n_gpus": 1}
+    assert "library banner" in r.stderr and "python-level chatter" in r.stderr
+
+
+def test_torchrun_world2_stdout_is_one_json_line(tmp_path):
+    port = 29600 + (os.getpid() % 1500)
+    r = _run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+              "--master-port", str(port)], tmp_path)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout
+    assert json.loads(lines[0]) == {"metric": "m", "value": 3.0, "n_gpus": 2}
