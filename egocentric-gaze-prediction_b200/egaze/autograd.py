@@ -13,7 +13,6 @@ Backward schedule per layer (reverse order):
 import os
 
 import torch
-import torch.nn as nn
 
 from . import engine, ops
 

@@ -4,7 +4,6 @@ Same attribute names / state_dict keys ('features.*', 'decoder.*'); `return_feat
 that also returns conv5_3 (run_spatialstream.py:49-53)."""
 import math
 
-import torch
 import torch.nn as nn
 
 from . import engine, ops, _lib

@@ -2,10 +2,9 @@
 (features_t before features_s), state_dict keys/shapes and forward signature; forward runs on the egaze engine."""
 import math
 
-import torch
 import torch.nn as nn
 
-from egaze import engine, ops, _lib
+from egaze import engine, _lib
 from egaze.modules import DecoderSequential, _needs_grad
 
 

@@ -4,7 +4,6 @@ mean over samples; BatchNorm-free model)."""
 import os
 import sys
 
-import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp

@@ -1,5 +1,5 @@
 """Quick device-timed probe of the SP forward (not the contract bench)."""
-import os, sys, time
+import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "egocentric-gaze-prediction_b200"))
 import torch
