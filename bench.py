@@ -127,9 +127,28 @@ class ClockSampler(threading.Thread):
 # --------------------------------------------------------------------------------------------------------------------
 # workloads
 # --------------------------------------------------------------------------------------------------------------------
+def synth_sp_inputs(B, S, seed=1234):
+    """The bench's synthetic batch: an RGB frame at normalised-image scale (data/STdatas.py:54-55), a
+    20-channel flow stack quantised to 256 levels in [-1, 1] (data/STdatas.py:66-68) and a min-max-normalised, 8-bit
+    quantised Gaussian gaze blob (data/dataset_preprocessing.py:113-119, data/STdatas.py:64,69-71).  Same numbers as the
+    generator the parity fixtures were made with (tests/test_bench_output.py checks that), kept here so that nothing under
+    oracle/ is on the measured path."""
+    rs = np.random.RandomState(seed)
+    x_s = rs.randn(B, 3, S, S).astype(np.float32)
+    x_t = ((rs.randint(0, 256, (B, 20, S, S)).astype(np.float32) / 255 - 0.5) / 0.5).astype(np.float32)
+    rows, cols = np.meshgrid(np.arange(S, dtype=np.float64), np.arange(S, dtype=np.float64), indexing='ij')
+    sig_r, sig_c = S * 16.3 / 224, S * 12.25 / 224
+    gt = np.empty((B, 1, S, S), np.float32)
+    for b in range(B):
+        cr, cc = (rs.rand(2) * 0.7 + 0.15) * S
+        blob = np.exp(-((rows - cr) ** 2 / (2 * sig_r ** 2) + (cols - cc) ** 2 / (2 * sig_c ** 2)))
+        blob = (blob - blob.min()) / (blob.max() - blob.min())
+        gt[b, 0] = np.round(blob * 255) / 255
+    return x_s, x_t, gt
+
+
 class Workload(object):
     def __init__(self, name, B, S, rank, world, device):
-        from oracle import egaze_oracle as orc  # synthetic-input generator only (no oracle compute on this path)
         from utils import make_layers, cfg
         from models.model_SP import model_SP
         from models.late_fusion import late_fusion
@@ -140,7 +159,7 @@ class Workload(object):
         from egaze.ddp import shard_seed
         self.model = model_SP(make_layers(cfg['D'], 3), make_layers(cfg['D'], 20)).to(device) if name != "at_seq" else None
         self.crit = floss_mod.floss()
-        x_s, x_t, gt = orc.synth_sp_inputs(B, S, shard_seed(1234, rank))
+        x_s, x_t, gt = synth_sp_inputs(B, S, shard_seed(1234, rank))
         self.host = [torch.from_numpy(a).pin_memory() for a in (x_s, x_t, gt)]
         self.dev = [t.to(device) for t in self.host]
         self.h2d_bytes = sum(t.numel() * 4 for t in self.host[:2]) + (self.host[2].numel() * 4 if name == "sp_train" else 0)
@@ -337,7 +356,7 @@ def cpu_reference_fps(workload, B, S, steps, warmup, threads):
     torch.set_num_threads(threads)
     torch.manual_seed(0)
     m = ref.ModelSP()
-    x_s, x_t, gt = [torch.from_numpy(a) for a in orc.synth_sp_inputs(B, S, 1234)]
+    x_s, x_t, gt = [torch.from_numpy(a) for a in synth_sp_inputs(B, S, 1234)]
     if workload == "at_seq":
         # BASELINE configs[2] the way AT.extract_late walks a video: frame by frame, batch = the 16 sequences
         T, NB = 30, 16

@@ -53,3 +53,15 @@ def test_torchrun_world2_stdout_is_one_json_line(tmp_path):
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1, r.stdout
     assert json.loads(lines[0]) == {"metric": "m", "value": 3.0, "n_gpus": 2}
+
+
+def test_bench_inputs_match_the_fixture_generator():
+    """bench.py carries its own synthetic-batch generator (nothing under oracle/ on the measured path); it must produce the
+    numbers the parity fixtures were generated from."""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import bench
+    from oracle import egaze_oracle as orc
+    for B, S, seed in ((2, 32, 1234), (1, 48, 7)):
+        for a, b in zip(bench.synth_sp_inputs(B, S, seed), orc.synth_sp_inputs(B, S, seed)):
+            assert a.dtype == b.dtype and np.array_equal(a, b)
