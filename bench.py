@@ -480,10 +480,13 @@ def run_reference(args):
     claim_stdout()
     threads = os.cpu_count() or 1
     B = args.ref_batch
-    steps = max(1, min(args.steps, 3))
-    fps, dt, sample = cpu_reference_fps(args.workload, B, args.size, steps, 1, threads)
+    # --steps / --warmup are honoured up to 10 / 2: each step is the bounded sample (batch 4 of the workload's 32 per GPU,
+    # under a second on the GPU box's host cores), so the whole arm stays within a minute
+    steps = max(1, min(args.steps, 10))
+    warmup = max(1, min(args.warmup, 2))
+    fps, dt, sample = cpu_reference_fps(args.workload, B, args.size, steps, warmup, threads)
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "batch_per_gpu": 32, "size": args.size,
                        "note": "reference CPU path timed on a bounded sample (%s) of the same workload" % sample},
@@ -679,10 +682,11 @@ def main():
     }
     if not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1
-        fps, dt, sample = cpu_reference_fps(args.workload, args.ref_batch, args.size, 1, 1, threads)
+        cpu_steps = 5   # ~5-10 s of CPU work on the GPU box's host (a batch-4 train step takes ~0.8 s on 16 threads)
+        fps, dt, sample = cpu_reference_fps(args.workload, args.ref_batch, args.size, cpu_steps, 1, threads)
         line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": "%s, 1 warm-up + 1 timed step, torch %s CPU (oneDNN), %d threads"
-                                          % (sample, torch.__version__, threads)}
+                                "sample": "%s, 1 warm-up + %d timed steps, torch %s CPU (oneDNN), %d threads"
+                                          % (sample, cpu_steps, torch.__version__, threads)}
     emit(line)
     finish(world)
 
