@@ -408,41 +408,36 @@ def vgg_with_grad(model, x):
 # late_fusion
 # ---------------------------------------------------------------------------------------------------------------------
 class _LateFusionFn(torch.autograd.Function):
+    """models/late_fusion.py forward + backward through the dedicated LF kernels (csrc/lf.cu): one C-ABI call each way."""
+
     @staticmethod
     def forward(ctx, model, f, g, *params):
-        ops.pack_cache.refresh()   # one launch re-packs every weight copy the optimiser step made stale
-        x = torch.cat((f, g), dim=1)
-        specs, head = engine.parse_sequential(model.fusion)
-        saved = []
-        act = ops.to_split(x, ops.pad_channels(2))
-        for sp in specs:
-            act = engine.run_conv_spec(act, sp, saved)
-        out = ops.head_fwd(act, head.weight, head.bias)
-        ctx.model, ctx.rec = model, (specs, saved, head, act, out)
+        out, saved = ops.lf_forward(model.fusion, f, g, keep=True)
+        ctx.model, ctx.saved = model, saved
         ctx.need_x = (f.requires_grad, g.requires_grad)
         return out
 
     @staticmethod
     def backward(ctx, gout):
         model = ctx.model
-        specs, saved, head, head_in, out = ctx.rec
+        convs, bns = ops.lf_parts(model.fusion)
+        r = ops.lf_backward(model.fusion, ctx.saved, gout, need_w=tuple(_req(c.weight) for c in convs),
+                            need_f=ctx.need_x[0], need_g=ctx.need_x[1])
         bag = _GradBag()
-        # the head's input is ReLU(BN(conv)): its dx (ReLU-masked) is the gradient w.r.t. the BN output; bn_bwd applies the
-        # same mask again (idempotent)
-        gact, dw, db = ops.head_bwd(head_in, head.weight, out, gout, relu_mask=True)
-        bag.put(head.weight, dw)
-        bag.put(head.bias, db)
-        g = ops.from_split_nhwc(gact)
-        need_x = any(ctx.need_x)
-        gx = bn_sequential_backward(specs, saved, g, bag, need_x)
-        gf = gg = None
-        if gx is not None and need_x:
-            gx = ops.nhwc_f32_to_nchw(gx, 2)
-            gf = gx[:, 0:1].contiguous() if ctx.need_x[0] else None
-            gg = gx[:, 1:2].contiguous() if ctx.need_x[1] else None
-        ctx.rec = None
-        _join_side_stream()
-        return (None, gf, gg) + _ret_grads(bag, _params(model))
+        for i, c in enumerate(convs):
+            if r["dw"][i] is not None:
+                bag.put(c.weight, r["dw"][i])
+        for i, bn in enumerate(bns):
+            bag.put(bn.weight, r["dgamma"][i][:bn.num_features])
+            bag.put(bn.bias, r["dbeta"][i][:bn.num_features])
+            if _req(convs[i].bias):
+                if ctx.saved[7]:   # feeds a batch-statistics BatchNorm: exactly zero (SURVEY App. D)
+                    bag.put(convs[i].bias, torch.zeros_like(convs[i].bias))
+                else:              # running statistics: d(raw) = scale * gz, so sum d(raw) = scale * dbeta
+                    bag.put(convs[i].bias, ctx.saved[5][i, 2, :bn.num_features] * r["dbeta"][i][:bn.num_features])
+        bag.put(convs[3].bias, r["dbh"])
+        ctx.saved = None
+        return (None, r["gf"], r["gg"]) + _ret_grads(bag, _params(model))
 
 
 def late_fusion_with_grad(model, f, g):

@@ -424,6 +424,99 @@ def head_bwd(act, w, y, gy, relu_mask=True):
     return dx, dw, db
 
 
+# ---- late fusion (models/late_fusion.py) ----------------------------------------------------------------------------
+_lf_scratch = {}
+
+
+def _lf_scratch_buf(dev, which):
+    """Per (device, stream) scratch for the LF kernels' per-CTA partials (sizes from egaze_lf_scratch)."""
+    key = (dev, stream_ptr(), which)
+    buf = _lf_scratch.get(key)
+    if buf is None:
+        a, b = ctypes.c_int(0), ctypes.c_int(0)
+        call("egaze_lf_scratch", ctypes.addressof(a), ctypes.addressof(b))
+        buf = _lf_scratch[key] = torch.empty((a.value if which == 0 else b.value,), dtype=F32, device=dev)
+    return buf
+
+
+def _ptr_array(tensors):
+    return (ctypes.c_void_p * len(tensors))(*[None if t is None else t.data_ptr() for t in tensors])
+
+
+def lf_parts(seq):
+    """The parameter containers of late_fusion.fusion (models/late_fusion.py:10-14): 3 x (Conv2d 3x3, BatchNorm2d) + Conv2d 1x1."""
+    mods = list(seq.children())
+    convs = [m for m in mods if isinstance(m, torch.nn.Conv2d)]
+    bns = [m for m in mods if isinstance(m, torch.nn.BatchNorm2d)]
+    shapes = [tuple(c.weight.shape) for c in convs]
+    if shapes != [(32, 2, 3, 3), (32, 32, 3, 3), (8, 32, 3, 3), (1, 8, 1, 1)] or len(bns) != 3:
+        raise RuntimeError("egaze: late_fusion kernels are specialised for the reference's 2->32->32->8->1 net, got %r" % (shapes,))
+    if any(c.padding != ((1, 1) if c.kernel_size == (3, 3) else (0, 0)) or c.stride != (1, 1) for c in convs):
+        raise RuntimeError("egaze: late_fusion convs must be stride 1, 'same' padding")
+    if len({(bn.eps, bn.momentum) for bn in bns}) != 1 or bns[0].momentum is None or any(not bn.affine for bn in bns):
+        raise RuntimeError("egaze: late_fusion BatchNorm layers must share eps / momentum and be affine")
+    return convs, bns
+
+
+def lf_forward(seq, f, g, keep=False, precise=None):
+    """late_fusion.forward (models/late_fusion.py:18-23) in one C-ABI call.  -> (out [B,1,H,W], saved | None)."""
+    convs, bns = lf_parts(seq)
+    precise = is_precise() if precise is None else precise
+    f = f.detach().contiguous().float()
+    g = g.detach().contiguous().float()
+    if f.shape != g.shape or f.dim() != 4 or f.shape[1] != 1:
+        raise RuntimeError("egaze: late_fusion expects two (B,1,H,W) maps, got %s and %s" % (tuple(f.shape), tuple(g.shape)))
+    B, _, H, W = f.shape
+    dev = f.device
+    batch_stats = [bn.training or (bn.running_mean is None and bn.running_var is None) for bn in bns]
+    if len(set(batch_stats)) != 1:
+        raise RuntimeError("egaze: late_fusion BatchNorm layers must all be in the same mode")
+    training = batch_stats[0]
+    raw1 = torch.empty((B, H, W, 32), dtype=F32, device=dev)
+    raw2 = torch.empty((B, H, W, 32), dtype=F32, device=dev)
+    raw3 = torch.empty((B, H, W, 8), dtype=F32, device=dev) if (training or keep) else None
+    bn_ws = torch.empty((3, 4, 32), dtype=F32, device=dev)
+    out = torch.empty((B, 1, H, W), dtype=F32, device=dev)
+    ws = [c.weight.detach() for c in convs]
+    bs = [c.bias.detach() if c.bias is not None else None for c in convs]
+    gam = [bn.weight.detach() for bn in bns]
+    bet = [bn.bias.detach() for bn in bns]
+    rms = [bn.running_mean if bn.track_running_stats else None for bn in bns]
+    rvs = [bn.running_var if bn.track_running_stats else None for bn in bns]
+    for t in ws + gam + bet + [x for x in bs + rms + rvs if x is not None]:
+        if not (t.is_cuda and t.is_contiguous() and t.dtype == F32):
+            raise RuntimeError("egaze: late_fusion parameters must be contiguous fp32 CUDA tensors")
+    call("egaze_lf_fwd", f, g, B, H, W, _ptr_array(ws), _ptr_array(bs), _ptr_array(gam), _ptr_array(bet), _ptr_array(rms),
+         _ptr_array(rvs), int(training), float(bns[0].eps), float(bns[0].momentum), raw1, raw2, raw3, bn_ws,
+         _lf_scratch_buf(dev, 0), out, int(precise), stream_ptr())
+    if training:
+        for bn in bns:
+            if bn.track_running_stats and bn.num_batches_tracked is not None:
+                bn.num_batches_tracked.add_(1)
+    saved = (f, g, raw1, raw2, raw3, bn_ws, out, training, precise) if keep else None
+    return out, saved
+
+
+def lf_backward(seq, saved, gout, need_w=(True, True, True, True), need_f=False, need_g=False):
+    """Backward of lf_forward.  -> dict(dw=[4], dbh, dgamma=[3], dbeta=[3], gf, gg)."""
+    convs, bns = lf_parts(seq)
+    f, g, raw1, raw2, raw3, bn_ws, out, training, precise = saved
+    B, _, H, W = f.shape
+    dev = f.device
+    new = lambda *shape: torch.empty(shape, dtype=F32, device=dev)
+    g1, g2 = new(B, H, W, 32), new(B, H, W, 32)
+    dw = [torch.empty_like(c.weight) if need else None for c, need in zip(convs, need_w)]
+    dbh = new(1)
+    dgamma, dbeta = [new(32), new(32), new(8)], [new(32), new(32), new(8)]
+    gf = new(B, 1, H, W) if need_f else None
+    gg = new(B, 1, H, W) if need_g else None
+    ws = [c.weight.detach() for c in convs]
+    call("egaze_lf_bwd", f, g, B, H, W, _ptr_array(ws), raw1, raw2, raw3, bn_ws, int(training), out,
+         gout.detach().contiguous().float(), g1, g2, _lf_scratch_buf(dev, 1), _ptr_array(dw), dbh, _ptr_array(dgamma),
+         _ptr_array(dbeta), gf, gg, int(precise), stream_ptr())
+    return dict(dw=dw, dbh=dbh, dgamma=dgamma, dbeta=dbeta, gf=gf, gg=gg)
+
+
 # ---- floss -------------------------------------------------------------------------------------------------------
 def floss_centroid(target):
     B, H, W = target.shape[0], target.shape[-2], target.shape[-1]

@@ -1,12 +1,12 @@
 """Drop-in for the reference's models/late_fusion.py: same attributes (`upsample`, `fusion`, `final`), state_dict
-and forward(f, g) signature.  The three 3x3 convs run on the same tcgen05 kernel as the SP stack (channels padded
-to 16/32 inside the packed weights), BatchNorm/ReLU fused as in the trunks, 1x1 + sigmoid in the HBM-bound head."""
+and forward(f, g) signature.  The whole net runs through the dedicated late-fusion kernels (egaze_lf_fwd / egaze_lf_bwd,
+csrc/lf.cu): BatchNorm affine + ReLU applied while the next conv stages its window, statistics in the conv epilogues."""
 import math
 
 import torch
 import torch.nn as nn
 
-from egaze import engine, ops, _lib
+from egaze import ops, _lib
 from egaze.modules import _needs_grad
 
 
@@ -27,10 +27,7 @@ class late_fusion(nn.Module):
         if _needs_grad(self, f, g):
             from egaze.autograd import late_fusion_with_grad
             return late_fusion_with_grad(self, f, g)
-        x = torch.cat((f, g), dim=1)  # (B,2,H,W): channel order (f, g) as in late_fusion.py:20
-        act = ops.to_split(x, ops.pad_channels(2))
-        act, tail = engine.run_sequential(self.fusion, act)
-        return ops.head_fwd(act, tail.weight, tail.bias)
+        return ops.lf_forward(self.fusion, f, g)[0]  # channel order (f, g) as in late_fusion.py:20
 
     def _initialize_weights(self):
         for m in self.modules():

@@ -103,6 +103,31 @@ int egaze_head_fwd(const void* x_hi, const void* x_lo, const float* w, const flo
 int egaze_head_bwd(const void* x_hi, const void* x_lo, const float* w, int C, int Cs, long long P, const float* y,
                    const float* gy, int relu_mask, void* dx_hi, void* dx_lo, float* dw, float* db, void* stream);
 
+/* ---- late fusion (models/late_fusion.py:6-23): cat(f, g) -> [conv3x3 + BN + ReLU] x3 (2->32->32->8) -> conv1x1 -> sigmoid ---
+ * One call runs the whole network (csrc/lf.cu: warp-level tensor-core kernels with the BatchNorm affine + ReLU applied while
+ * the next layer stages its input window, batch statistics in the conv epilogues).  All pointers are device pointers;
+ * w / b / gamma / beta / run_mean / run_var / dw / dgamma / dbeta are HOST arrays of device pointers:
+ *   w[4]  = fusion.{0,3,6,9}.weight (OIHW fp32: 32x2x3x3, 32x32x3x3, 8x32x3x3, 1x8x1x1), b[4] the biases (entries may be null)
+ *   gamma[3], beta[3], run_mean[3], run_var[3] = fusion.{1,4,7}.* (run_mean / run_var may be null in training mode)
+ * training != 0: batch statistics (running statistics updated exactly like nn.BatchNorm2d); 0: running statistics.
+ * Workspaces (caller-allocated fp32): raw1, raw2 [B][H][W][32], raw3 [B][H][W][8] (raw conv outputs, kept for the backward;
+ * raw3 may be null in eval mode), bn_ws [3][4][32] (per layer: mean, invstd, scale, shift -- outputs), scratch
+ * (egaze_lf_scratch floats).  out: [B][1][H][W].  precise != 0: split bf16, 3 MMAs per product. */
+int egaze_lf_scratch(int* fwd_floats, int* bwd_floats);
+int egaze_lf_fwd(const float* f, const float* g, int B, int H, int W, const float* const* w, const float* const* b,
+                 const float* const* gamma, const float* const* beta, float* const* run_mean, float* const* run_var,
+                 int training, float eps, float momentum, float* raw1, float* raw2, float* raw3, float* bn_ws,
+                 float* scratch, float* out, int precise, void* stream);
+/* Backward of egaze_lf_fwd (loss.backward() in LF.py:98).  gout: gradient w.r.t. out.  g1, g2: [B][H][W][32] fp32 workspaces
+ * (gradients w.r.t. the post-ReLU activations of layers 1 and 2).  dw[4]: OIHW gradients written directly (null entry = skip
+ * that weight gradient); dbh [1]; dgamma[3] / dbeta[3]: BatchNorm parameter gradients (required: they are also the two sums
+ * the BatchNorm backward needs).  gf / gg: optional [B][1][H][W] gradients of the inputs.  batch_stats = the `training` flag
+ * of the forward.  Conv biases feeding a batch-statistics BatchNorm have an exactly-zero gradient (not computed here). */
+int egaze_lf_bwd(const float* f, const float* g, int B, int H, int W, const float* const* w, const float* raw1,
+                 const float* raw2, const float* raw3, const float* bn_ws, int batch_stats, const float* out,
+                 const float* gout, float* g1, float* g2, float* scratch, float* const* dw, float* dbh,
+                 float* const* dgamma, float* const* dbeta, float* gf, float* gg, int precise, void* stream);
+
 /* ---- floss (floss.py:9-41) ----------------------------------------------------------------------------------- */
 int egaze_floss_centroid(const float* target, int B, int H, int W, double* centroid, void* stream);
 int egaze_floss_weight(const double* centroid, int B, int H, int W, float* weights, void* stream);
