@@ -4,16 +4,18 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload sp_train|sp_fwd|pipeline_fwd|full_train|at_seq]
                     [--impl reference]
 
-Metric (BASELINE.json): SP(+AT+LF) gaze-map frames/s at 224x224, batch 32 per GPU.  One "step" = one pass of the hot
-path over one synthetic batch: `sp_train` = model_SP two-stream forward + floss + backward +
-Adam step (BASELINE configs[1], the default); `sp_fwd` = eval-mode two-stream forward; `pipeline_fwd` = SP forward -> AT
-step -> LF forward (gaze-map inference); `full_train` = BASELINE configs[3] per rank: SP train step, AT step on the hooked
-conv5_3 map, LF train step on (AT map, SP map) with floss; `at_seq` = BASELINE configs[2]: crop-mean -> 2-layer LSTM ->
+Metric (BASELINE.json): SP+AT+LF gaze-map frames/s at 224x224, batch 32 per GPU.  One "step" = one pass of the hot
+path over one synthetic batch.  `full_train` (the default: BASELINE configs[3] per rank, the configuration the
+metric is quoted on) = SP two-stream train step (forward + floss + backward + Adam), AT step on the hooked conv5_3 map, LF
+train step on (AT map, SP map) with floss + Adam; `sp_train` = the SP part alone (BASELINE configs[1]); `sp_fwd` = eval-mode
+two-stream forward; `pipeline_fwd` = SP forward -> AT step -> LF forward (gaze-map inference); `at_seq` = BASELINE configs[2]: crop-mean -> 2-layer LSTM ->
 channel-weighted map over 16 feature sequences of 30 steps (a "frame" is one sequence step).  N > 1 ranks (torchrun) shard frames: weak scaling, B=32 per rank, one NCCL
 allreduce of the weight gradients per training step and no collective for inference.
 
-Prints ONE JSON line (rank 0).  `value` = device-resident throughput; `e2e` = same metric through the public module
-API with HOST (pinned) inputs and a host read of the result inside the timed region.
+Prints ONE JSON line (rank 0).  `value` = device-resident throughput; `e2e` = same metric through the public API
+(egaze.graph.GraphedStep over the drop-in modules) with HOST (pinned) inputs and a host read of the result inside the timed
+region; `e2e_dropin` = the reference's own loop bodies (SP.py:125-142, AT.py:224-248, LF.py:86-99) written out literally over
+the drop-in modules: eager launches, blocking `.to(device)` copies, every `loss.item()` the reference calls.
 """
 import argparse
 import contextlib
@@ -33,8 +35,20 @@ for _p in (PKG, ROOT):
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-METRIC = "SP+AT+LF gaze-map frames/sec at 224x224 b32"
+# one metric string per workload: the line must say what was timed
+METRICS = {
+    "full_train": "SP+AT+LF gaze-map frames/sec at 224x224 b32 (train step: SP fwd/bwd + AT step + LF fwd/bwd, BASELINE configs[3])",
+    "sp_train": "SP two-stream gaze-map frames/sec at 224x224 b32 (train step: fwd + floss + bwd + Adam, BASELINE configs[1])",
+    "sp_fwd": "SP two-stream gaze-map frames/sec at 224x224 b32 (eval forward)",
+    "pipeline_fwd": "SP+AT+LF gaze-map frames/sec at 224x224 b32 (inference: SP fwd -> AT step -> LF fwd)",
+    "at_seq": "AT sequence-steps/sec over 512x14x14 feature sequences, seq_len 30, batch 16 (BASELINE configs[2])",
+}
 UNIT = "frames/s"
+
+
+def metric_name(workload, B=32, S=224):
+    m = METRICS[workload]
+    return m if (B, S) == (32, 224) else m.replace("224x224 b32", "%dx%d b%d" % (S, S, B))
 # algorithmic FLOPs per frame (SURVEY 8d / BASELINE.md 4): 2 FLOP per MAC of the reference's direct convolutions
 FLOP_SP_FWD = 114.167e9
 FLOP_SP_TRAIN = 341.171e9
@@ -166,7 +180,7 @@ class Workload(object):
         self.flat = None
         if name == "sp_train":
             self.model.train()
-            self.opt = torch.optim.Adam(self.model.parameters(), lr=1e-7)  # gaze_full.py:11 default lr, SP.py:113
+            self._make_optimizers(False)
             self.flop = FLOP_SP_TRAIN
             self.d2h_bytes = 4
             if world > 1:
@@ -190,8 +204,7 @@ class Workload(object):
             self.model.train()
             self.lstm = lstmnet().to(device).eval()
             self.lf = late_fusion().to(device).train()
-            self.opt = torch.optim.Adam(self.model.parameters(), lr=1e-7)
-            self.opt_lf = torch.optim.Adam(self.lf.parameters(), lr=1e-7)
+            self._make_optimizers(False)
             self.lf_stream = torch.cuda.Stream(device=device)
             self.feats = []
             self.model._modules.get('features_s').register_forward_hook(lambda m, i, o: self.feats.append(o))  # AT.py:105
@@ -227,16 +240,22 @@ class Workload(object):
             broadcast_parameters(self.lf, 0)
         self.flat = FlatGradBucket(self.model.parameters() if params is None else params, self.device)
 
+    def _make_optimizers(self, capturable):
+        kw = {"capturable": True} if capturable else {}
+        self.opt = torch.optim.Adam(self.model.parameters(), lr=1e-7, **kw)   # gaze_full.py:11 default lr, SP.py:113
+        if self.name == "full_train":
+            self.opt_lf = torch.optim.Adam(self.lf.parameters(), lr=1e-7, **kw)  # LF.py:77
+
     def capture(self):
-        """Capture one whole training step (forward, floss, backward on all three streams, the NCCL gradient all-reduce
-        under torchrun, Adam) on the resident inputs into a CUDA graph (egaze.graph.GraphedStep); `replay()` then runs a
-        step with no host work at all.  Used for the device-resident and the end-to-end loop of `sp_train`
-        (EGAZE_BENCH_GRAPH=0 turns it off: eager module calls in both); returns False -- and the caller stays on the eager
-        path -- if the capture fails."""
+        """Capture one whole training step (forward, floss, backward on all streams, the AT step and the LF train step on
+        their side stream, the NCCL gradient all-reduce under torchrun, the Adam steps) on the resident inputs into a CUDA
+        graph (egaze.graph.GraphedStep); `replay()` then runs a step with no host work at all.  EGAZE_BENCH_GRAPH=0 turns it
+        off (eager module calls everywhere); returns False -- and the caller stays on the eager path -- if the capture fails."""
         from egaze.graph import GraphedStep
         try:
-            self.opt = torch.optim.Adam(self.model.parameters(), lr=1e-7, capturable=True)
-            self.graph = GraphedStep(self.step, self.dev, optimizers=[self.opt], own_inputs=True, restore=False)
+            self._make_optimizers(True)
+            opts = [self.opt] + ([self.opt_lf] if self.name == "full_train" else [])
+            self.graph = GraphedStep(self.step, self.dev, optimizers=opts, own_inputs=True, restore=False)
             return True
         except Exception as exc:  # noqa: BLE001 -- any capture problem means: stay eager
             sys.stderr.write("bench: CUDA-graph capture failed (%s: %s); staying on the eager path\n" % (type(exc).__name__, exc))
@@ -245,14 +264,14 @@ class Workload(object):
                 torch.cuda.synchronize(self.device)
             except Exception:
                 pass
-            self.opt = torch.optim.Adam(self.model.parameters(), lr=1e-7)
+            self._make_optimizers(False)
             return False
 
     def replay(self):
         return self.graph.replay()
 
     def drop_graph(self):
-        """Destroy the captured graph (and its memory pool) and go back to the eager optimiser."""
+        """Destroy the captured graph (and its memory pool) and go back to the eager optimisers."""
         import gc
         torch.cuda.synchronize(self.device)
         try:
@@ -260,9 +279,51 @@ class Workload(object):
         except Exception as exc:  # noqa: BLE001 -- the measurements are taken; a failed clean-up must not lose them
             sys.stderr.write("bench: releasing the CUDA graph failed (%s: %s)\n" % (type(exc).__name__, exc))
         self.graph = None
-        self.opt = torch.optim.Adam(self.model.parameters(), lr=1e-7)
+        self._make_optimizers(False)
         gc.collect()
         torch.cuda.synchronize(self.device)
+
+    def dropin_step(self, sample):
+        """The reference's loop bodies written out literally over the drop-in modules: SP.trainSP (SP.py:126-142) and, for
+        `full_train`, the AT step of AT.extract_late (AT.py:224-248, on the device) and LF.trainLate (LF.py:86-99, without its
+        per-batch scipy metric).  `sample` holds HOST tensors as a DataLoader yields them.  Returns the number of host syncs."""
+        from egaze import ops
+        input_s = sample['image']
+        target = sample['gt']
+        input_t = sample['flow']
+        input_s = input_s.float().to(self.device)
+        input_t = input_t.float().to(self.device)
+        target = target.float().to(self.device)
+        if self.name == "full_train":
+            self.feats.clear()
+        output = self.model(input_s, input_t)
+        target = target.view(output.size())
+        loss = self.crit(output, target)
+        self.loss_mini_batch = loss.item()
+        loss.backward()
+        if self.flat is not None:
+            self.flat.allreduce()
+        self.opt.step()
+        self.opt.zero_grad()
+        self.loss_avg = loss.item()
+        if self.name != "full_train":
+            return 2
+        with torch.no_grad():
+            feature_s = self.feats[0]
+            chn_weight = ops.crop_mean(feature_s, self.gaze, 3)
+            chn_weight, hidden = self.lstm(chn_weight.unsqueeze(0), self.hidden)
+            for dst, src in zip(self.hidden, hidden):
+                dst.copy_(src)
+            feat = ops.bilinear_up(ops.weighted_map(chn_weight.squeeze(0), feature_s).unsqueeze(1), 16, False)
+        out = self.lf(feat, output.detach())
+        loss = self.crit(out, target)
+        self.loss_lf_avg = loss.item()
+        self.opt_lf.zero_grad()
+        loss.backward()
+        if self.flat is not None:
+            self.flat.allreduce()
+        self.opt_lf.step()
+        return 3
 
     def step(self, x_s, x_t, gt):
         """One pass of the hot path; returns the tensor a user would read back."""
@@ -302,7 +363,8 @@ class Workload(object):
                     feat = self.feats[0]
                     vec = ops.crop_mean(feat, self.gaze, 3)
                     w, hidden = self.lstm(vec.unsqueeze(0), self.hidden)
-                    self.hidden = tuple(h.detach() for h in hidden)
+                    for dst, src in zip(self.hidden, hidden):   # the state stays in the same buffers (CUDA-graph replay)
+                        dst.copy_(src)
                     amap = ops.weighted_map(w.squeeze(0), feat)
                     up = ops.bilinear_up(amap.unsqueeze(1), 16, False)
                 fused = self.lf(up, out.detach())                              # LF.py:90
@@ -473,11 +535,19 @@ def finish(world):
     os._exit(0)
 
 
+def common_config(args, world):
+    """The part of `config` both arms share (the reference arm times a bounded sample of this same workload)."""
+    return {"workload": args.workload, "batch_per_gpu": args.batch, "size": args.size, "global_batch": args.batch * world,
+            "parallelism": "dp%d" % world,
+            "l2": "per-step inputs+activations (>1 GB) exceed the 126 MB L2; no explicit flush"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     claim_stdout()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     threads = os.cpu_count() or 1
     B = args.ref_batch
     # --steps / --warmup are honoured up to 10 / 2: each step is the bounded sample (batch 4 of the workload's 32 per GPU,
@@ -485,11 +555,13 @@ def run_reference(args):
     steps = max(1, min(args.steps, 10))
     warmup = max(1, min(args.warmup, 2))
     fps, dt, sample = cpu_reference_fps(args.workload, B, args.size, steps, warmup, threads)
-    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+    line = {"impl": "reference", "metric": metric_name(args.workload, args.batch, args.size), "value": fps, "unit": UNIT,
+            "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "batch_per_gpu": 32, "size": args.size,
-                       "note": "reference CPU path timed on a bounded sample (%s) of the same workload" % sample},
+            "config": common_config(args, max(world, args.gpus)),
+            "detail": {"note": "reference CPU path (stock torch.nn modules, oneDNN) timed on ONE process on a bounded sample "
+                               "(%s) of the same workload" % sample},
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": "%s, %d step(s), torch %s CPU (oneDNN), %d threads" % (
                                  sample, steps, torch.__version__, threads)},
@@ -502,12 +574,13 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default=os.environ.get("EGAZE_BENCH_WORKLOAD", "sp_train"))
+    ap.add_argument("--workload", default=os.environ.get("EGAZE_BENCH_WORKLOAD", "full_train"), choices=sorted(METRICS))
     ap.add_argument("--impl", default="egaze")
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--size", type=int, default=224)
     ap.add_argument("--ref-batch", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dropin", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -526,6 +599,7 @@ def main():
     W = max(args.warmup, 3)
     K = args.steps
     wl = Workload(args.workload, args.batch, args.size, rank, world, device)
+    training = args.workload in ("sp_train", "full_train")
 
     def barrier():
         if world > 1:
@@ -537,9 +611,11 @@ def main():
         wl.step(*wl.dev)
     launches = count_launches(lambda: wl.step(*wl.dev))
     graphed = False
-    if os.environ.get("EGAZE_BENCH_GRAPH", "1") == "1" and args.workload == "sp_train":
+    if os.environ.get("EGAZE_BENCH_GRAPH", "1") == "1" and training:
         graphed = wl.capture()
     run_step = (lambda: wl.replay()) if graphed else (lambda: wl.step(*wl.dev))
+    for _ in range(2):
+        run_step()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -554,29 +630,6 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1) / K
     clocks = sampler.finish() if sampler else None
-
-    # ---- roofline pass: duration of every tcgen05 conv / wgrad launch ------------------------------------------------------
-    # Same workload, same process, right after the timed region, with a CUDA-event pair around every launch on the stream
-    # it is launched on.  The weight-gradient GEMMs normally run on a second stream and overlap other kernels (their event
-    # intervals then overlap too and the sum double-counts time), and so do the two trunks; this pass keeps everything on one
-    # stream: each number is the kernel's own duration inside a long step.
-    R = max(1, min(K, 5))
-    knobs = ("EGAZE_WGRAD_STREAM", "EGAZE_TRUNK_STREAM")
-    prev = {k: os.environ.get(k) for k in knobs}
-    for k in knobs:
-        os.environ[k] = "0"
-    wl.step(*wl.dev)
-    ops.conv_timer_reset(True)
-    for _ in range(R):
-        wl.step(*wl.dev)
-    conv_ms, conv_launches = ops.conv_timer_read()   # summed over the R steps
-    ops.conv_timer_reset(False)
-    for k in knobs:
-        if prev[k] is None:
-            os.environ.pop(k, None)
-        else:
-            os.environ[k] = prev[k]
-    barrier()
 
     # ---- end to end: host (pinned) inputs in, result read back, every step -----------------------------------------------
     # What a data loader does: the H2D copy of batch i+1 runs on a copy stream while batch i computes (double-buffered
@@ -633,10 +686,47 @@ def main():
         wl.drop_graph()   # before any teardown: the graph holds the captured all-reduce of the NCCL communicator
         barrier()
 
-    t = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
+    # ---- the reference's own loop bodies over the drop-in modules (eager launches, blocking copies, loss.item() syncs) ------
+    ms_dropin, dropin_syncs, dropin_host_ms = None, 0, None
+    if training and not args.no_dropin:
+        sample = {"image": wl.host[0], "flow": wl.host[1], "gt": wl.host[2]}
+        for _ in range(2):
+            wl.dropin_step(sample)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            dropin_syncs = wl.dropin_step(sample)
+        torch.cuda.synchronize()
+        ms_dropin = (time.perf_counter() - t0) * 1e3 / K   # every step ends in a host sync: wall clock == device time
+        barrier()
+
+    # ---- roofline pass: duration of every tcgen05 conv / wgrad launch ------------------------------------------------------
+    # Same workload, same process, with a CUDA-event pair around every launch on the stream it is launched on.  The
+    # weight-gradient GEMMs normally run on a second stream and overlap other kernels (their event intervals then overlap too
+    # and the sum double-counts time), and so do the two trunks; this pass keeps everything on one stream: each number is the
+    # kernel's own duration inside a long step.
+    R = max(1, min(K, 5))
+    knobs = ("EGAZE_WGRAD_STREAM", "EGAZE_TRUNK_STREAM", "EGAZE_BENCH_LF_STREAM")
+    prev = {k: os.environ.get(k) for k in knobs}
+    for k in knobs:
+        os.environ[k] = "0"
+    wl.step(*wl.dev)
+    ops.conv_timer_reset(True)
+    for _ in range(R):
+        wl.step(*wl.dev)
+    conv_ms, conv_launches = ops.conv_timer_read()   # summed over the R steps
+    ops.conv_timer_reset(False)
+    for k in knobs:
+        if prev[k] is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = prev[k]
+    barrier()
+
+    t = torch.tensor([ms, ms_e2e, ms_dropin or 0.0], device=device, dtype=torch.float64)
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    ms, ms_e2e = t.tolist()
+    ms, ms_e2e, ms_dropin_max = t.tolist()
     if rank != 0:
         return finish(world)
 
@@ -656,21 +746,25 @@ def main():
                     "frac": alg_bytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "peak_source": "%s hbm_gbs" % peak_src,
                     "note": "achieved = algorithmic bytes / whole-step time (the step is 3 C-ABI calls)", "traffic": None}
     else:
-        roofline = {"bound": "tensor", "kernel": "tcgen05 conv kernels (conv3x3_tc fprop/dgrad + wgrad_tc launches of the step)",
+        roofline = {"bound": "tensor", "kernel": "tcgen05 conv kernels (conv3x3_tc fprop/dgrad + wgrad_tc launches of the SP step)",
                     "achieved": conv_tflops, "peak": peak_tf, "unit": "TFLOP/s", "frac": conv_tflops / peak_tf,
                     "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step)" % peak_src,
                     "launches_per_step": conv_launches / max(R, 1), "kernel_ms_per_step": conv_ms / max(R, 1),
-                    "measured": "CUDA events around every launch, %d steps right after the timed region, single-stream order" % R,
+                    "algorithmic_tflop_per_step": conv_flop_step / 1e12,
+                    "measured": "CUDA events around every launch, %d steps after the timed regions, single-stream order" % R,
                     "step_tflops": wl.flop * args.batch / (ms * 1e-3) / 1e12,
                     "traffic": traffic}
+    cfg = common_config(args, world)
+    cfg["batch_per_gpu"] = wl.B
+    cfg["global_batch"] = frames
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms,
+        "metric": metric_name(args.workload, args.batch, args.size), "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
+        "warmup": W, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16x3-split (fp32 accumulate)" if ops.is_precise() else "bf16 (fp32 accumulate)", "data": "synthetic",
-        "config": {"workload": args.workload, "batch_per_gpu": wl.B, "size": args.size, "global_batch": frames,
-                   "precision_mode": ops.precision(), "parallelism": "dp%d" % world,
-                   "device_loop": "CUDA graph replay of the whole step" if graphed else "eager launches",
-                   "l2": "per-step inputs+activations (>1 GB) exceed the 126 MB L2; no explicit flush"},
+        "dtype": ops.dtype_string(), "data": "synthetic",
+        "config": cfg,
+        "detail": {"precision_mode": ops.precision(),
+                   "device_loop": "CUDA graph replay of the whole step" if graphed else "eager launches"},
         "clocks": clocks,
         "e2e": {"value": frames / ms_e2e * 1e3, "unit": UNIT, "h2d_bytes_per_step": wl.h2d_bytes,
                 "d2h_bytes_per_step": wl.d2h_bytes,
@@ -680,6 +774,13 @@ def main():
         "gpu_launches": launches * K, "host_enqueue_ms_per_step": host_ms,
         "roofline": roofline,
     }
+    if ms_dropin is not None:
+        line["e2e_dropin"] = {"value": frames / ms_dropin_max * 1e3, "unit": UNIT, "ms_per_step": ms_dropin_max,
+                              "h2d_bytes_per_step": wl.h2d_bytes, "d2h_bytes_per_step": 4 * dropin_syncs,
+                              "host_syncs_per_step": dropin_syncs,
+                              "call": "the reference's loop bodies verbatim over the drop-in modules (SP.py:126-142"
+                                      + (", AT.py:224-248, LF.py:86-99" if args.workload == "full_train" else "")
+                                      + "): eager launches, blocking .to(device) copies from pinned memory, every loss.item()"}
     if not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1
         cpu_steps = 5   # ~5-10 s of CPU work on the GPU box's host (a batch-4 train step takes ~0.8 s on 16 threads)

@@ -152,10 +152,9 @@ extern "C" int egaze_weighted_map(const float* feat_nchw, const float* chn_weigh
   EGAZE_CHECK_ARG(feat_nchw && chn_weight && out && B > 0, "weighted_map: bad args");
   EGAZE_CHECK_ARG(C % 4 == 0 && HW <= 8192, "weighted_map: unsupported C=%d HW=%d", C, HW);
   const size_t smem = ((size_t)4 * HW + 64) * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr = 0;
+  if (egaze_first_on_device(&attr)) {
     EGAZE_CUDA(cudaFuncSetAttribute(weighted_map_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr = true;
   }
   weighted_map_kernel<<<B, 1024, smem, (cudaStream_t)stream>>>(feat_nchw, chn_weight, C, HW, out);
   EGAZE_LAUNCH_CHECK();

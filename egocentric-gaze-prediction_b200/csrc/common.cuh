@@ -47,6 +47,17 @@ void egaze_set_error(const char* fmt, ...);
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// One-time per-DEVICE setup (cudaFuncSetAttribute is per device and one process may drive several GPUs, e.g. the reference's
+// `--device N` without torch.cuda.set_device): true the first time it is called on the current device for this mask.
+static inline bool egaze_first_on_device(unsigned long long* mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return true;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (*mask & bit) return false;
+  *mask |= bit;
+  return true;
+}
+
 // ---------------------------------------------------------------------------------------------
 // split-bf16 helpers: x ~= hi + lo with hi = bf16(x), lo = bf16(x - hi)  (16 mantissa bits)
 // ---------------------------------------------------------------------------------------------

@@ -1136,11 +1136,10 @@ extern "C" int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* 
   const int ksteps = p.KC / 16;
 #define EGAZE_CONV_LAUNCH(NS, KS, C)                                                                                  \
   do {                                                                                                                \
-    static bool attr_set = false;                                                                                     \
-    if (!attr_set) {                                                                                                  \
+    static unsigned long long attr_set = 0;                                                                           \
+    if (egaze_first_on_device(&attr_set)) {                                                                           \
       EGAZE_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<NS, KS, C>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
                                       224 * 1024));                                                                   \
-      attr_set = true;                                                                                                \
     }                                                                                                                 \
     EGAZE_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<NS, KS, C>, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p));            \
   } while (0)

@@ -613,10 +613,9 @@ int launch_conv(const ConvArgs& a, int grid, cudaStream_t st) {
   constexpr int STRIDE = CP * 2 + 16;
   constexpr int NROWS = ((NOUT + 7) / 8) * 8;
   const size_t smem = 2 * (size_t)(WH * WW * STRIDE) + 2 * (size_t)(9 * NROWS * STRIDE);
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr = 0;
+  if (egaze_first_on_device(&attr)) {
     EGAZE_CUDA(cudaFuncSetAttribute(lf_conv_kernel<KIND, C, CP, NOUT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
   }
   lf_conv_kernel<KIND, C, CP, NOUT, EPI><<<grid, kConvThreads, smem, st>>>(a);
   EGAZE_LAUNCH_CHECK();
@@ -626,10 +625,9 @@ int launch_conv(const ConvArgs& a, int grid, cudaStream_t st) {
 template <int KY, int CY, int CPY, int KX, int CX, int CPX>
 int launch_wgrad(const WgArgs& a, int grid, cudaStream_t st) {
   const size_t smem = 2 * (size_t)(TH * TW * (CPY * 2 + 16)) + 2 * (size_t)(WH * WW * (CPX * 2 + 16));
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr = 0;
+  if (egaze_first_on_device(&attr)) {
     EGAZE_CUDA(cudaFuncSetAttribute(lf_wgrad_kernel<KY, CY, CPY, KX, CX, CPX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
   }
   lf_wgrad_kernel<KY, CY, CPY, KX, CX, CPX><<<grid, kWgradThreads, smem, st>>>(a);
   EGAZE_LAUNCH_CHECK();

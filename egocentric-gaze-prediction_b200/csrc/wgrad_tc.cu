@@ -281,17 +281,15 @@ extern "C" int egaze_wgrad3x3_tc(const void* x_hi, const void* x_lo, const void*
   }
   dim3 grid((unsigned)ksplit, (unsigned)jobs);
   if (precise) {
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr = 0;
+    if (egaze_first_on_device(&attr)) {
       EGAZE_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-      attr = true;
     }
     wgrad_tc_kernel<2><<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmY_hi, tmY_lo, tmX_hi, tmX_lo, p);
   } else {
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr = 0;
+    if (egaze_first_on_device(&attr)) {
       EGAZE_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-      attr = true;
     }
     wgrad_tc_kernel<1><<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmY_hi, tmY_lo, tmX_hi, tmX_lo, p);
   }

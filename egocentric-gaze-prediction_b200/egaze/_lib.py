@@ -70,16 +70,28 @@ def last_error():
     return buf.value.decode(errors="replace")
 
 
-def _arg(a):
-    if a is None:
-        return None
-    if isinstance(a, torch.Tensor):
-        if not a.is_cuda:
-            raise RuntimeError("egaze: expected a CUDA tensor (no CPU fallback), got device %s" % a.device)
-        if not a.is_contiguous():
-            raise RuntimeError("egaze: non-contiguous tensor passed to the C-ABI")
-        return a.data_ptr()
-    return a
+class _CurrentStream(object):
+    """Placeholder for "the current stream of the device the call's tensors live on": resolved inside call()."""
+    __slots__ = ()
+
+
+STREAM = _CurrentStream()
+
+
+def _raw_stream(dev_idx):
+    """cudaStream_t of PyTorch's current stream on device dev_idx, as an integer.  (The public torch.cuda.current_stream()
+    costs ~10 us per call -- several ms of host time per training step at ~300 launches.)"""
+    try:
+        return torch._C._cuda_getCurrentRawStream(dev_idx)
+    except AttributeError:  # private API moved: fall back to the public one
+        return torch.cuda.current_stream(dev_idx).cuda_stream
+
+
+def _cur_device():
+    try:
+        return torch._C._cuda_getDevice()
+    except AttributeError:
+        return torch.cuda.current_device()
 
 
 # kernels launched per C-ABI call (bench.py's `gpu_launches` claim); entries not listed launch nothing
@@ -94,9 +106,38 @@ def launch_counter():
 
 
 def call(name, *args):
+    """Invoke one C-ABI entry point.  The library launches on the CUDA runtime's CURRENT device, so the call runs under a
+    device guard for the device its tensors live on (the reference puts models on `cuda:N` without torch.cuda.set_device,
+    gaze_full.py:37-38), and the stream argument is that device's current PyTorch stream.  Tensors on different devices, CPU
+    tensors and non-contiguous tensors are errors (no fallback)."""
     global _launch_count
     fn = getattr(lib(), name)
-    rc = fn(*[_arg(a) for a in args])
+    dev = None
+    cargs = []
+    for a in args:
+        if isinstance(a, torch.Tensor):
+            if not a.is_cuda:
+                raise RuntimeError("egaze: expected a CUDA tensor (no CPU fallback), got device %s" % a.device)
+            if not a.is_contiguous():
+                raise RuntimeError("egaze: non-contiguous tensor passed to the C-ABI")
+            if dev is None:
+                dev = a.device.index
+            elif a.device.index != dev:
+                raise RuntimeError("egaze: %s got tensors on cuda:%d and cuda:%d" % (name, dev, a.device.index))
+            cargs.append(a.data_ptr())
+        else:
+            cargs.append(a)
+    cur = _cur_device()
+    if dev is None:
+        dev = cur
+    for i, a in enumerate(cargs):
+        if a is STREAM:
+            cargs[i] = _raw_stream(dev)
+    if dev != cur:
+        with torch.cuda.device(dev):
+            rc = fn(*cargs)
+    else:
+        rc = fn(*cargs)
     if name == "egaze_lstm_seq_fwd":
         _launch_count += int(args[9]) + 2  # T+1 wavefront launches (layer 0 at t | layer 1 at t-1) + one Linear over all steps
     elif name == "egaze_lstm_seq_bwd":
@@ -108,23 +149,32 @@ def call(name, *args):
 
 
 def stream_ptr():
-    """cudaStream_t of PyTorch's current stream on the current device, as an integer for the C-ABI.  (The public
-    torch.cuda.current_stream() costs ~10 us per call -- several ms of host time per training step at ~300 launches.)"""
-    try:
-        return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
-    except AttributeError:  # private API moved: fall back to the public one
-        return torch.cuda.current_stream().cuda_stream
+    """The stream argument of a C-ABI call: resolved by call() to the current PyTorch stream of the tensors' device."""
+    return STREAM
+
+
+def stream_key(device=None):
+    """Integer identity of the current stream on `device` (for per-stream scratch buffers)."""
+    idx = _cur_device() if device is None else torch.device(device).index
+    return _raw_stream(_cur_device() if idx is None else idx)
 
 
 _checked = set()
 
 
 def check_device(device=None):
-    """Fail loudly unless the current device is a B200-class (sm_100) GPU."""
+    """Fail loudly unless `device` (default: the current device) is a B200-class (sm_100) GPU."""
     if not torch.cuda.is_available():
         raise RuntimeError("egaze: CUDA device required (hand-written sm_100a kernels, no CPU fallback)")
-    idx = torch.cuda.current_device() if device is None else torch.device(device).index
+    if device is None:
+        idx = _cur_device()
+    else:
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("egaze: expected a CUDA tensor (no CPU fallback), got device %s" % device)
+        idx = _cur_device() if device.index is None else device.index
     if idx in _checked:
         return
-    call("egaze_check_device")
+    with torch.cuda.device(idx):
+        call("egaze_check_device")
     _checked.add(idx)

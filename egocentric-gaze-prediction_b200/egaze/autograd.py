@@ -32,9 +32,28 @@ def _use_side_stream():
     return os.environ.get("EGAZE_WGRAD_STREAM", "1") != "0"
 
 
+def _emu(name):
+    """Experiment knobs (tools/grad_modes.py): emulate a cheaper backward numerically with the existing kernels."""
+    return os.environ.get(name, "0") == "1"
+
+
+def _hi_only(act):
+    return ops.Act(act.hi, torch.zeros_like(act.lo), act.C) if (act.lo is not None and _emu("EGAZE_EMU_DGRAD_HI")) else act
+
+
 def _wgrad(x_act, dy_act, cout, cin):
+    if _emu("EGAZE_EMU_WGRAD_1PASS"):
+        wg = lambda a, b, c, d: ops.wgrad3x3(a, b, c, d, precise=False)
+    elif _emu("EGAZE_EMU_WGRAD_XHI"):
+        wg = lambda a, b, c, d: ops.wgrad3x3(ops.Act(a.hi, torch.zeros_like(a.lo), a.C), b, c, d)
+    else:
+        wg = ops.wgrad3x3
+    return _wgrad_impl(wg, x_act, dy_act, cout, cin)
+
+
+def _wgrad_impl(wg, x_act, dy_act, cout, cin):
     if not _use_side_stream():
-        return ops.wgrad3x3(x_act, dy_act, cout, cin)
+        return wg(x_act, dy_act, cout, cin)
     dev = x_act.hi.device
     side = _side_streams.get(dev)
     if side is None:
@@ -42,7 +61,7 @@ def _wgrad(x_act, dy_act, cout, cin):
     main = torch.cuda.current_stream(dev)
     side.wait_stream(main)                      # the operands were produced on the main stream
     with torch.cuda.stream(side):
-        gw = ops.wgrad3x3(x_act, dy_act, cout, cin)
+        gw = wg(x_act, dy_act, cout, cin)
     for t in (x_act.hi, x_act.lo, dy_act.hi, dy_act.lo):
         if t is not None:
             t.record_stream(side)               # the caching allocator must not recycle them while the side stream reads
@@ -92,7 +111,7 @@ def _dgrad(conv, gpre_act, **kw):
     cin = conv.in_channels
     rows_p = ops.pad_channels(cin) if cin % 16 else cin
     wpack = ops.pack_cache.get(conv.weight, 1, rows_p=rows_p, cols_p=gpre_act.Cp)
-    return ops.conv3x3(gpre_act, wpack, **kw)
+    return ops.conv3x3(_hi_only(gpre_act), wpack, **kw)
 
 
 def _first_cp(conv):
@@ -291,7 +310,7 @@ class _ModelSPFn(torch.autograd.Function):
                 bag.put(fus.bias, torch.zeros_like(fus.bias))  # feeds model_SP.bn in batch-stat mode: exactly zero
             if trunk_need:
                 wpack = ops.pack_cache.get(fus.weight, 1, cols_p=d2.Cp)
-                _, gf, _ = ops.conv3x3(d2, wpack, want_f32=True, want_split=False)
+                _, gf, _ = ops.conv3x3(_hi_only(d2), wpack, want_f32=True, want_split=False)
                 B = gf.shape[0] // 2
                 g_s, g_t = gf[:B], gf[B:]
                 ts = _trunk_stream(gf.device)

@@ -80,6 +80,8 @@ class GraphedStep(object):
         torch.cuda.synchronize(self.device)
         self.graph = graph
         self.outputs = out
+        # device tables a captured multi-weight re-pack launch reads (their addresses are baked into the graph)
+        self._held = ops.pack_cache.held_tables()
 
         if restore:
             with torch.no_grad():
@@ -114,6 +116,7 @@ class GraphedStep(object):
         self.graph = None
         self.outputs = None
         self.fn = None
+        self._held = None
 
     def replay(self):
         """Run the step on whatever the static inputs hold."""

@@ -26,6 +26,13 @@ def is_precise():
     return precision() == "precise"
 
 
+def dtype_string():
+    """What bench.py reports as `dtype`: the arithmetic type of the tensor-core contractions, MMAs per product included."""
+    if is_precise():
+        return "bf16 split hi+lo operands, 3 MMAs per product (fwd, dgrad, wgrad), fp32 accumulate"
+    return "bf16, 1 MMA per product, fp32 accumulate"
+
+
 def pad_channels(c):
     """Channel padding of the K dimension: multiples of 64 when >= 64, else 16/32/48."""
     if c % 64 == 0:
@@ -159,6 +166,11 @@ class _PackCache(object):
         self._d[key] = (weakref.ref(w), ver, w.data_ptr(), val)
         return val
 
+    def held_tables(self):
+        """Every job table currently alive (egaze/graph.py keeps the list next to a captured graph so that the memory a
+        captured re-pack launch reads can never be recycled while the graph exists)."""
+        return list(self._tables.values())
+
     def mark_stale(self):
         """Forget that any packed copy is current: the next get() / refresh() re-packs it.  For weights that change without
         their tensor version changing (an optimiser step replayed inside a CUDA graph, egaze/graph.py)."""
@@ -188,8 +200,14 @@ class _PackCache(object):
             for i, (key, ent, w, Co, Ci, rows) in enumerate(stale):
                 hi, lo, rp, cp = ent[3]
                 rec[i] = (w.data_ptr(), hi.data_ptr(), lo.data_ptr(), Co | (Ci << 32), rows | (cp << 32), key[1])
-            self._tables.clear()
+            # Tables are never freed behind a CUDA graph's back: a captured egaze_pack_w3x3_multi launch has this table's
+            # address baked in.  Old tables age out of a small LRU; graphs keep their own references (held_tables()).
+            while len(self._tables) >= 16:
+                self._tables.pop(next(iter(self._tables)))
             table = self._tables[tkey] = torch.from_numpy(rec).to(stale[0][2].device)
+        else:
+            self._tables[tkey] = self._tables.pop(tkey)   # most recently used last
+        self._last_table = table
         call("egaze_pack_w3x3_multi", table, len(stale), stream_ptr())
         for key, ent, w, _, _, _ in stale:
             self._d[key] = (ent[0], w._version, ent[2], ent[3])
@@ -355,7 +373,9 @@ def wgrad3x3(x_act, dy_act, Cout, Cin, precise=None):
     N, H, W = x_act.N, x_act.H, x_act.W
     dev = x_act.hi.device
     # persistent accumulator per shape: allocated zeroed once, left zeroed again by egaze_unpack_wgrad (clear=1)
-    key = (dy_act.Cp, x_act.Cp, dev)
+    # (keyed by stream too: two streams -- the two trunks of model_SP have identical layer shapes -- must never accumulate
+    # into the same buffer concurrently)
+    key = (dy_act.Cp, x_act.Cp, dev, _lib.stream_key(dev))
     dwp = _dwp_cache.get(key)
     if dwp is None:
         dwp = _dwp_cache[key] = torch.zeros((9, dy_act.Cp, x_act.Cp), dtype=F32, device=dev)
@@ -430,7 +450,7 @@ _lf_scratch = {}
 
 def _lf_scratch_buf(dev, which):
     """Per (device, stream) scratch for the LF kernels' per-CTA partials (sizes from egaze_lf_scratch)."""
-    key = (dev, stream_ptr(), which)
+    key = (dev, _lib.stream_key(dev), which)
     buf = _lf_scratch.get(key)
     if buf is None:
         a, b = ctypes.c_int(0), ctypes.c_int(0)

@@ -65,3 +65,26 @@ def test_bench_inputs_match_the_fixture_generator():
     for B, S, seed in ((2, 32, 1234), (1, 48, 7)):
         for a, b in zip(bench.synth_sp_inputs(B, S, seed), orc.synth_sp_inputs(B, S, seed)):
             assert a.dtype == b.dtype and np.array_equal(a, b)
+
+
+def test_metric_string_names_the_workload_that_is_timed():
+    """the JSON line must be labelled with what was measured.  The default workload is the one BASELINE.json's metric
+    is quoted on (SP+AT+LF, configs[3]); every other workload carries its own metric string."""
+    sys.path.insert(0, ROOT)
+    import bench
+    assert "SP+AT+LF" in bench.METRICS["full_train"] and "train" in bench.METRICS["full_train"]
+    assert "SP+AT+LF" not in bench.METRICS["sp_train"] and "SP+AT+LF" not in bench.METRICS["sp_fwd"]
+    assert len(set(bench.METRICS.values())) == len(bench.METRICS)
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    env.pop("EGAZE_BENCH_WORKLOAD", None)
+    for extra, workload in (([], "full_train"), (["--workload", "sp_train"], "sp_train")):
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                            "--ref-batch", "1", "--size", "32"] + extra, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env,
+                           timeout=600, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+        assert len(lines) == 1, r.stdout
+        line = json.loads(lines[0])
+        assert line["impl"] == "reference" and line["config"]["workload"] == workload
+        assert line["metric"] == bench.metric_name(workload, 32, 32)
+        assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0

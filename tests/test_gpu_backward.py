@@ -275,8 +275,9 @@ def test_multi_stream_schedule_matches_single_stream(cuda_dev):
     gradients are summed with fp32 atomics, so to rounding) as the single-stream schedule; repeated to catch ordering bugs."""
     import floss as floss_mod
 
-    def run(streams):
-        os.environ["EGAZE_WGRAD_STREAM"] = os.environ["EGAZE_TRUNK_STREAM"] = "1" if streams else "0"
+    def run(wgrad_stream, trunk_stream):
+        os.environ["EGAZE_WGRAD_STREAM"] = "1" if wgrad_stream else "0"
+        os.environ["EGAZE_TRUNK_STREAM"] = "1" if trunk_stream else "0"
         try:
             m, _ = _sp_pair(cuda_dev, 0, 0.8)
             x_s, x_t, gt = [torch.from_numpy(a).to(cuda_dev) for a in orc.synth_sp_inputs(4, 64, 5)]
@@ -289,9 +290,12 @@ def test_multi_stream_schedule_matches_single_stream(cuda_dev):
             os.environ.pop("EGAZE_WGRAD_STREAM", None)
             os.environ.pop("EGAZE_TRUNK_STREAM", None)
 
-    ref_out, ref_grads = run(False)
-    for _ in range(3):
-        out, grads = run(True)
-        assert torch.equal(out, ref_out)
-        for g, r in zip(grads, ref_grads):
-            assert rel_l2(g, r) <= 1e-5 or (g - r).abs().max().item() <= 1e-9
+    ref_out, ref_grads = run(False, False)
+    # both on (default), and the mixed settings: with the weight-gradient stream off and the trunk stream on, the two trunks
+    # (identical layer shapes) run their weight gradients concurrently -- each stream must own its accumulators
+    for knobs in ((True, True), (False, True), (True, False)):
+        for _ in range(3):
+            out, grads = run(*knobs)
+            assert torch.equal(out, ref_out), knobs
+            for g, r in zip(grads, ref_grads):
+                assert rel_l2(g, r) <= 1e-5 or (g - r).abs().max().item() <= 1e-9, knobs
