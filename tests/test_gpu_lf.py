@@ -36,7 +36,9 @@ def test_lf_forward_shapes(cuda_dev, shape, train):
         got = m(f, a)
         ref = torch_ref.late_fusion_forward(m64, f.double(), a.double())
     assert got.shape == (B, 1, H, W)
-    assert (got.double() - ref).abs().max().item() <= 2e-4, (got.double() - ref).abs().max().item()
+    err = (got.double() - ref).abs().max().item()
+    print('lf fwd %s train=%s max-abs err vs fp64 %.2e' % (shape, train, err))
+    assert err <= 5e-4, err
     if train:
         sd, sr = m.state_dict(), m64.state_dict()
         for k in sd:
@@ -77,9 +79,10 @@ def test_lf_backward_vs_fp64_autograd(cuda_dev, shape):
             # bias in front of a batch-statistics BatchNorm: exactly zero here, rounding noise in stock autograd
             assert p.grad.abs().max().item() == 0.0 and q.grad.abs().max().item() <= 1e-8 * max(1.0, loss64.item()), k
             continue
-        assert rel_l2(p.grad, q.grad) <= 2e-3, "%s: %.3e" % (k, rel_l2(p.grad, q.grad))
-    assert rel_l2(f.grad, f64.grad) <= 2e-3, rel_l2(f.grad, f64.grad)
-    assert rel_l2(a.grad, a64.grad) <= 2e-3, rel_l2(a.grad, a64.grad)
+        print("lf grad %s %s rel-L2 vs fp64 %.2e" % (shape, k, rel_l2(p.grad, q.grad)))
+        assert rel_l2(p.grad, q.grad) <= 5e-3, "%s: %.3e" % (k, rel_l2(p.grad, q.grad))
+    assert rel_l2(f.grad, f64.grad) <= 5e-3, rel_l2(f.grad, f64.grad)
+    assert rel_l2(a.grad, a64.grad) <= 5e-3, rel_l2(a.grad, a64.grad)
 
 
 def test_lf_frozen_weights_and_determinism(cuda_dev):
@@ -113,5 +116,5 @@ def test_lf_eval_mode_backward(cuda_dev):
     f64 = f.detach().double().requires_grad_(True)
     (torch_ref.late_fusion_forward(m64, f64, a.double()) * wgt.double()).sum().backward()
     for (k, p), (_, q) in zip(m.named_parameters(), m64.named_parameters()):
-        assert rel_l2(p.grad, q.grad) <= 2e-3, "%s: %.3e" % (k, rel_l2(p.grad, q.grad))
-    assert rel_l2(f.grad, f64.grad) <= 2e-3
+        assert rel_l2(p.grad, q.grad) <= 5e-3, "%s: %.3e" % (k, rel_l2(p.grad, q.grad))
+    assert rel_l2(f.grad, f64.grad) <= 5e-3

@@ -3,7 +3,7 @@
 # sp_train beside it, backward-precision experiment.      usage: tools/gpu_r2a.sh <tag>
 TAG=${1:-r02a}; OUT=gpurun_out/$TAG; mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/smi.txt 2>&1
-timeout 600 python -m pytest tests/test_gpu_lf.py -m gpu -x -q > $OUT/pytest_lf.log 2>&1; echo "pytest_lf exit $?" | tee -a $OUT/pytest_lf.log
+timeout 600 python -m pytest tests/test_gpu_lf.py -m gpu -q -s > $OUT/pytest_lf.log 2>&1; echo "pytest_lf exit $?" | tee -a $OUT/pytest_lf.log
 tail -15 $OUT/pytest_lf.log
 timeout 300 python tools/lf_bench.py > $OUT/lf_bench.txt 2>&1; cat $OUT/lf_bench.txt | tail -6
 timeout 1500 python -m pytest tests -m gpu -q > $OUT/pytest_gpu.log 2>&1; echo "pytest exit $?" | tee -a $OUT/pytest_gpu.log
