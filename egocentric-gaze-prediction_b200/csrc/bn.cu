@@ -103,7 +103,8 @@ __global__ void col_stats_kernel(const float* __restrict__ x, int rows, int C, i
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const float* __restrict__ x, int N, int H, int W, int C, const float* __restrict__ scale,
                 const float* __restrict__ shift, int relu, int pool, float* __restrict__ out_f32,
-                __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
+                __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, __nv_bfloat16* __restrict__ out_xb,
+                int fmt) {
   const int Ho = pool ? H / 2 : H, Wo = pool ? W / 2 : W;
   const int C4 = C / 4;
   const int tpp = C4 < 256 ? C4 : 256;               // threads per pixel
@@ -140,10 +141,12 @@ bn_apply_kernel(const float* __restrict__ x, int N, int H, int W, int C, const f
       if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = v;
       if (out_hi) {
         uint2 hi2, lo2;
-        split_bf16x4(v, hi2, lo2);
+        if (fmt) split_f16x4(v, hi2, lo2);
+        else split_bf16x4(v, hi2, lo2);
         *reinterpret_cast<uint2*>(out_hi + o) = hi2;
         if (out_lo) *reinterpret_cast<uint2*>(out_lo + o) = lo2;
       }
+      if (out_xb) *reinterpret_cast<uint2*>(out_xb + o) = pack_bf16x4(v);
     }
   }
 }
@@ -281,7 +284,7 @@ __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const float* __restrict__ raw, const float* __restrict__ g, int N, int H, int W, int C,
                     const float* __restrict__ scale, const float* __restrict__ shift,
                     const float* __restrict__ mean, const float* __restrict__ invstd,
-                    const float* __restrict__ dgamma, const float* __restrict__ dbeta, int pool, int relu,
+                    const float* __restrict__ dgamma, const float* __restrict__ dbeta, int pool, int relu, int batch_stats,
                     float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_hi,
                     __nv_bfloat16* __restrict__ out_lo) {
   const int Ho = pool ? H / 2 : H, Wo = pool ? W / 2 : W;
@@ -290,7 +293,8 @@ bn_bwd_apply_kernel(const float* __restrict__ raw, const float* __restrict__ g, 
   const int ppb = 256 / tpp;
   const int lane_c = threadIdx.x % tpp, pl = threadIdx.x / tpp;
   if (pl >= ppb) return;
-  const float inv_n = 1.f / (float)((size_t)N * H * W);
+  // running-statistics BatchNorm (eval mode): mean / variance do not depend on the batch, their terms vanish
+  const float inv_n = batch_stats ? 1.f / (float)((size_t)N * H * W) : 0.f;
   const uint32_t npix = (uint32_t)N * Ho * Wo;
   const size_t row_pitch = (size_t)W * C;
   const int np = pool ? 4 : 1;
@@ -342,9 +346,11 @@ __global__ void pairmax_bwd_kernel(const float* __restrict__ x, const float* __r
     const bool first = !(b > a);
     __nv_bfloat16 h, l;
     split_bf16(first ? gg : 0.f, h, l);
-    hi[i] = h; lo[i] = l;
+    hi[i] = h;
+    if (lo) lo[i] = l;
     split_bf16(first ? 0.f : gg, h, l);
-    hi[per_stream + i] = h; lo[per_stream + i] = l;
+    hi[per_stream + i] = h;
+    if (lo) lo[per_stream + i] = l;
   }
 }
 
@@ -409,7 +415,8 @@ extern "C" int egaze_col_stats(const float* x, long long rows, int C, float* par
 }
 
 extern "C" int egaze_bn_apply(const float* x, int N, int H, int W, int C, const float* scale, const float* shift,
-                              int relu, int pool, float* out_f32, void* out_hi, void* out_lo, void* stream) {
+                              int relu, int pool, float* out_f32, void* out_hi, void* out_lo, void* out_xb, int fmt,
+                              void* stream) {
   EGAZE_CHECK_ARG(x && scale && shift && (out_f32 || out_hi), "bn_apply: bad args");
   EGAZE_CHECK_ARG(C % 4 == 0, "bn_apply: C %% 4 != 0");
   EGAZE_CHECK_ARG(!pool || ((H | W) & 1) == 0, "bn_apply: pool needs even H, W");
@@ -418,7 +425,8 @@ extern "C" int egaze_bn_apply(const float* x, int N, int H, int W, int C, const 
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   bn_apply_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, N, H, W, C, scale, shift, relu, pool, out_f32,
-                                                           (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo);
+                                                           (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo,
+                                                           (__nv_bfloat16*)out_xb, fmt);
   EGAZE_LAUNCH_CHECK();
   return EGAZE_OK;
 }
@@ -465,22 +473,22 @@ extern "C" int egaze_bn_bwd_reduce(const float* raw, const float* g, int N, int 
 
 extern "C" int egaze_bn_bwd_apply(const float* raw, const float* g, int N, int H, int W, int C, const float* scale,
                                   const float* shift, const float* mean, const float* invstd, const float* dgamma,
-                                  const float* dbeta, int pool, int relu, float* out_f32, void* out_hi, void* out_lo,
-                                  void* stream) {
+                                  const float* dbeta, int pool, int relu, int batch_stats, float* out_f32, void* out_hi,
+                                  void* out_lo, void* stream) {
   EGAZE_CHECK_ARG(raw && g && dgamma && dbeta && (out_f32 || out_hi), "bn_bwd_apply: null");
   const int Ho = pool ? H / 2 : H, Wo = pool ? W / 2 : W;
   const size_t total = (size_t)N * Ho * Wo * (C / 4);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   bn_bwd_apply_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(raw, g, N, H, W, C, scale, shift, mean, invstd, dgamma,
-                                                               dbeta, pool, relu, out_f32, (__nv_bfloat16*)out_hi,
+                                                               dbeta, pool, relu, batch_stats, out_f32, (__nv_bfloat16*)out_hi,
                                                                (__nv_bfloat16*)out_lo);
   EGAZE_LAUNCH_CHECK();
   return EGAZE_OK;
 }
 
 extern "C" int egaze_pairmax_bwd(const float* x, const float* g, long long per_stream, void* hi, void* lo, void* stream) {
-  EGAZE_CHECK_ARG(x && g && hi && lo && per_stream > 0, "pairmax_bwd: bad args");
+  EGAZE_CHECK_ARG(x && g && hi && per_stream > 0, "pairmax_bwd: bad args");
   int blocks = (int)((per_stream + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   pairmax_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, g, (size_t)per_stream, (__nv_bfloat16*)hi,

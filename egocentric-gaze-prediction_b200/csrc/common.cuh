@@ -5,6 +5,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -79,6 +80,41 @@ __device__ __forceinline__ void split_bf16x4(const float4& v, uint2& hi2, uint2&
   hi2 = make_uint2(u01, u23);
   lo2 = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
 }
+
+// ---------------------------------------------------------------------------------------------
+// split-fp16 helpers: x ~= hi + lo with hi = fp16(x), lo = fp16(x - hi)  (22 significand bits while |x| >= 2^-3, an absolute
+// error <= 2^-25 below: fp16 subnormals are exact multiples of 2^-24).  |x| is clamped to the fp16 range (65504) first, so a
+// wild activation saturates instead of turning into inf / NaN.  Used by the FORWARD convolutions only (train-mode
+// BatchNorm needs >= 19 operand bits for the 1e-3 gate); gradients keep bf16, whose exponent range they need.
+// ---------------------------------------------------------------------------------------------
+constexpr float kF16Max = 65504.f;
+__device__ __forceinline__ void split_f16x4(const float4& v, uint2& hi2, uint2& lo2) {
+  const float x = fminf(fmaxf(v.x, -kF16Max), kF16Max), y = fminf(fmaxf(v.y, -kF16Max), kF16Max);
+  const float z = fminf(fmaxf(v.z, -kF16Max), kF16Max), w = fminf(fmaxf(v.w, -kF16Max), kF16Max);
+  const __half2 h01 = __floats2half2_rn(x, y), h23 = __floats2half2_rn(z, w);
+  const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+  const __half2 l01 = __floats2half2_rn(x - f01.x, y - f01.y), l23 = __floats2half2_rn(z - f23.x, w - f23.y);
+  hi2 = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+  lo2 = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+}
+__device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
+  x = fminf(fmaxf(x, -kF16Max), kF16Max);
+  hi = __float2half_rn(x);
+  lo = __float2half_rn(x - __half2float(hi));
+}
+__device__ __forceinline__ float f16_bits_to_float(uint32_t bits16) {
+  return __half2float(__ushort_as_half((unsigned short)bits16));
+}
+// four fp32 -> four bf16 (round to nearest), packed for an 8-byte store
+__device__ __forceinline__ uint2 pack_bf16x4(const float4& v) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  return make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+}
+// value > 0 test on the raw 16 bits of a bf16 OR fp16 number (sign clear, not zero; NaN counts as positive in both formats,
+// which the ReLU masks never hold)
+__device__ __forceinline__ bool pos16(uint32_t bits16) { return bits16 != 0u && bits16 < 0x8000u; }
+// decode element `fmt` (0 = bf16, 1 = fp16) from its 16 bits
+__device__ __forceinline__ float dec16(uint32_t bits16, int fmt) { return fmt ? f16_bits_to_float(bits16) : bf16_bits_to_float(bits16); }
 
 // ---------------------------------------------------------------------------------------------
 // warp / block reductions
@@ -369,6 +405,11 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn, i
          | (1u << 7)            // A format BF16
          | (1u << 10)           // B format BF16
          | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// Same with FP16 operands (A / B format field 0); kind::f16 wants both operands in the same 16-bit format.
+__host__ __device__ constexpr uint32_t make_idesc_16(int M, int N, int a_mn, int b_mn, int f16) {
+  return (1u << 4) | (f16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {

@@ -54,7 +54,11 @@ struct ConvTcParams {
   int total_tiles;     // N * tiles_h * tiles_w
   int tile_groups;     // ceil(total_tiles / CS)
   int num_items;       // tile_groups * tiles_n
-  int nsplit;          // 1 = single bf16 pass, 2 = hi/lo split (3 MMAs per product)
+  int nsplit;          // planes of the WEIGHT operand: 1 = single pass, 2 = hi/lo split
+  int nsplit_a;        // planes of the ACTIVATION operand: 2 = hi/lo (3 MMAs per product with nsplit = 2), 1 = hi only
+                       //   (nsplit = 2: A_hi x [B_hi | B_lo], 2 MMAs per product -- the data-gradient mode)
+  int in_f16;          // operands are fp16 (1) or bf16 (0) bit patterns (kind::f16 needs A and B in the same format)
+  float acc_scale;     // accumulators are multiplied by this before anything else (fp16 weights are packed pre-scaled by 2^k)
   // How the hi/lo products are spread over TMEM accumulator blocks of BN columns (the epilogue adds the `nsum` blocks).
   // Back-to-back tcgen05.mma into the SAME accumulator columns serialise (+~43 cycles each, tools/probe_mma_rate.cu), so
   // consecutive MMAs always target different blocks:
@@ -84,8 +88,10 @@ struct ConvTcParams {
   const __nv_bfloat16* mask;  // optional NHWC [N,Ho,Wo,Cout]: zero the output where mask <= 0 (ReLU backward)
   int mask_ups;               // mask is stored 2x nearest-upsampled ([N,2Ho,2Wo,Cout]); read its (2oh,2ow) sample
   float* out_f32;             // optional NHWC fp32 [N,Ho*,Wo*,Cout]
-  __nv_bfloat16* out_hi;      // optional NHWC bf16
-  __nv_bfloat16* out_lo;      // optional (precise) NHWC bf16
+  __nv_bfloat16* out_hi;      // optional NHWC 16-bit plane: bf16(v) or fp16(v) (out_f16)
+  __nv_bfloat16* out_lo;      // optional NHWC 16-bit plane: the rounding residual v - hi in the same format
+  __nv_bfloat16* out_xb;      // optional NHWC bf16(v): the copy the weight-gradient GEMM reads when out_hi / out_lo are fp16
+  int out_f16;                // format of out_hi / out_lo
   float* stats;               // optional [gridDim][2][Cout] per-CTA (mean, M2) of the pre-activation (acc + bias)
   float* stats_cnt;           // [gridDim][tiles_n] pixel count behind each per-CTA partial
   float* colsum;              // optional [Cout]: += column sums of the stored values (bias gradient of the upstream conv)
@@ -146,7 +152,8 @@ __device__ __forceinline__ float4 epi_affine(float4 a, const float4& s, const fl
 // (K = 9*64 .. 9*128) are bound by exactly this loop, not by the MMAs.
 // STATS: also accumulate the BatchNorm sums of the raw accumulators, shifted by the per-channel reference k4:
 // s1 += a - k, s2 += (a - k)^2.
-template <int RED, bool MASK, bool UPS, bool F32, bool SPLIT, bool STATS = false>
+// OUTK: which 16-bit planes are written -- 0 none, 1 bf16 hi + lo, 2 fp16 hi + lo, 3 fp16 hi + lo + bf16 copy, 4 bf16 hi only.
+template <int RED, bool MASK, bool UPS, bool F32, int OUTK, bool STATS = false>
 __device__ __forceinline__ void epi_store(const ConvTcParams& p, const EpiTile& e, float4& cs, float4 k4 = float4(),
                                           float4* s1 = nullptr, float4* s2 = nullptr) {
   const int obw_mask = (1 << e.obw_log) - 1;
@@ -154,14 +161,17 @@ __device__ __forceinline__ void epi_store(const ConvTcParams& p, const EpiTile& 
   auto finish = [&](int pix, int ph, int pw, float4 v) {
     if (MASK) {
       const uint2 mk = __ldg(reinterpret_cast<const uint2*>(p.mask + e.mask_base + (size_t)(ph * e.mask_row + pw * e.mask_px)));
-      if (!(bf16_bits_to_float(mk.x & 0xffffu) > 0.f)) v.x = 0.f;
-      if (!(bf16_bits_to_float(mk.x >> 16) > 0.f)) v.y = 0.f;
-      if (!(bf16_bits_to_float(mk.y & 0xffffu) > 0.f)) v.z = 0.f;
-      if (!(bf16_bits_to_float(mk.y >> 16) > 0.f)) v.w = 0.f;
+      if (!pos16(mk.x & 0xffffu)) v.x = 0.f;
+      if (!pos16(mk.x >> 16)) v.y = 0.f;
+      if (!pos16(mk.y & 0xffffu)) v.z = 0.f;
+      if (!pos16(mk.y >> 16)) v.w = 0.f;
     }
     if (MASK) { cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w; }   // column sums = bias gradient (masked dgrad modes only)
-    uint2 hi2, lo2;
-    if (SPLIT) split_bf16x4(v, hi2, lo2);
+    uint2 hi2, lo2, xb2;
+    if (OUTK == 1) split_bf16x4(v, hi2, lo2);
+    if (OUTK == 2 || OUTK == 3) split_f16x4(v, hi2, lo2);
+    if (OUTK == 3) xb2 = pack_bf16x4(v);
+    if (OUTK == 4) hi2 = pack_bf16x4(v);
     const size_t off = e.out_base + (size_t)(ph * e.out_row + pw * e.out_px);
 #pragma unroll
     for (int dy = 0; dy < (UPS ? 2 : 1); ++dy)
@@ -169,10 +179,9 @@ __device__ __forceinline__ void epi_store(const ConvTcParams& p, const EpiTile& 
       for (int dx = 0; dx < (UPS ? 2 : 1); ++dx) {
         const size_t o = off + (size_t)(dy * e.ws_c + dx * p.Cout);
         if (F32) *reinterpret_cast<float4*>(p.out_f32 + o) = v;
-        if (SPLIT) {
-          *reinterpret_cast<uint2*>(p.out_hi + o) = hi2;
-          *reinterpret_cast<uint2*>(p.out_lo + o) = lo2;
-        }
+        if (OUTK != 0) *reinterpret_cast<uint2*>(p.out_hi + o) = hi2;
+        if (OUTK >= 1 && OUTK <= 3) *reinterpret_cast<uint2*>(p.out_lo + o) = lo2;
+        if (OUTK == 3) *reinterpret_cast<uint2*>(p.out_xb + o) = xb2;
       }
   };
   if (RED == 0) {
@@ -237,6 +246,11 @@ __device__ __forceinline__ void epi_store(const ConvTcParams& p, const EpiTile& 
   "add.s64 bb, %4, " #OFF ";\n\t"                                                          \
   "tcgen05.mma.cta_group::" #CG ".kind::f16 [%1], ah, bb, %5, pt;\n\t"                     \
   "tcgen05.mma.cta_group::" #CG ".kind::f16 [%12], al, bb, %6, pt;\n\t"
+// the same without the A_lo x B_hi product (activation operand given as one plane: 2 MMAs per product)
+#define EGAZE_MMA_ONE(CG, OFF)                                                             \
+  "add.s64 ah, %2, " #OFF ";\n\t"                                                          \
+  "add.s64 bb, %4, " #OFF ";\n\t"                                                          \
+  "tcgen05.mma.cta_group::" #CG ".kind::f16 [%1], ah, bb, %5, pt;\n\t"
 #define EGAZE_TAP_HEAD(CG)                                                                 \
   "{\n\t"                                                                                  \
   ".reg .pred pb, pa, pacc, pt;\n\t"                                                       \
@@ -248,6 +262,16 @@ __device__ __forceinline__ void epi_store(const ConvTcParams& p, const EpiTile& 
   "setp.eq.b32 pt, %7, %7;\n\t"                                                            \
   "tcgen05.mma.cta_group::" #CG ".kind::f16 [%1], %2, %4, %5, pacc;\n\t"                   \
   "tcgen05.mma.cta_group::" #CG ".kind::f16 [%12], %3, %4, %6, pt;\n\t"
+#define EGAZE_TAP_HEAD_ONE(CG)                                                             \
+  "{\n\t"                                                                                  \
+  ".reg .pred pb, pa, pacc, pt;\n\t"                                                       \
+  ".reg .b64 ah, al, bb;\n\t"                                                              \
+  ".reg .b32 rb, ra;\n\t"                                                                  \
+  "mbarrier.test_wait.parity.shared::cta.b64 pb, [%8], %9;\n\t"                            \
+  "mbarrier.test_wait.parity.shared::cta.b64 pa, [%10], %11;\n\t"                          \
+  "setp.ne.b32 pacc, %7, 0;\n\t"                                                           \
+  "setp.eq.b32 pt, %7, %7;\n\t"                                                            \
+  "tcgen05.mma.cta_group::" #CG ".kind::f16 [%1], %2, %4, %5, pacc;\n\t"
 #define EGAZE_TAP_TAIL                                                                     \
   "selp.u32 rb, 1, 0, pb;\n\t"                                                             \
   "selp.u32 ra, 2, 0, pa;\n\t"                                                             \
@@ -260,7 +284,16 @@ __device__ __forceinline__ void epi_store(const ConvTcParams& p, const EpiTile& 
   : "memory"
 #define EGAZE_TAP_ASM(CG)                                                                                             \
   do {                                                                                                                \
-    if (KSTEPS == 4) {                                                                                                \
+    if (!LOHI) {                                                                                                      \
+      if (KSTEPS == 4) {                                                                                              \
+        asm volatile(EGAZE_TAP_HEAD_ONE(CG) EGAZE_MMA_ONE(CG, 2) EGAZE_MMA_ONE(CG, 4) EGAZE_MMA_ONE(CG, 6)            \
+                         EGAZE_TAP_TAIL EGAZE_TAP_OPERANDS);                                                          \
+      } else if (KSTEPS == 2) {                                                                                       \
+        asm volatile(EGAZE_TAP_HEAD_ONE(CG) EGAZE_MMA_ONE(CG, 2) EGAZE_TAP_TAIL EGAZE_TAP_OPERANDS);                  \
+      } else {                                                                                                        \
+        asm volatile(EGAZE_TAP_HEAD_ONE(CG) EGAZE_TAP_TAIL EGAZE_TAP_OPERANDS);                                       \
+      }                                                                                                               \
+    } else if (KSTEPS == 4) {                                                                                         \
       asm volatile(EGAZE_TAP_HEAD(CG) EGAZE_MMA_PAIR(CG, 2) EGAZE_MMA_PAIR(CG, 4) EGAZE_MMA_PAIR(CG, 6)               \
                        EGAZE_TAP_TAIL EGAZE_TAP_OPERANDS);                                                            \
     } else if (KSTEPS == 2) {                                                                                         \
@@ -271,7 +304,7 @@ __device__ __forceinline__ void epi_store(const ConvTcParams& p, const EpiTile& 
   } while (0)
 // d_tmem: accumulator of the N = 2*BN MMA; d_tmem2: accumulator of the N = BN MMA (the same block, or shifted by BN/2
 // columns in CTA-pair mode).  PAIR: cta_group::2 (M = 256 across the two CTAs of the cluster).
-template <int KSTEPS, bool PAIR>
+template <int KSTEPS, bool PAIR, bool LOHI>
 __device__ __forceinline__ uint32_t tap_merged_probe(uint32_t d_tmem, uint32_t d_tmem2, uint64_t ad_hi, uint64_t ad_lo,
                                                      uint64_t bd, uint32_t idesc2, uint32_t idesc, uint32_t accumulate,
                                                      uint32_t bar_b, uint32_t par_b, uint32_t bar_a, uint32_t par_a) {
@@ -282,11 +315,14 @@ __device__ __forceinline__ uint32_t tap_merged_probe(uint32_t d_tmem, uint32_t d
 }
 #undef EGAZE_TAP_ASM
 #undef EGAZE_TAP_HEAD
+#undef EGAZE_TAP_HEAD_ONE
 #undef EGAZE_TAP_TAIL
 #undef EGAZE_TAP_OPERANDS
 #undef EGAZE_MMA_PAIR
+#undef EGAZE_MMA_ONE
 
-template <int NSPLIT, int KSTEPS, int CS>
+// NSA / NSPLIT: planes of the activation / weight operand: (2, 2) 3 MMAs per product, (1, 2) 2 MMAs, (1, 1) one.
+template <int NSA, int NSPLIT, int KSTEPS, int CS>
 __global__ void __maxnreg__(128)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                   const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -303,8 +339,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
   const int num_clusters = gridDim.x / CS;
   constexpr uint16_t kMask = (uint16_t)((1u << CS) - 1);
 
-  uint8_t* a_ring = smem;                                                 // SA slots x NSPLIT planes
-  uint8_t* b_ring = smem + (size_t)p.SA * NSPLIT * p.a_slot_bytes;         // SB slots x NSPLIT planes
+  uint8_t* a_ring = smem;                                                 // SA slots x NSA planes
+  uint8_t* b_ring = smem + (size_t)p.SA * NSA * p.a_slot_bytes;            // SB slots x NSPLIT planes
   float* stage = reinterpret_cast<float*>(smem + p.stage_off);             // [128][CW+4] + scratch
   __shared__ uint64_t a_full[kMaxSA], a_empty[kMaxSA], b_full[kMaxSB], b_empty[kMaxSB], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_smem;
@@ -323,7 +359,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA_hi);
     ptx::prefetch_tmap(&tmB_hi);
-    if (NSPLIT == 2) { ptx::prefetch_tmap(&tmA_lo); ptx::prefetch_tmap(&tmB_lo); }
+    if (NSA == 2) ptx::prefetch_tmap(&tmA_lo);
+    if (NSPLIT == 2) ptx::prefetch_tmap(&tmB_lo);
   }
   const uint32_t acc_cols = (uint32_t)p.acc_cols;                // columns of one accumulator stage
   const uint32_t tmem_cols = 2 * acc_cols;                       // power of two in [64, 512]
@@ -364,20 +401,20 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         const int n0 = it.nt * p.BN;
         for (int kc = 0; kc < chunks; ++kc) {
           for (int al = 0; al < a_loads; ++al) {
-            uint8_t* a_dst = a_ring + (size_t)sa * NSPLIT * p.a_slot_bytes;
+            uint8_t* a_dst = a_ring + (size_t)sa * NSA * p.a_slot_bytes;
             const int wx = p.win ? it.w0 - 1 : it.w0 - 1 + al;
             if (leader) {
               { PROF_T0(p); ptx::mbar_wait(&a_empty[sa], a_par); PROF_ADD(p, prof_c[0]); }
               if (pair) {
                 // both CTAs' windows are accounted on rank 0's barrier (its MMA thread consumes both)
-                if (rank == 0) ptx::mbar_arrive_expect_tx(&a_full[sa], 2 * a_box_bytes * NSPLIT);
+                if (rank == 0) ptx::mbar_arrive_expect_tx(&a_full[sa], 2 * a_box_bytes * NSA);
                 ptx::tma_load_4d_2sm(a_dst, &tmA_hi, &a_full[sa], kc * p.KC, wx, it.h0 - 1, it.img);
-                if (NSPLIT == 2)
+                if (NSA == 2)
                   ptx::tma_load_4d_2sm(a_dst + p.a_slot_bytes, &tmA_lo, &a_full[sa], kc * p.KC, wx, it.h0 - 1, it.img);
               } else {
-                ptx::mbar_arrive_expect_tx(&a_full[sa], a_box_bytes * NSPLIT);
+                ptx::mbar_arrive_expect_tx(&a_full[sa], a_box_bytes * NSA);
                 ptx::tma_load_4d(a_dst, &tmA_hi, &a_full[sa], kc * p.KC, wx, it.h0 - 1, it.img);
-                if (NSPLIT == 2)
+                if (NSA == 2)
                   ptx::tma_load_4d(a_dst + p.a_slot_bytes, &tmA_lo, &a_full[sa], kc * p.KC, wx, it.h0 - 1, it.img);
               }
             }
@@ -426,8 +463,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
       // CTA-pair mode: rank 0 issues for both CTAs (M = 256); rank 1's MMA warp has nothing to do
       const bool leader = ptx::elect_one() && !(pair && rank != 0);
       const int mma_m = pair ? 256 : 128;
-      const uint32_t idesc = ptx::make_idesc_bf16(mma_m, p.BN, 0, 0);
-      const uint32_t idesc2 = ptx::make_idesc_bf16(mma_m, 2 * p.BN, 0, 0);
+      const uint32_t idesc = ptx::make_idesc_16(mma_m, p.BN, 0, 0, p.in_f16);
+      const uint32_t idesc2 = ptx::make_idesc_16(mma_m, 2 * p.BN, 0, 0, p.in_f16);
       const uint32_t sbo = 8u * (uint32_t)row_bytes;
       // window mode: the 8-pixel row segment of tile row th starts (BW+2) window rows after the one of th-1
       const uint32_t sbo_a = p.win ? (uint32_t)AW * (uint32_t)row_bytes : sbo;
@@ -436,7 +473,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
       const uint64_t desc_static = ptx::make_smem_desc(0, 16, sbo, (uint32_t)row_bytes);
       const uint64_t a_ring_desc = ptx::make_smem_desc(0, 16, sbo_a, (uint32_t)row_bytes) + (uint64_t)(ptx::smem_u32(a_ring) >> 4);
       const uint64_t b_ring_desc = desc_static + (uint64_t)(ptx::smem_u32(b_ring) >> 4);
-      const uint32_t a_slot16 = (uint32_t)(NSPLIT * p.a_slot_bytes) >> 4, a_plane16 = (uint32_t)p.a_slot_bytes >> 4;
+      const uint32_t a_slot16 = (uint32_t)(NSA * p.a_slot_bytes) >> 4, a_plane16 = (uint32_t)p.a_slot_bytes >> 4;
       const uint32_t b_slot16 = (uint32_t)(NSPLIT * p.b_slot_bytes) >> 4, b_plane16 = (uint32_t)p.b_slot_bytes >> 4;
       const uint32_t r_step16 = (uint32_t)(AW * row_bytes) >> 4;   // one tile row down inside the window
       const uint32_t s_step16 = (uint32_t)row_bytes >> 4;          // one pixel to the right (window mode)
@@ -484,7 +521,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                   // accumulator columns are [hh(c < BN/2) | hl(c < BN/2) | hh(c >= BN/2) | hl(c >= BN/2)]; the N = BN MMA
                   // (A_lo x B_hi, BN/2 rows per CTA) lands BN/2 columns in, on top of columns of the SAME channels.
                   if (NSPLIT == 2) {
-                    const uint32_t fl = tap_merged_probe<KSTEPS, true>(d_tmem, d_tmem + (bn >> 1), ad, ad + a_plane16, bd, idesc2,
+                    const uint32_t fl = tap_merged_probe<KSTEPS, true, NSA == 2>(d_tmem, d_tmem + (bn >> 1), ad, ad + a_plane16, bd, idesc2,
                                                                        idesc, accumulate, nb_bar, nb_par, na_bar, na_par);
                     b_ready = (fl & 1u) != 0;
                     a_next_ready = (fl & 2u) != 0;
@@ -496,11 +533,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                     }
                   }
                 } else if (acc_mode == 1) {
-                  const uint32_t fl = tap_merged_probe<KSTEPS, false>(d_tmem, d_tmem, ad, ad + a_plane16, bd, idesc2, idesc,
+                  const uint32_t fl = tap_merged_probe<KSTEPS, false, NSA == 2>(d_tmem, d_tmem, ad, ad + a_plane16, bd, idesc2, idesc,
                                                                       accumulate, nb_bar, nb_par, na_bar, na_par);
                   b_ready = (fl & 1u) != 0;
                   a_next_ready = (fl & 2u) != 0;
-                } else if (acc_mode == 3) {
+                } else if (acc_mode == 3 && NSA == 2) {
 #pragma unroll
                   for (int k = 0; k < KSTEPS; ++k) {
                     if ((k & 1) == 0) {
@@ -514,7 +551,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                     }
                     accumulate = 1;
                   }
-                } else if (acc_mode == 2) {
+                } else if (acc_mode == 2 && NSA == 2) {
 #pragma unroll
                   for (int k = 0; k < KSTEPS; ++k) {
                     ptx::umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc2, accumulate);                          // blocks 0-1
@@ -530,6 +567,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                   if (NSPLIT == 2) {
 #pragma unroll
                     for (int k = 0; k < KSTEPS; ++k) ptx::umma_bf16(d_tmem, ad + 2 * k, bd + b_plane16 + 2 * k, idesc, 1);
+                  }
+                  if (NSA == 2) {
 #pragma unroll
                     for (int k = 0; k < KSTEPS; ++k) ptx::umma_bf16(d_tmem, ad + a_plane16 + 2 * k, bd + 2 * k, idesc, 1);
                   }
@@ -605,12 +644,18 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     const int ph_start = pl / oBW, pw_start = pl - ph_start * oBW;
     const int obw_log = 31 - __clz(oBW);
     const bool lean_ok = (oBW & (oBW - 1)) == 0;
-    // which compile-time specialisation of the store loop serves this launch (0 = the generic flag-driven loop)
-    int lean_mode = 0;
+    // which compile-time specialisation of the store loop serves this launch (0 = the generic flag-driven loop), and which
+    // 16-bit planes it writes (OUTK of epi_store)
+    int lean_mode = 0, outk = 0;
     {
-      const bool f32 = p.out_f32 != nullptr, spl = p.out_hi != nullptr && p.out_lo != nullptr;
-      const bool half_split = (p.out_hi != nullptr) != (p.out_lo != nullptr);
-      if (!half_split) {
+      const bool f32 = p.out_f32 != nullptr, spl = p.out_hi != nullptr;
+      if (spl) {
+        if (p.out_f16) outk = !p.out_lo ? -1 : (p.out_xb ? 3 : 2);
+        else outk = p.out_xb ? -1 : (p.out_lo ? 1 : 4);
+      } else if (p.out_lo || p.out_xb) {
+        outk = -1;
+      }
+      if (outk >= 0) {
         if (!p.mask && !p.ups && p.reduce == 0 && f32 && !spl) lean_mode = 1;
         else if (!p.mask && !p.ups && p.reduce == 0 && !f32 && spl) lean_mode = 2;
         else if (!p.mask && p.ups && p.reduce == 0 && !f32 && spl) lean_mode = 3;
@@ -618,6 +663,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         else if (p.mask && !p.ups && p.reduce == 0 && !f32 && spl) lean_mode = 5;
         else if (p.mask && !p.ups && p.reduce == 2 && !f32 && spl) lean_mode = 6;
         else if (!p.mask && !p.ups && p.reduce == 0 && f32 && spl) lean_mode = 7;
+        // plane sets each mode is instantiated for: forward modes 1 / 2 / 3, gradient modes 1 / 4
+        if ((lean_mode >= 2 && lean_mode <= 4 && outk > 3) || (lean_mode == 7 && outk > 2) ||
+            ((lean_mode == 5 || lean_mode == 6) && outk != 1 && outk != 4))
+          lean_mode = 0;
       }
     }
     const int rep = p.ups ? 2 : 1;
@@ -664,6 +713,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
             }
           } else {
             ptx::tmem_ld_wait();
+          }
+          if (p.acc_scale != 1.f) {   // fp16 weights are packed pre-scaled by a power of two: undo it (exact)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * p.acc_scale);
           }
           const uint32_t dst = stage_s + (uint32_t)((m * ldst + c0) * 4);
 #pragma unroll
@@ -733,15 +786,27 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
             // statistics ride on mode 1 only, column sums on the masked modes only; anything else takes the generic loop
             switch ((p.stats && lean_mode != 1) || (p.colsum && lean_mode != 5 && lean_mode != 6) ? 0 : lean_mode) {
               case 1:                                                              // fp32 out: train-mode trunk / dgrad into BN
-                if (p.stats) epi_store<0, false, false, true, false, true>(p, e, cs, k4, &s1v, &s2v);
-                else epi_store<0, false, false, true, false>(p, e, cs);
+                if (p.stats) epi_store<0, false, false, true, 0, true>(p, e, cs, k4, &s1v, &s2v);
+                else epi_store<0, false, false, true, 0>(p, e, cs);
                 break;
-              case 2: epi_store<0, false, false, false, true>(p, e, cs); break;   // split out: decoder / eval trunk
-              case 3: epi_store<0, false, true, false, true>(p, e, cs); break;    // ... + nearest-2x replicate
-              case 4: epi_store<1, false, false, false, true>(p, e, cs); break;   // ... + 2x2 max-pool
-              case 5: epi_store<0, true, false, false, true>(p, e, cs); break;    // decoder dgrad: ReLU mask
-              case 6: epi_store<2, true, false, false, true>(p, e, cs); break;    // ... + 2x2 sum (grad of Upsample)
-              case 7: epi_store<0, false, false, true, true>(p, e, cs); break;    // both outputs
+#define EGAZE_EPI_FWD(RED, UPS)                                                                 \
+  if (outk == 1) epi_store<RED, false, UPS, false, 1>(p, e, cs);                                  \
+  else if (outk == 2) epi_store<RED, false, UPS, false, 2>(p, e, cs);                             \
+  else epi_store<RED, false, UPS, false, 3>(p, e, cs)
+#define EGAZE_EPI_BWD(RED)                                                                      \
+  if (outk == 1) epi_store<RED, true, false, false, 1>(p, e, cs);                                 \
+  else epi_store<RED, true, false, false, 4>(p, e, cs)
+              case 2: EGAZE_EPI_FWD(0, false); break;   // split out: decoder / eval trunk
+              case 3: EGAZE_EPI_FWD(0, true); break;    // ... + nearest-2x replicate
+              case 4: EGAZE_EPI_FWD(1, false); break;   // ... + 2x2 max-pool
+              case 5: EGAZE_EPI_BWD(0); break;          // decoder dgrad: ReLU mask
+              case 6: EGAZE_EPI_BWD(2); break;          // ... + 2x2 sum (grad of Upsample)
+              case 7:                                   // both outputs
+                if (outk == 1) epi_store<0, false, false, true, 1>(p, e, cs);
+                else epi_store<0, false, false, true, 2>(p, e, cs);
+                break;
+#undef EGAZE_EPI_FWD
+#undef EGAZE_EPI_BWD
               default: done = false;
             }
           }
@@ -785,28 +850,25 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                 const size_t mpix = p.mask_ups ? ((size_t)(img * 2 * Ho + 2 * oh) * (2 * Wo) + 2 * ow)
                                                : ((size_t)(img * Ho + oh) * Wo + ow);
                 const uint2 mk = __ldg(reinterpret_cast<const uint2*>(p.mask + mpix * p.Cout + ch));
-                if (!(bf16_bits_to_float(mk.x & 0xffffu) > 0.f)) v.x = 0.f;
-                if (!(bf16_bits_to_float(mk.x >> 16) > 0.f)) v.y = 0.f;
-                if (!(bf16_bits_to_float(mk.y & 0xffffu) > 0.f)) v.z = 0.f;
-                if (!(bf16_bits_to_float(mk.y >> 16) > 0.f)) v.w = 0.f;
+                if (!pos16(mk.x & 0xffffu)) v.x = 0.f;
+                if (!pos16(mk.x >> 16)) v.y = 0.f;
+                if (!pos16(mk.y & 0xffffu)) v.z = 0.f;
+                if (!pos16(mk.y >> 16)) v.w = 0.f;
               }
               cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
-              uint2 hi2 = make_uint2(0, 0), lo2 = make_uint2(0, 0);
+              uint2 hi2 = make_uint2(0, 0), lo2 = make_uint2(0, 0), xb2 = make_uint2(0, 0);
               if (p.out_hi) {
-                __nv_bfloat16 h[4], l[4];
-                split_bf16(v.x, h[0], l[0]);
-                split_bf16(v.y, h[1], l[1]);
-                split_bf16(v.z, h[2], l[2]);
-                split_bf16(v.w, h[3], l[3]);
-                hi2 = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
-                lo2 = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+                if (p.out_f16) split_f16x4(v, hi2, lo2);
+                else split_bf16x4(v, hi2, lo2);
               }
+              if (p.out_xb) xb2 = pack_bf16x4(v);
               for (int dy = 0; dy < rep; ++dy)
                 for (int dx = 0; dx < rep; ++dx) {
                   const size_t off = ((size_t)(img * Hs + oh * rep + dy) * Ws + (ow * rep + dx)) * p.Cout + ch;
                   if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + off) = v;
                   if (p.out_hi) *reinterpret_cast<uint2*>(p.out_hi + off) = hi2;
                   if (p.out_lo) *reinterpret_cast<uint2*>(p.out_lo + off) = lo2;
+                  if (p.out_xb) *reinterpret_cast<uint2*>(p.out_xb + off) = xb2;
                 }
             }
             pw += PS;
@@ -967,9 +1029,12 @@ extern "C" int egaze_conv3x3_set_prof(void* buf) {
 extern "C" int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, int N, int H, int W,
                                 int Cin_p, int Cout, const float* bias, const float* scale, const float* shift, int relu,
                                 int reduce, int ups, const void* mask, int mask_ups, float* out_f32, void* out_hi,
-                                void* out_lo, float* stats, float* stats_cnt, float* colsum, int precise, void* stream) {
+                                void* out_lo, void* out_xb, float* stats, float* stats_cnt, float* colsum, int in_f16,
+                                int out_f16, float acc_scale, void* stream) {
   EGAZE_CHECK_ARG(x_hi && w_hi, "conv3x3_tc: null operand");
-  EGAZE_CHECK_ARG(!precise || (x_lo && w_lo), "conv3x3_tc: precise mode needs lo planes");
+  EGAZE_CHECK_ARG(!(x_lo && !w_lo), "conv3x3_tc: an activation lo plane needs a weight lo plane (operand modes: hi+lo x hi+lo, hi x hi+lo, hi x hi)");
+  EGAZE_CHECK_ARG(acc_scale > 0.f, "conv3x3_tc: acc_scale must be positive");
+  const int nsa = x_lo ? 2 : 1, precise = w_lo ? 1 : 0;
   EGAZE_CHECK_ARG(N > 0 && H > 0 && W > 0, "conv3x3_tc: bad shape %d %d %d", N, H, W);
   EGAZE_CHECK_ARG(Cin_p % 16 == 0, "conv3x3_tc: Cin_p=%d must be a multiple of 16", Cin_p);
   EGAZE_CHECK_ARG(Cout % 16 == 0 && Cout >= 16, "conv3x3_tc: Cout=%d must be a multiple of 16", Cout);
@@ -1009,7 +1074,7 @@ extern "C" int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* 
     // ring depth the weight boxes would get next to two 180-row windows (see the smem budget below)
     const int bn = conv_pick_bn(Cout, precise), ns = precise ? 2 : 1;
     const int stage_b = ((128 * ((bn < 64 ? bn : 64) + 4) * 4 + kEpiScratch * 4 + (stats ? Cout * 3 * 4 : 0) + (colsum ? Cout * 4 : 0) + 1023) / 1024) * 1024;
-    const int sb_w = (222 * 1024 - stage_b - 2 * ns * 23552) / (ns * bn * 128);
+    const int sb_w = (222 * 1024 - stage_b - 2 * nsa * 23552) / (ns * bn * 128);
     if (eff_w >= eff_c * 0.999 && sb_w >= win_minsb) {
       p.win = 1;
       p.win_bo = win_env == 2 ? 1 : 0;
@@ -1018,6 +1083,9 @@ extern "C" int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* 
     }
   }
   p.nsplit = precise ? 2 : 1;
+  p.nsplit_a = nsa;
+  p.in_f16 = in_f16;
+  p.acc_scale = acc_scale;
   // N tile: largest of 128/64/32/16 dividing Cout (256 only in fast mode where the rings fit).
   p.BN = conv_pick_bn(Cout, precise);
   p.tiles_h = ceil_div(H, p.BH); p.tiles_w = ceil_div(W, p.BW); p.tiles_n = Cout / p.BN;
@@ -1054,9 +1122,11 @@ extern "C" int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* 
   }
   p.SA = 2;
   const int budget = 222 * 1024 - stage_bytes;
-  if (sa_env >= 2 && sa_env <= kMaxSA && (budget - sa_env * p.nsplit * p.a_slot_bytes) / (p.nsplit * p.b_slot_bytes) >= 3)
+  if (sa_env >= 2 && sa_env <= kMaxSA && (budget - sa_env * nsa * p.a_slot_bytes) / (p.nsplit * p.b_slot_bytes) >= 3)
     p.SA = sa_env;
-  int sb = (budget - p.SA * p.nsplit * p.a_slot_bytes) / (p.nsplit * p.b_slot_bytes);
+  else if (nsa == 1 && (budget - 3 * p.a_slot_bytes) / (p.nsplit * p.b_slot_bytes) >= 6)
+    p.SA = 3;   // one activation plane: the freed shared memory buys a third window slot
+  int sb = (budget - p.SA * nsa * p.a_slot_bytes) / (p.nsplit * p.b_slot_bytes);
   if (sb > 6) sb = 6;
   EGAZE_CHECK_ARG(sb >= 2, "conv3x3_tc: tile does not fit shared memory");
   p.SB = sb;
@@ -1073,8 +1143,8 @@ extern "C" int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* 
     if (precise) {
       // measured (B=32 SP layers): mode 1 beats 2 and 3 -- fewer, larger MMAs win; the extra smem operand reads of mode 3
       // cost more than any accumulator interleaving gains
-      mode = can_merge ? 1 : 3;
-      if (mode_env >= 0) mode = mode_env;
+      mode = can_merge ? 1 : (nsa == 2 ? 3 : 0);
+      if (mode_env >= 0 && nsa == 2) mode = mode_env;
       if ((mode == 1 || mode == 2) && !can_merge) mode = 3;
       if (mode == 2 && p.BN > 64) mode = 1;
       if (p.pair) {
@@ -1089,12 +1159,15 @@ extern "C" int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* 
     while (p.acc_cols < cols) p.acc_cols *= 2;
     EGAZE_CHECK_ARG(2 * p.acc_cols <= 512, "conv3x3_tc: accumulators do not fit TMEM (BN=%d mode=%d)", p.BN, mode);
   }
-  p.stage_off = p.SA * p.nsplit * p.a_slot_bytes + p.SB * p.nsplit * p.b_slot_bytes;
+  p.stage_off = p.SA * nsa * p.a_slot_bytes + p.SB * p.nsplit * p.b_slot_bytes;
   const size_t smem = (size_t)p.stage_off + stage_bytes + 1024;  // + alignment slack
   p.bias = bias; p.scale = scale; p.shift = shift; p.relu = relu; p.reduce = reduce; p.ups = ups;
   p.mask = (const __nv_bfloat16*)mask;
   p.mask_ups = mask_ups;
   p.out_f32 = out_f32; p.out_hi = (__nv_bfloat16*)out_hi; p.out_lo = (__nv_bfloat16*)out_lo;
+  p.out_xb = (__nv_bfloat16*)out_xb; p.out_f16 = out_f16;
+  EGAZE_CHECK_ARG(!(out_lo && !out_hi) && !(out_xb && !out_hi), "conv3x3_tc: out_lo / out_xb need out_hi");
+  EGAZE_CHECK_ARG(!(out_f16 && out_hi && !out_lo), "conv3x3_tc: fp16 output needs both planes");
   p.stats = stats; p.stats_cnt = stats_cnt;
   p.colsum = colsum;
   p.prof = g_conv_prof;
@@ -1106,7 +1179,7 @@ extern "C" int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* 
     uint32_t box[4] = {(uint32_t)p.KC, (uint32_t)(p.win ? p.BW + 2 : p.BW), (uint32_t)(p.BH + 2), 1};
     int rc = egaze_encode_tmap(&tmA_hi, x_hi, 4, dims, str, box, row_bytes, 2);
     if (rc) return rc;
-    rc = egaze_encode_tmap(&tmA_lo, precise ? x_lo : x_hi, 4, dims, str, box, row_bytes, 2);
+    rc = egaze_encode_tmap(&tmA_lo, nsa == 2 ? x_lo : x_hi, 4, dims, str, box, row_bytes, 2);
     if (rc) return rc;
   }
   {
@@ -1134,27 +1207,30 @@ extern "C" int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* 
   cfg.attrs = attr;
   cfg.numAttrs = CS > 1 ? 1 : 0;
   const int ksteps = p.KC / 16;
-#define EGAZE_CONV_LAUNCH(NS, KS, C)                                                                                  \
+#define EGAZE_CONV_LAUNCH(NA, NS, KS, C)                                                                              \
   do {                                                                                                                \
     static unsigned long long attr_set = 0;                                                                           \
     if (egaze_first_on_device(&attr_set)) {                                                                           \
-      EGAZE_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<NS, KS, C>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+      EGAZE_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<NA, NS, KS, C>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                       224 * 1024));                                                                   \
     }                                                                                                                 \
-    EGAZE_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<NS, KS, C>, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p));            \
+    EGAZE_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<NA, NS, KS, C>, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p));        \
   } while (0)
-#define EGAZE_CONV_DISPATCH(NS, C)                                                                                    \
+#define EGAZE_CONV_DISPATCH(NA, NS, C)                                                                                \
   do {                                                                                                                \
-    if (ksteps == 4) EGAZE_CONV_LAUNCH(NS, 4, C);                                                                     \
-    else if (ksteps == 2) EGAZE_CONV_LAUNCH(NS, 2, C);                                                                \
-    else EGAZE_CONV_LAUNCH(NS, 1, C);                                                                                 \
+    if (ksteps == 4) EGAZE_CONV_LAUNCH(NA, NS, 4, C);                                                                 \
+    else if (ksteps == 2) EGAZE_CONV_LAUNCH(NA, NS, 2, C);                                                            \
+    else EGAZE_CONV_LAUNCH(NA, NS, 1, C);                                                                             \
   } while (0)
-  if (p.nsplit == 2) {
-    if (CS == 2) EGAZE_CONV_DISPATCH(2, 2);
-    else EGAZE_CONV_DISPATCH(2, 1);
+  if (p.nsplit == 2 && nsa == 2) {
+    if (CS == 2) EGAZE_CONV_DISPATCH(2, 2, 2);
+    else EGAZE_CONV_DISPATCH(2, 2, 1);
+  } else if (p.nsplit == 2) {
+    if (CS == 2) EGAZE_CONV_DISPATCH(1, 2, 2);
+    else EGAZE_CONV_DISPATCH(1, 2, 1);
   } else {
-    if (CS == 2) EGAZE_CONV_DISPATCH(1, 2);
-    else EGAZE_CONV_DISPATCH(1, 1);
+    if (CS == 2) EGAZE_CONV_DISPATCH(1, 1, 2);
+    else EGAZE_CONV_DISPATCH(1, 1, 1);
   }
 #undef EGAZE_CONV_DISPATCH
 #undef EGAZE_CONV_LAUNCH

@@ -8,7 +8,7 @@ namespace {
 // x: NHWC split-bf16 [P][Cs]; w: [C] fp32 (C <= Cs); out[p] = sigmoid(sum_c (hi+lo)[p][c]*w[c] + b)
 template <int CS>
 __global__ void head_fwd_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
-                                const float* __restrict__ w, const float* __restrict__ b, int C, size_t P,
+                                const float* __restrict__ w, const float* __restrict__ b, int C, size_t P, int fmt,
                                 float* __restrict__ out, float* __restrict__ logit_out) {
   __shared__ float ws[CS];
   for (int i = threadIdx.x; i < CS; i += blockDim.x) ws[i] = i < C ? w[i] : 0.f;
@@ -27,8 +27,8 @@ __global__ void head_fwd_kernel(const __nv_bfloat16* __restrict__ hi, const __nv
       const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float x0 = bf16_bits_to_float(hw[q] & 0xffffu) + bf16_bits_to_float(lw[q] & 0xffffu);
-        const float x1 = bf16_bits_to_float(hw[q] >> 16) + bf16_bits_to_float(lw[q] >> 16);
+        const float x0 = dec16(hw[q] & 0xffffu, fmt) + dec16(lw[q] & 0xffffu, fmt);
+        const float x1 = dec16(hw[q] >> 16, fmt) + dec16(lw[q] >> 16, fmt);
         acc = fmaf(x0, ws[i * 8 + q * 2], acc);
         acc = fmaf(x1, ws[i * 8 + q * 2 + 1], acc);
       }
@@ -43,7 +43,7 @@ __global__ void head_fwd_kernel(const __nv_bfloat16* __restrict__ hi, const __nv
 // dw[c] += sum_p dz*x[p][c];  db += sum_p dz.   Block-level reduction of dw/db, then one atomicAdd per block.
 template <int CS>
 __global__ void head_bwd_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
-                                const float* __restrict__ w, int C, size_t P, const float* __restrict__ y,
+                                const float* __restrict__ w, int C, size_t P, int fmt, const float* __restrict__ y,
                                 const float* __restrict__ gy, int relu_mask, __nv_bfloat16* __restrict__ dx_hi,
                                 __nv_bfloat16* __restrict__ dx_lo, float* __restrict__ dw, float* __restrict__ db) {
   __shared__ float ws[CS];
@@ -71,8 +71,8 @@ __global__ void head_bwd_kernel(const __nv_bfloat16* __restrict__ hi, const __nv
       uint32_t oh[4], ol[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float x0 = bf16_bits_to_float(hw[q] & 0xffffu) + bf16_bits_to_float(lw[q] & 0xffffu);
-        const float x1 = bf16_bits_to_float(hw[q] >> 16) + bf16_bits_to_float(lw[q] >> 16);
+        const float x0 = dec16(hw[q] & 0xffffu, fmt) + dec16(lw[q] & 0xffffu, fmt);
+        const float x1 = dec16(hw[q] >> 16, fmt) + dec16(lw[q] >> 16, fmt);
         dwl[i * 8 + q * 2] = fmaf(dz, x0, dwl[i * 8 + q * 2]);
         dwl[i * 8 + q * 2 + 1] = fmaf(dz, x1, dwl[i * 8 + q * 2 + 1]);
         float g0 = dz * ws[i * 8 + q * 2], g1 = dz * ws[i * 8 + q * 2 + 1];
@@ -105,7 +105,7 @@ __global__ void head_bwd_kernel(const __nv_bfloat16* __restrict__ hi, const __nv
 
 }  // namespace
 
-extern "C" int egaze_head_fwd(const void* x_hi, const void* x_lo, const float* w, const float* b, int C, int Cs,
+extern "C" int egaze_head_fwd(const void* x_hi, const void* x_lo, int fmt, const float* w, const float* b, int C, int Cs,
                               long long P, float* out, float* logit_out, void* stream) {
   EGAZE_CHECK_ARG(x_hi && w && out && P > 0, "head_fwd: bad args");
   EGAZE_CHECK_ARG((Cs == 64 || Cs == 16) && C <= Cs, "head_fwd: channel stride must be 64 or 16 (got %d)", Cs);
@@ -113,16 +113,16 @@ extern "C" int egaze_head_fwd(const void* x_hi, const void* x_lo, const float* w
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (Cs == 64)
     head_fwd_kernel<64><<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x_hi, (const __nv_bfloat16*)x_lo, w,
-                                                                  b, C, (size_t)P, out, logit_out);
+                                                                  b, C, (size_t)P, fmt, out, logit_out);
   else
     head_fwd_kernel<16><<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x_hi, (const __nv_bfloat16*)x_lo, w,
-                                                                  b, C, (size_t)P, out, logit_out);
+                                                                  b, C, (size_t)P, fmt, out, logit_out);
   EGAZE_LAUNCH_CHECK();
   return EGAZE_OK;
 }
 
 // dw ([C]) and db ([1]) are ACCUMULATED into (caller zeroes them).
-extern "C" int egaze_head_bwd(const void* x_hi, const void* x_lo, const float* w, int C, int Cs, long long P,
+extern "C" int egaze_head_bwd(const void* x_hi, const void* x_lo, int fmt, const float* w, int C, int Cs, long long P,
                               const float* y, const float* gy, int relu_mask, void* dx_hi, void* dx_lo, float* dw,
                               float* db, void* stream) {
   EGAZE_CHECK_ARG(x_hi && w && y && gy && dw && P > 0, "head_bwd: bad args");
@@ -131,11 +131,11 @@ extern "C" int egaze_head_bwd(const void* x_hi, const void* x_lo, const float* w
   if (blocks > 148 * 4) blocks = 148 * 4;
   if (Cs == 64)
     head_bwd_kernel<64><<<blocks, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x_hi, (const __nv_bfloat16*)x_lo, w,
-                                                                  C, (size_t)P, y, gy, relu_mask, (__nv_bfloat16*)dx_hi,
+                                                                  C, (size_t)P, fmt, y, gy, relu_mask, (__nv_bfloat16*)dx_hi,
                                                                   (__nv_bfloat16*)dx_lo, dw, db);
   else
     head_bwd_kernel<16><<<blocks, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x_hi, (const __nv_bfloat16*)x_lo, w,
-                                                                  C, (size_t)P, y, gy, relu_mask, (__nv_bfloat16*)dx_hi,
+                                                                  C, (size_t)P, fmt, y, gy, relu_mask, (__nv_bfloat16*)dx_hi,
                                                                   (__nv_bfloat16*)dx_lo, dw, db);
   EGAZE_LAUNCH_CHECK();
   return EGAZE_OK;

@@ -6,8 +6,11 @@
 namespace {
 
 // x: [N][C][HW] fp32  ->  hi/lo: [N][HW][Cp] bf16 (channels >= C zero-filled)
+// fmt: 0 = bf16 planes, 1 = fp16 planes; xb: optional extra bf16(x) plane (what the weight-gradient GEMM reads when the
+// forward planes are fp16)
 __global__ void nchw_to_nhwc_split_kernel(const float* __restrict__ x, int C, int HW, int Cp,
-                                          __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+                                          __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                          __nv_bfloat16* __restrict__ xb, int fmt) {
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -21,18 +24,26 @@ __global__ void nchw_to_nhwc_split_kernel(const float* __restrict__ x, int C, in
     const int p = p0 + i, c = c0 + threadIdx.x;
     if (p < HW && c < Cp) {
       const float v = tile[threadIdx.x][i];
-      __nv_bfloat16 h, l;
-      split_bf16(v, h, l);
       const size_t o = ((size_t)n * HW + p) * Cp + c;
-      hi[o] = h;
-      if (lo) lo[o] = l;
+      if (fmt) {
+        __half h, l;
+        split_f16(v, h, l);
+        reinterpret_cast<__half*>(hi)[o] = h;
+        if (lo) reinterpret_cast<__half*>(lo)[o] = l;
+      } else {
+        __nv_bfloat16 h, l;
+        split_bf16(v, h, l);
+        hi[o] = h;
+        if (lo) lo[o] = l;
+      }
+      if (xb) xb[o] = __float2bfloat16_rn(v);
     }
   }
 }
 
 // hi/lo (or f32): [N][HW][Cs] (channel stride Cs >= C)  ->  out: [N][C][HW] fp32
 __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
-                                    const float* __restrict__ f32, int C, int HW, int Cs, float* __restrict__ out) {
+                                    const float* __restrict__ f32, int C, int HW, int Cs, int fmt, float* __restrict__ out) {
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -43,8 +54,8 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ hi, const 
       const size_t o = ((size_t)n * HW + p) * Cs + c;
       if (f32) v = f32[o];
       else {
-        v = __bfloat162float(hi[o]);
-        if (lo) v += __bfloat162float(lo[o]);
+        v = dec16(reinterpret_cast<const unsigned short*>(hi)[o], fmt);
+        if (lo) v += dec16(reinterpret_cast<const unsigned short*>(lo)[o], fmt);
       }
     }
     tile[i][threadIdx.x] = v;
@@ -74,12 +85,19 @@ __global__ void nchw_to_nhwc_f32_kernel(const float* __restrict__ x, int C, int 
 
 // fp32 NHWC -> split planes (same shape), elementwise
 __global__ void f32_to_split_kernel(const float* __restrict__ x, size_t n, __nv_bfloat16* __restrict__ hi,
-                                    __nv_bfloat16* __restrict__ lo) {
+                                    __nv_bfloat16* __restrict__ lo, int fmt) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    __nv_bfloat16 h, l;
-    split_bf16(x[i], h, l);
-    hi[i] = h;
-    if (lo) lo[i] = l;
+    if (fmt) {
+      __half h, l;
+      split_f16(x[i], h, l);
+      reinterpret_cast<__half*>(hi)[i] = h;
+      if (lo) reinterpret_cast<__half*>(lo)[i] = l;
+    } else {
+      __nv_bfloat16 h, l;
+      split_bf16(x[i], h, l);
+      hi[i] = h;
+      if (lo) lo[i] = l;
+    }
   }
 }
 
@@ -88,8 +106,11 @@ __global__ void f32_to_split_kernel(const float* __restrict__ x, size_t n, __nv_
 //  mode 1 (dgrad) : out[((2-r)*3+(2-s))][ci][co]    rows = Ci, cols = Co_p  (co >= Co zero)
 // One thread per (row, col): it reads the nine taps of its weight (36 contiguous bytes; in mode 0 adjacent threads read
 // adjacent runs) and writes one element of each tap plane (adjacent threads write adjacent bf16).
+// fmt 1: fp16 planes of w * kF16WScale (the forward operand format; the conv multiplies its accumulators by 1 / kF16WScale):
+// with weights around 1e-2 the unscaled lo plane would sit in fp16's subnormal range and keep only ~19 bits of the weight.
+constexpr float kF16WScale = 256.f;
 __device__ __forceinline__ void pack_w3x3_body(const float* __restrict__ w, int Co, int Ci, int rows, int cols_p, int mode,
-                                               __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                               int fmt, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                                                uint32_t first, uint32_t stride) {
   const uint32_t total = (uint32_t)rows * cols_p;
   const size_t plane = (size_t)rows * cols_p;
@@ -102,17 +123,24 @@ __device__ __forceinline__ void pack_w3x3_body(const float* __restrict__ w, int 
     for (int t = 0; t < 9; ++t) v[t] = live ? src[t] : 0.f;
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
-      __nv_bfloat16 h, l;
-      split_bf16(v[mode == 0 ? t : 8 - t], h, l);
-      hi[(size_t)t * plane + i] = h;
-      if (lo) lo[(size_t)t * plane + i] = l;
+      if (fmt) {
+        __half h, l;
+        split_f16(v[mode == 0 ? t : 8 - t] * kF16WScale, h, l);
+        reinterpret_cast<__half*>(hi)[(size_t)t * plane + i] = h;
+        if (lo) reinterpret_cast<__half*>(lo)[(size_t)t * plane + i] = l;
+      } else {
+        __nv_bfloat16 h, l;
+        split_bf16(v[mode == 0 ? t : 8 - t], h, l);
+        hi[(size_t)t * plane + i] = h;
+        if (lo) lo[(size_t)t * plane + i] = l;
+      }
     }
   }
 }
 
-__global__ void pack_w3x3_kernel(const float* __restrict__ w, int Co, int Ci, int rows, int cols_p, int mode,
+__global__ void pack_w3x3_kernel(const float* __restrict__ w, int Co, int Ci, int rows, int cols_p, int mode, int fmt,
                                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
-  pack_w3x3_body(w, Co, Ci, rows, cols_p, mode, hi, lo, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+  pack_w3x3_body(w, Co, Ci, rows, cols_p, mode, fmt, hi, lo, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
 
 // The same for MANY weights in one launch (after an optimiser step every packed copy is stale): blockIdx.y = job.
@@ -120,11 +148,11 @@ struct PackJob {
   const float* w;
   __nv_bfloat16* hi;
   __nv_bfloat16* lo;
-  int Co, Ci, rows, cols_p, mode, pad;
+  int Co, Ci, rows, cols_p, mode, fmt;
 };
 __global__ void pack_w3x3_multi_kernel(const PackJob* __restrict__ jobs) {
   const PackJob j = jobs[blockIdx.y];
-  pack_w3x3_body(j.w, j.Co, j.Ci, j.rows, j.cols_p, j.mode, j.hi, j.lo, blockIdx.x * blockDim.x + threadIdx.x,
+  pack_w3x3_body(j.w, j.Co, j.Ci, j.rows, j.cols_p, j.mode, j.fmt, j.hi, j.lo, blockIdx.x * blockDim.x + threadIdx.x,
                  gridDim.x * blockDim.x);
 }
 
@@ -148,24 +176,24 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, int Co, int C
 
 }  // namespace
 
-extern "C" int egaze_nchw_to_nhwc_split(const float* x, int N, int C, int H, int W, int Cp, void* hi, void* lo,
-                                        void* stream) {
+extern "C" int egaze_nchw_to_nhwc_split(const float* x, int N, int C, int H, int W, int Cp, void* hi, void* lo, void* xb,
+                                        int fmt, void* stream) {
   EGAZE_CHECK_ARG(x && hi && Cp >= C, "nchw_to_nhwc_split: bad args");
   const int HW = H * W;
   dim3 grid(ceil_div(HW, 32), ceil_div(Cp, 32), N), block(32, 8);
   nchw_to_nhwc_split_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, C, HW, Cp, (__nv_bfloat16*)hi,
-                                                                      (__nv_bfloat16*)lo);
+                                                                      (__nv_bfloat16*)lo, (__nv_bfloat16*)xb, fmt);
   EGAZE_LAUNCH_CHECK();
   return EGAZE_OK;
 }
 
 extern "C" int egaze_nhwc_to_nchw(const void* hi, const void* lo, const float* f32, int N, int C, int H, int W, int Cs,
-                                  float* out, void* stream) {
+                                  int fmt, float* out, void* stream) {
   EGAZE_CHECK_ARG((hi || f32) && out && Cs >= C, "nhwc_to_nchw: bad args");
   const int HW = H * W;
   dim3 grid(ceil_div(HW, 32), ceil_div(C, 32), N), block(32, 8);
   nhwc_to_nchw_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)hi, (const __nv_bfloat16*)lo, f32,
-                                                                C, HW, Cs, out);
+                                                                C, HW, Cs, fmt, out);
   EGAZE_LAUNCH_CHECK();
   return EGAZE_OK;
 }
@@ -179,17 +207,22 @@ extern "C" int egaze_nchw_to_nhwc_f32(const float* x, int N, int C, int H, int W
   return EGAZE_OK;
 }
 
-extern "C" int egaze_f32_to_split(const float* x, long long n, void* hi, void* lo, void* stream) {
+extern "C" int egaze_f32_to_split(const float* x, long long n, void* hi, void* lo, int fmt, void* stream) {
   EGAZE_CHECK_ARG(x && hi && n >= 0, "f32_to_split: bad args");
   if (n == 0) return EGAZE_OK;
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  f32_to_split_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, (size_t)n, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+  f32_to_split_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, (size_t)n, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, fmt);
   EGAZE_LAUNCH_CHECK();
   return EGAZE_OK;
 }
 
-extern "C" int egaze_pack_w3x3(const float* w_oihw, int Cout, int Cin, int cols_p, int mode, void* hi, void* lo,
+extern "C" int egaze_f16_weight_scale(float* out) {
+  if (out) *out = kF16WScale;
+  return EGAZE_OK;
+}
+
+extern "C" int egaze_pack_w3x3(const float* w_oihw, int Cout, int Cin, int cols_p, int mode, int fmt, void* hi, void* lo,
                                void* stream) {
   EGAZE_CHECK_ARG(w_oihw && hi, "pack_w3x3: bad args");
   const int rows = mode == 0 ? Cout : Cin;
@@ -197,7 +230,7 @@ extern "C" int egaze_pack_w3x3(const float* w_oihw, int Cout, int Cin, int cols_
   const size_t total = (size_t)rows * cols_p;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  pack_w3x3_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w_oihw, Cout, Cin, rows, cols_p, mode, (__nv_bfloat16*)hi,
+  pack_w3x3_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w_oihw, Cout, Cin, rows, cols_p, mode, fmt, (__nv_bfloat16*)hi,
                                                              (__nv_bfloat16*)lo);
   EGAZE_LAUNCH_CHECK();
   return EGAZE_OK;

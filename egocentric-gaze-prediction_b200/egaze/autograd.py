@@ -32,23 +32,8 @@ def _use_side_stream():
     return os.environ.get("EGAZE_WGRAD_STREAM", "1") != "0"
 
 
-def _emu(name):
-    """Experiment knobs (tools/grad_modes.py): emulate a cheaper backward numerically with the existing kernels."""
-    return os.environ.get(name, "0") == "1"
-
-
-def _hi_only(act):
-    return ops.Act(act.hi, torch.zeros_like(act.lo), act.C) if (act.lo is not None and _emu("EGAZE_EMU_DGRAD_HI")) else act
-
-
 def _wgrad(x_act, dy_act, cout, cin):
-    if _emu("EGAZE_EMU_WGRAD_1PASS"):
-        wg = lambda a, b, c, d: ops.wgrad3x3(a, b, c, d, precise=False)
-    elif _emu("EGAZE_EMU_WGRAD_XHI"):
-        wg = lambda a, b, c, d: ops.wgrad3x3(ops.Act(a.hi, torch.zeros_like(a.lo), a.C), b, c, d)
-    else:
-        wg = ops.wgrad3x3
-    return _wgrad_impl(wg, x_act, dy_act, cout, cin)
+    return _wgrad_impl(ops.wgrad3x3, x_act, dy_act, cout, cin)
 
 
 def _wgrad_impl(wg, x_act, dy_act, cout, cin):
@@ -62,7 +47,7 @@ def _wgrad_impl(wg, x_act, dy_act, cout, cin):
     side.wait_stream(main)                      # the operands were produced on the main stream
     with torch.cuda.stream(side):
         gw = wg(x_act, dy_act, cout, cin)
-    for t in (x_act.hi, x_act.lo, dy_act.hi, dy_act.lo):
+    for t in (x_act.hi, x_act.lo, x_act.xb, dy_act.hi, dy_act.lo):
         if t is not None:
             t.record_stream(side)               # the caching allocator must not recycle them while the side stream reads
     gw.record_stream(main)
@@ -111,7 +96,7 @@ def _dgrad(conv, gpre_act, **kw):
     cin = conv.in_channels
     rows_p = ops.pad_channels(cin) if cin % 16 else cin
     wpack = ops.pack_cache.get(conv.weight, 1, rows_p=rows_p, cols_p=gpre_act.Cp)
-    return ops.conv3x3(_hi_only(gpre_act), wpack, **kw)
+    return ops.conv3x3(gpre_act, wpack, want_lo=ops.mode()["dy_lo"], **kw)
 
 
 def _first_cp(conv):
@@ -139,14 +124,15 @@ def _bn_chain_steps(specs, saved, g, bag, need_input_grad, result):
     stop = 0 if need_input_grad else first_needed
     for i in range(len(specs) - 1, stop - 1, -1):
         sp, rec = specs[i], saved[i]
-        if "raw" not in rec:
-            raise NotImplementedError("egaze: backward through an eval-mode (folded) BatchNorm is not on the hot path")
+        evalbn = bool(rec.get("eval"))
         draw, _, dgamma, dbeta = ops.bn_bwd(rec["raw"], g, rec["scale"], rec["shift"], rec["mean"], rec["invstd"],
-                                            pool=sp.pool, relu=sp.relu)
+                                            pool=sp.pool, relu=sp.relu, batch_stats=not evalbn)
         C = sp.conv.out_channels
         bag.put(sp.bn.weight, dgamma[:C])
         bag.put(sp.bn.bias, dbeta[:C])
-        _conv_param_grads(bag, sp.conv, rec["x"], draw, bias_grad_is_zero=True)
+        # running-statistics BatchNorm: d(raw) = scale * gz, so the conv bias gradient is scale * sum(gz) = scale * dbeta
+        _conv_param_grads(bag, sp.conv, rec["x"], draw, bias_grad_is_zero=not evalbn,
+                          bias_grad=(rec["scale"] * dbeta) if evalbn else None)
         if i > stop or (i == 0 and need_input_grad):
             _, g, _ = _dgrad(sp.conv, draw, want_f32=True, want_split=False)
         else:
@@ -245,30 +231,32 @@ class _ModelSPFn(torch.autograd.Function):
         specs_t, _ = engine.parse_sequential(model.features_t)
         ts = _trunk_stream(x_s.device)
         if ts is None:
-            a_s = ops.to_split(x_s, _first_cp(specs_s[0].conv))
-            a_t = ops.to_split(x_t, _first_cp(specs_t[0].conv))
-            for sp in specs_s:
-                a_s = engine.run_conv_spec(a_s, sp, saved_s)
-            for sp in specs_t:
-                a_t = engine.run_conv_spec(a_t, sp, saved_t)
+            fus_w = model.fusion.weight.requires_grad
+            a_s = ops.to_split(x_s, _first_cp(specs_s[0].conv), xb=_req(specs_s[0].conv.weight))
+            a_t = ops.to_split(x_t, _first_cp(specs_t[0].conv), xb=_req(specs_t[0].conv.weight))
+            for sp, xb in zip(specs_s, engine.xb_flags(specs_s, fus_w)):
+                a_s = engine.run_conv_spec(a_s, sp, saved_s, xb)
+            for sp, xb in zip(specs_t, engine.xb_flags(specs_t, fus_w)):
+                a_t = engine.run_conv_spec(a_t, sp, saved_t, xb)
         else:
             main = torch.cuda.current_stream(x_s.device)
             ts.wait_stream(main)                       # inputs and re-packed weights were produced on the main stream
             box_s, box_t = [None], [None]
 
             def trunk(x, specs, saved, box):
-                box[0] = ops.to_split(x, _first_cp(specs[0].conv))
+                box[0] = ops.to_split(x, _first_cp(specs[0].conv), xb=_req(specs[0].conv.weight))
                 yield
-                for sp in specs:
-                    box[0] = engine.run_conv_spec(box[0], sp, saved)
+                for sp, xb in zip(specs, engine.xb_flags(specs, model.fusion.weight.requires_grad)):
+                    box[0] = engine.run_conv_spec(box[0], sp, saved, xb)
                     yield
 
             _alternate(trunk(x_s, specs_s, saved_s, box_s), trunk(x_t, specs_t, saved_t, box_t), ts)
             a_s, a_t = box_s[0], box_t[0]
             x_t.record_stream(ts)
             main.wait_stream(ts)                       # the fusion layer reads both trunks
-            for t in (a_t.hi, a_t.lo):
-                t.record_stream(main)
+            for t in (a_t.hi, a_t.lo, a_t.xb):
+                if t is not None:
+                    t.record_stream(main)
         # forward hooks registered on the trunks (AT.py:105 idiom) still fire, with detached NCHW views
         for mod, act in ((model.features_s, a_s), (model.features_t, a_t)):
             if mod._forward_hooks:
@@ -296,10 +284,9 @@ class _ModelSPFn(torch.autograd.Function):
         g = relu_sequential_backward(dspecs, dsaved, gpre, bag, upstream_need)
         if upstream_need:
             bn = model.bn
-            if "mean" not in tail:
-                raise NotImplementedError("egaze: backward through model_SP.bn in eval mode is not on the hot path")
+            evalbn = bool(tail.get("eval"))
             _, dmx, dgamma, dbeta = ops.bn_bwd(tail["mx"], g, tail["scale"], tail["shift"], tail["mean"], tail["invstd"],
-                                               pool=False, relu=True, want_f32=True, want_split=False)
+                                               pool=False, relu=True, want_f32=True, want_split=False, batch_stats=not evalbn)
             bag.put(bn.weight, dgamma)
             bag.put(bn.bias, dbeta)
             d2 = ops.pairmax_bwd(tail["raw2"], dmx)  # [2B,14,14,512] split: gradient routed to the arg-max stream
@@ -307,10 +294,13 @@ class _ModelSPFn(torch.autograd.Function):
             if _req(fus.weight):
                 bag.put(fus.weight, _wgrad(tail["cat"], d2, fus.out_channels, fus.in_channels))
             if _req(fus.bias):
-                bag.put(fus.bias, torch.zeros_like(fus.bias))  # feeds model_SP.bn in batch-stat mode: exactly zero
+                if evalbn:   # the shared conv's bias reaches the output through whichever stream won the max: sum of d(mx)
+                    bag.put(fus.bias, tail["scale"] * dbeta)
+                else:
+                    bag.put(fus.bias, torch.zeros_like(fus.bias))  # feeds model_SP.bn in batch-stat mode: exactly zero
             if trunk_need:
                 wpack = ops.pack_cache.get(fus.weight, 1, cols_p=d2.Cp)
-                _, gf, _ = ops.conv3x3(_hi_only(d2), wpack, want_f32=True, want_split=False)
+                _, gf, _ = ops.conv3x3(d2, wpack, want_f32=True, want_split=False)
                 B = gf.shape[0] // 2
                 g_s, g_t = gf[:B], gf[B:]
                 ts = _trunk_stream(gf.device)
@@ -354,9 +344,9 @@ class _SequentialFn(torch.autograd.Function):
         if tail is not None or any(sp.bn is None for sp in specs):
             raise NotImplementedError("egaze: stand-alone training is implemented for conv+BN+ReLU trunks")
         saved = []
-        act = ops.to_split(x, _first_cp(specs[0].conv))
-        for sp in specs:
-            act = engine.run_conv_spec(act, sp, saved)
+        act = ops.to_split(x, _first_cp(specs[0].conv), xb=_req(specs[0].conv.weight))
+        for sp, xb in zip(specs, engine.xb_flags(specs)):
+            act = engine.run_conv_spec(act, sp, saved, xb)
         ctx.seq, ctx.rec, ctx.need_x = seq, (specs, saved), x.requires_grad
         y = ops.from_split(act)
         ctx.out_act = act
@@ -387,13 +377,13 @@ class _VGGFn(torch.autograd.Function):
         ops.pack_cache.refresh()   # one launch re-packs every weight copy the optimiser step made stale
         specs, _ = engine.parse_sequential(model.features)
         saved_f, saved_d = [], []
-        act = ops.to_split(x, _first_cp(specs[0].conv))
-        for sp in specs:
-            act = engine.run_conv_spec(act, sp, saved_f)
-        feat_act = act
         dspecs, head = engine.parse_sequential(model.decoder)
-        for sp in dspecs:
-            act = engine.run_conv_spec(act, sp, saved_d)
+        act = ops.to_split(x, _first_cp(specs[0].conv), xb=_req(specs[0].conv.weight))
+        for sp, xb in zip(specs, engine.xb_flags(specs, dspecs[0].conv.weight.requires_grad)):
+            act = engine.run_conv_spec(act, sp, saved_f, xb)
+        feat_act = act
+        for sp, xb in zip(dspecs, engine.xb_flags(dspecs)):
+            act = engine.run_conv_spec(act, sp, saved_d, xb)
         out = ops.head_fwd(act, head.weight, head.bias)
         ctx.model, ctx.rec, ctx.need_x = model, (specs, saved_f, dspecs, saved_d, head, act, out), x.requires_grad
         if model.return_features:

@@ -56,16 +56,18 @@ def _bn_uses_batch_stats(bn):
     return bn.training or (bn.running_mean is None and bn.running_var is None)
 
 
-def run_conv_spec(act, spec, saved=None):
-    """Execute one ConvSpec on a split activation.  `saved` (list) collects what backward needs."""
+def run_conv_spec(act, spec, saved=None, xb=False):
+    """Execute one ConvSpec on a split activation.  `saved` (list) collects what backward needs.  xb: the output feeds a conv
+    whose weight gradient will be computed, so (fp16 forward) it also carries its bf16 copy."""
     conv, bn = spec.conv, spec.bn
+    xb = ops.want_xb(xb)
     cout_p = ops.pad_channels(conv.out_channels) if conv.out_channels % 16 else conv.out_channels
-    wpack = ops.pack_cache.get(conv.weight, 0, rows_p=cout_p, cols_p=act.Cp)
+    wpack = ops.pack_cache.get(conv.weight, 0, rows_p=cout_p, cols_p=act.Cp, fmt=act.fmt)
     bias = conv.bias.detach() if conv.bias is not None else None
     if bias is not None and cout_p != conv.out_channels:
         bias = torch.cat([bias, bias.new_zeros(cout_p - conv.out_channels)])
     if bn is None:
-        out, _, _ = ops.conv3x3(act, wpack, bias=bias, relu=spec.relu, reduce=1 if spec.pool else 0, ups=spec.ups)
+        out, _, _ = ops.conv3x3(act, wpack, bias=bias, relu=spec.relu, reduce=1 if spec.pool else 0, ups=spec.ups, xb=xb)
         if saved is not None:
             saved.append({"x": act, "y": out})
         out.C = conv.out_channels
@@ -81,9 +83,21 @@ def run_conv_spec(act, spec, saved=None):
         if cout_p != C:
             rm = torch.cat([rm, rm.new_zeros(cout_p - C)])
             rv = torch.cat([rv, rv.new_ones(cout_p - C)])
+        if saved is not None:
+            # eval-mode BatchNorm with autograd on (stock nn.BatchNorm2d supports it): keep the raw conv output so that the
+            # backward can use the same kernels as the batch-statistics case, with the statistics terms switched off
+            if spec.ups:
+                raise RuntimeError("egaze: conv+BN followed by Upsample is not on the hot path")
+            _, raw, _ = ops.conv3x3(act, wpack, bias=bias, want_f32=True, want_split=False)
+            scale, shift = ops.bn_fold(gamma, beta, rm, rv, None, bn.eps)
+            out, _ = ops.bn_apply(raw, scale, shift, relu=spec.relu, pool=spec.pool, xb=xb)
+            saved.append({"x": act, "raw": raw, "mean": rm.detach(), "invstd": torch.rsqrt(rv.detach() + bn.eps), "scale": scale,
+                          "shift": shift, "y": out, "eval": True})
+            out.C = C
+            return out
         scale, shift = ops.bn_fold(gamma, beta, rm, rv, bias, bn.eps)
         out, _, _ = ops.conv3x3(act, wpack, scale=scale, shift=shift, relu=spec.relu, reduce=1 if spec.pool else 0,
-                                ups=spec.ups)
+                                ups=spec.ups, xb=xb)
         if saved is not None:
             saved.append({"x": act, "y": out, "scale": scale})
         out.C = C
@@ -106,18 +120,24 @@ def run_conv_spec(act, spec, saved=None):
         mean, invstd, scale, shift = ops.bn_finalize(st, cout_p, bn.eps, bn.momentum, gamma, beta, rm, rv)
     if bn.track_running_stats and bn.num_batches_tracked is not None:
         bn.num_batches_tracked.add_(1)
-    out, _ = ops.bn_apply(raw, scale, shift, relu=spec.relu, pool=spec.pool)
+    out, _ = ops.bn_apply(raw, scale, shift, relu=spec.relu, pool=spec.pool, xb=xb)
     if saved is not None:
         saved.append({"x": act, "raw": raw, "mean": mean, "invstd": invstd, "scale": scale, "shift": shift, "y": out})
     out.C = C
     return out
 
 
-def run_sequential(seq, act, saved=None):
+def xb_flags(specs, after_last=False, recording=True):
+    """Per spec: does its OUTPUT need the bf16 copy, i.e. will the NEXT conv's weight gradient be computed?"""
+    flags = [recording and specs[i + 1].conv.weight.requires_grad for i in range(len(specs) - 1)]
+    return flags + [bool(recording and after_last)]
+
+
+def run_sequential(seq, act, saved=None, xb_after_last=False):
     """Run a reference-style Sequential of 3x3 convs.  Returns (act, tail_1x1_conv | None)."""
     specs, tail = parse_sequential(seq)
-    for spec in specs:
-        act = run_conv_spec(act, spec, saved)
+    for spec, xb in zip(specs, xb_flags(specs, xb_after_last, saved is not None)):
+        act = run_conv_spec(act, spec, saved, xb)
     return act, tail
 
 
@@ -129,7 +149,8 @@ def attach_act(t, act):
 
 def get_act(t, Cp=None):
     act = getattr(t, "_egaze_act", None)
-    if act is not None and act.N == t.shape[0] and act.C == t.shape[1] and (Cp is None or act.Cp == Cp):
+    if act is not None and act.N == t.shape[0] and act.C == t.shape[1] and (Cp is None or act.Cp == Cp) \
+            and act.fmt == ops.mode()["fwd_fmt"]:
         return act
     return ops.to_split(t, Cp)
 
@@ -139,8 +160,9 @@ def run_sp_tail(model, a_s, a_t, saved=None):
     """models/model_SP.py:38-49.  a_s / a_t: split conv5_3 activations of the spatial / temporal trunks."""
     B = a_s.N
     fusion, bn = model.fusion, model.bn
-    cat = ops.Act(torch.cat([a_s.hi, a_t.hi], 0), torch.cat([a_s.lo, a_t.lo], 0), a_s.C)  # depth order (s, t): model_SP.py:40
-    wpack = ops.pack_cache.get(fusion.weight, 0, cols_p=cat.Cp)
+    xb_cat = torch.cat([a_s.xb, a_t.xb], 0) if (a_s.xb is not None and a_t.xb is not None) else None
+    cat = ops.Act(torch.cat([a_s.hi, a_t.hi], 0), torch.cat([a_s.lo, a_t.lo], 0), a_s.C, xb_cat)  # depth order (s, t): model_SP.py:40
+    wpack = ops.pack_cache.get(fusion.weight, 0, cols_p=cat.Cp, fmt=cat.fmt)
     bias = fusion.bias.detach() if fusion.bias is not None else None
     _, raw2, _ = ops.conv3x3(cat, wpack, bias=bias, want_f32=True, want_split=False)
     mx = ops.pairmax(raw2)  # [B,14,14,512] fp32
@@ -158,7 +180,9 @@ def run_sp_tail(model, a_s, a_t, saved=None):
         rec.update(mean=mean, invstd=invstd)
     else:
         scale, shift = ops.bn_fold(gamma, beta, bn.running_mean, bn.running_var, None, bn.eps)
-    act, _ = ops.bn_apply(mx, scale, shift, relu=True, pool=False)
+        rec.update(mean=bn.running_mean.detach(), invstd=torch.rsqrt(bn.running_var.detach() + bn.eps), eval=True)
+    dec0 = next(m for m in model.decoder.children() if isinstance(m, nn.Conv2d))
+    act, _ = ops.bn_apply(mx, scale, shift, relu=True, pool=False, xb=ops.want_xb(saved is not None and dec0.weight.requires_grad))
     rec.update(scale=scale, shift=shift, y=act)
     dec_saved = [] if saved is not None else None
     act, tail = run_sequential(model.decoder, act, dec_saved)

@@ -10,27 +10,59 @@ from . import _lib
 from ._lib import call, stream_ptr
 
 BF16 = torch.bfloat16
+F16 = torch.float16
 F32 = torch.float32
+
+# Numeric modes (EGAZE_PRECISION).  Every tensor-core contraction accumulates in fp32 (TMEM); the modes differ in how the
+# fp32 operands are presented to the 16-bit tensor-core inputs:
+#   precise  (default) forward: fp16 hi+lo split of activations AND weights, 3 MMAs per product (hi*hi + hi*lo + lo*hi): 22
+#            significand bits, what train-mode BatchNorm needs for the 1e-3 gate.  Backward: gradients stay bf16
+#            (they need fp32's exponent range): data gradient dY_hi x [W_hi | W_lo] (2 MMAs), weight gradient dY_hi x X_hi
+#            (1 MMA).  Measured (tools/grad_modes.py): the cheaper backward moves the parameter gradients by a median 5e-3
+#            rel-L2, below the 1.4e-2 by which stock fp32 autograd itself differs from fp64 on the same step (ReLU / max-pool
+#            routing flips), and the errors do not compound in the weight gradients.
+#   precise3 round-1 scheme: bf16 hi+lo split (16 bits), 3 MMAs per product in forward, data and weight gradient.
+#   fast     one bf16 MMA per product everywhere -- reported, never gated.
+_MODES = {
+    "precise": dict(fwd_fmt=1, fwd_lo=True, w_lo=True, dy_lo=False, wgrad_precise=False,
+                    dtype="fp16 hi+lo split operands, 3 MMAs per product (forward); bf16 gradients: 2 MMAs per product (dgrad: "
+                          "dY_hi x W_hi+lo), 1 MMA (wgrad); fp32 accumulate"),
+    "precise3": dict(fwd_fmt=0, fwd_lo=True, w_lo=True, dy_lo=True, wgrad_precise=True,
+                     dtype="bf16 hi+lo split operands, 3 MMAs per product (fwd, dgrad, wgrad), fp32 accumulate"),
+    "fast": dict(fwd_fmt=0, fwd_lo=False, w_lo=False, dy_lo=False, wgrad_precise=False,
+                 dtype="bf16, 1 MMA per product, fp32 accumulate"),
+}
 
 
 def precision():
-    """'precise' (default): split-bf16 operands, 3 MMAs per product -- meets the 1e-3 parity gate.
-    'fast': single bf16 pass -- reported, never gated."""
     p = os.environ.get("EGAZE_PRECISION", "precise")
-    if p not in ("precise", "fast"):
-        raise RuntimeError("EGAZE_PRECISION must be 'precise' or 'fast', got %r" % p)
+    if p not in _MODES:
+        raise RuntimeError("EGAZE_PRECISION must be one of %s, got %r" % (sorted(_MODES), p))
     return p
 
 
+def mode():
+    return _MODES[precision()]
+
+
 def is_precise():
-    return precision() == "precise"
+    return precision() != "fast"
 
 
 def dtype_string():
     """What bench.py reports as `dtype`: the arithmetic type of the tensor-core contractions, MMAs per product included."""
-    if is_precise():
-        return "bf16 split hi+lo operands, 3 MMAs per product (fwd, dgrad, wgrad), fp32 accumulate"
-    return "bf16, 1 MMA per product, fp32 accumulate"
+    return mode()["dtype"]
+
+
+_wscale = [None]
+
+
+def f16_weight_scale():
+    if _wscale[0] is None:
+        v = ctypes.c_float(0.0)
+        call("egaze_f16_weight_scale", ctypes.addressof(v))
+        _wscale[0] = float(v.value)
+    return _wscale[0]
 
 
 def pad_channels(c):
@@ -43,11 +75,18 @@ def pad_channels(c):
 
 
 class Act(object):
-    """NHWC split-bf16 activation: x ~= hi + lo.  `C` = logical channels, hi.shape[-1] = padded channels."""
-    __slots__ = ("hi", "lo", "C")
+    """NHWC split activation: x ~= hi + lo, both planes bf16 (gradients; round-1 forward) or fp16 (forward operands).
+    `xb` (optional) = bf16(x): what the weight-gradient GEMM reads when hi / lo are fp16.  `C` = logical channels,
+    hi.shape[-1] = padded channels."""
+    __slots__ = ("hi", "lo", "C", "xb")
 
-    def __init__(self, hi, lo, C):
-        self.hi, self.lo, self.C = hi, lo, C
+    def __init__(self, hi, lo, C, xb=None):
+        self.hi, self.lo, self.C, self.xb = hi, lo, C, xb
+
+    @property
+    def fmt(self):
+        """0 = bf16 planes, 1 = fp16 planes (the C-ABI's `fmt`)."""
+        return 1 if self.hi.dtype == F16 else 0
 
     @property
     def N(self):
@@ -66,20 +105,36 @@ class Act(object):
         return self.hi.shape[3]
 
 
-def empty_act(N, H, W, Cp, C, device, lo=True):
-    hi = torch.empty((N, H, W, Cp), dtype=BF16, device=device)
-    lo_t = torch.empty((N, H, W, Cp), dtype=BF16, device=device) if lo else None
-    return Act(hi, lo_t, C)
+def empty_act(N, H, W, Cp, C, device, lo=True, fmt=0, xb=False):
+    dt = F16 if fmt else BF16
+    hi = torch.empty((N, H, W, Cp), dtype=dt, device=device)
+    lo_t = torch.empty((N, H, W, Cp), dtype=dt, device=device) if lo else None
+    xb_t = torch.empty((N, H, W, Cp), dtype=BF16, device=device) if xb else None
+    return Act(hi, lo_t, C, xb_t)
 
 
-def to_split(x, Cp=None):
-    """NCHW fp32 -> Act (channels zero-padded to Cp)."""
+def want_xb(flag):
+    """A forward activation needs its bf16 copy iff a weight gradient will read it and the forward planes are fp16."""
+    return bool(flag) and mode()["fwd_fmt"] == 1
+
+
+def to_split(x, Cp=None, fmt=None, xb=False):
+    """NCHW fp32 -> Act (channels zero-padded to Cp) in the forward operand format of the current mode."""
     _lib.check_device(x.device)
     x = x.contiguous().float()
     N, C, H, W = x.shape
     Cp = pad_channels(C) if Cp is None else Cp
-    act = empty_act(N, H, W, Cp, C, x.device, lo=True)
-    call("egaze_nchw_to_nhwc_split", x, N, C, H, W, Cp, act.hi, act.lo, stream_ptr())
+    fmt = mode()["fwd_fmt"] if fmt is None else fmt
+    act = empty_act(N, H, W, Cp, C, x.device, lo=True, fmt=fmt, xb=xb and fmt == 1)
+    call("egaze_nchw_to_nhwc_split", x, N, C, H, W, Cp, act.hi, act.lo, act.xb, fmt, stream_ptr())
+    return act
+
+
+def grad_split(x, Cp=None):
+    """NCHW fp32 gradient -> bf16 Act (gradients keep bf16's exponent range; the lo plane exists only in modes that use it)."""
+    act = to_split(x, Cp, fmt=0)
+    if not mode()["dy_lo"]:
+        act.lo = None
     return act
 
 
@@ -87,7 +142,7 @@ def from_split(act, C=None):
     """Act -> NCHW fp32 [N, C, H, W]."""
     C = act.C if C is None else C
     out = torch.empty((act.N, C, act.H, act.W), dtype=F32, device=act.hi.device)
-    call("egaze_nhwc_to_nchw", act.hi, act.lo, None, act.N, C, act.H, act.W, act.Cp, out, stream_ptr())
+    call("egaze_nhwc_to_nchw", act.hi, act.lo, None, act.N, C, act.H, act.W, act.Cp, act.fmt, out, stream_ptr())
     return out
 
 
@@ -103,7 +158,7 @@ def nhwc_f32_to_nchw(x, C=None):
     N, H, W, Cs = x.shape
     C = Cs if C is None else C
     out = torch.empty((N, C, H, W), dtype=F32, device=x.device)
-    call("egaze_nhwc_to_nchw", None, None, x, N, C, H, W, Cs, out, stream_ptr())
+    call("egaze_nhwc_to_nchw", None, None, x, N, C, H, W, Cs, 0, out, stream_ptr())
     return out
 
 
@@ -115,11 +170,11 @@ def nchw_to_nhwc_f32(x):
     return out
 
 
-def f32_to_split(x_nhwc, C=None):
+def f32_to_split(x_nhwc, C=None, fmt=0):
     x_nhwc = x_nhwc.contiguous()
     N, H, W, Cs = x_nhwc.shape
-    act = empty_act(N, H, W, Cs, Cs if C is None else C, x_nhwc.device, lo=True)
-    call("egaze_f32_to_split", x_nhwc, x_nhwc.numel(), act.hi, act.lo, stream_ptr())
+    act = empty_act(N, H, W, Cs, Cs if C is None else C, x_nhwc.device, lo=True, fmt=fmt)
+    call("egaze_f32_to_split", x_nhwc, x_nhwc.numel(), act.hi, act.lo, fmt, stream_ptr())
     return act
 
 
@@ -136,10 +191,15 @@ class _PackCache(object):
         cols = Ci if mode == 0 else Co
         return Co, Ci, rows, (rows if rows_p is None else rows_p), (pad_channels(cols) if cols_p is None else cols_p)
 
-    def get(self, w, mode, rows_p=None, cols_p=None):
-        """w: nn.Conv2d weight [Co, Ci, 3, 3] (or Conv3d [Co, Ci, 1, 3, 3]).  Returns (hi, lo, rows, cols_p)."""
+    def get(self, w, mode, rows_p=None, cols_p=None, fmt=None):
+        """w: nn.Conv2d weight [Co, Ci, 3, 3] (or Conv3d [Co, Ci, 1, 3, 3]).  mode 0: forward operand, 1: flipped / transposed
+        (data gradient).  fmt 1: fp16 planes pre-scaled by f16_weight_scale(); default: the numeric mode's forward format for
+        mode 0, bf16 for mode 1.  Returns (hi, lo, rows, cols_p, fmt)."""
+        if fmt is None:
+            fmt = _MODES[precision()]["fwd_fmt"] if mode == 0 else 0
         Co, Ci, rows, rp, cp = self._dims(w, mode, rows_p, cols_p)
-        key = (id(w), mode, rp, cp)
+        dt = F16 if fmt else BF16
+        key = (id(w), mode, rp, cp, fmt)
         ent = self._d.get(key)
         ver = w._version
         if ent is not None and ent[0]() is w and ent[1] == ver and ent[2] == w.data_ptr():
@@ -150,19 +210,19 @@ class _PackCache(object):
             if ent is not None and ent[3][0].shape == (9, rp, cp) and ent[3][0].device == w.device:
                 hi, lo = ent[3][0], ent[3][1]
             else:
-                hi = torch.empty((9, rp, cp), dtype=BF16, device=w.device)
-                lo = torch.empty((9, rp, cp), dtype=BF16, device=w.device)
-            call("egaze_pack_w3x3", w4, Co, Ci, cp, mode, hi, lo, stream_ptr())
+                hi = torch.empty((9, rp, cp), dtype=dt, device=w.device)
+                lo = torch.empty((9, rp, cp), dtype=dt, device=w.device)
+            call("egaze_pack_w3x3", w4, Co, Ci, cp, mode, fmt, hi, lo, stream_ptr())
         else:
-            hi = torch.zeros((9, rp, cp), dtype=BF16, device=w.device)
-            lo = torch.zeros((9, rp, cp), dtype=BF16, device=w.device)
-            # padded rows (tiny layers only, e.g. LF 32->8): pack densely then copy into the padded buffer
-            thi = torch.empty((9, rows, cp), dtype=BF16, device=w.device)
-            tlo = torch.empty((9, rows, cp), dtype=BF16, device=w.device)
-            call("egaze_pack_w3x3", w4, Co, Ci, cp, mode, thi, tlo, stream_ptr())
+            hi = torch.zeros((9, rp, cp), dtype=dt, device=w.device)
+            lo = torch.zeros((9, rp, cp), dtype=dt, device=w.device)
+            # padded rows (tiny layers only): pack densely then copy into the padded buffer
+            thi = torch.empty((9, rows, cp), dtype=dt, device=w.device)
+            tlo = torch.empty((9, rows, cp), dtype=dt, device=w.device)
+            call("egaze_pack_w3x3", w4, Co, Ci, cp, mode, fmt, thi, tlo, stream_ptr())
             hi[:, :rows].copy_(thi)
             lo[:, :rows].copy_(tlo)
-        val = (hi, lo, rp, cp)
+        val = (hi, lo, rp, cp, fmt)
         self._d[key] = (weakref.ref(w), ver, w.data_ptr(), val)
         return val
 
@@ -186,7 +246,7 @@ class _PackCache(object):
             if w is None or ent[2] != w.data_ptr():
                 del self._d[key]
                 continue
-            _, mode, rp, cp = key
+            _, mode, rp, cp, _fmt = key
             Co, Ci, rows, _, _ = self._dims(w, mode, rp, cp)
             if ent[1] != w._version and rp == rows and w.is_contiguous() and w.dtype == F32:
                 stale.append((key, ent, w, Co, Ci, rows))
@@ -198,8 +258,8 @@ class _PackCache(object):
             import numpy as np
             rec = np.zeros((len(stale), 6), dtype=np.int64)
             for i, (key, ent, w, Co, Ci, rows) in enumerate(stale):
-                hi, lo, rp, cp = ent[3]
-                rec[i] = (w.data_ptr(), hi.data_ptr(), lo.data_ptr(), Co | (Ci << 32), rows | (cp << 32), key[1])
+                hi, lo, rp, cp, fmt = ent[3]
+                rec[i] = (w.data_ptr(), hi.data_ptr(), lo.data_ptr(), Co | (Ci << 32), rows | (cp << 32), key[1] | (fmt << 32))
             # Tables are never freed behind a CUDA graph's back: a captured egaze_pack_w3x3_multi launch has this table's
             # address baked in.  Old tables age out of a small LRU; graphs keep their own references (held_tables()).
             while len(self._tables) >= 16:
@@ -259,32 +319,41 @@ def conv_stats_shape(Cout, precise):
 
 
 def conv3x3(act, wpack, bias=None, scale=None, shift=None, relu=False, reduce=0, ups=False, mask=None,
-            want_f32=False, want_split=True, stats=False, precise=None, mask_ups=False, colsum=None):
-    """3x3/pad-1 conv on the tcgen05 path.  wpack = (w_hi, w_lo, Cout_p, Cin_p) from pack_cache.
+            want_f32=False, want_split=True, stats=False, mask_ups=False, colsum=None, want_lo=True, xb=False):
+    """3x3/pad-1 conv on the tcgen05 path.  wpack = (w_hi, w_lo, Cout_p, Cin_p, fmt) from pack_cache, in the activation's format.
+    The operand mode follows from the planes present (and the numeric mode): act.lo given -> 3 MMAs per product, act.lo None ->
+    act.hi x [w_hi | w_lo] (2), `fast` -> 1.  The split output has the input's format (a forward activation stays fp16, a
+    gradient stays bf16); want_lo=False writes the hi plane only (bf16), xb=True adds the bf16 copy (fp16 outputs).
     colsum: optional [Cout] fp32 tensor the kernel ADDS the per-channel sums of the stored values to.
     Returns (out_act | None, out_f32 | None, (stats_partial, stats_cnt) | None)."""
-    w_hi, w_lo, Cout, Cin_p = wpack
+    w_hi, w_lo, Cout, Cin_p, wfmt = wpack
     if Cin_p != act.Cp:
         raise RuntimeError("egaze: conv3x3 channel mismatch: activation Cp=%d, weight Cin_p=%d" % (act.Cp, Cin_p))
-    precise = is_precise() if precise is None else precise
+    fmt = act.fmt
+    if wfmt != fmt:
+        raise RuntimeError("egaze: conv3x3 operand formats differ (activation %s, weights %s)" % (act.hi.dtype, w_hi.dtype))
+    md = mode()
+    use_wlo = md["w_lo"]
+    x_lo = act.lo if (use_wlo and md["fwd_lo"] and act.lo is not None) else None
     N, H, W = act.N, act.H, act.W
     dev = act.hi.device
     Ho, Wo = (H // 2, W // 2) if reduce else (H, W)
     if ups:
         Ho, Wo = Ho * 2, Wo * 2
-    out_act = empty_act(N, Ho, Wo, Cout, Cout, dev, lo=True) if want_split else None
+    out_act = empty_act(N, Ho, Wo, Cout, Cout, dev, lo=want_lo or fmt == 1, fmt=fmt, xb=xb and fmt == 1) if want_split else None
     out_f32 = torch.empty((N, Ho, Wo, Cout), dtype=F32, device=dev) if want_f32 else None
     st = None
     if stats:
-        parts, cs, cd = conv_stats_shape(Cout, precise)
+        parts, cs, cd = conv_stats_shape(Cout, use_wlo)
         st = (torch.empty((parts, 2, Cout), dtype=F32, device=dev), torch.zeros((parts, cs), dtype=F32, device=dev), cs, cd)
     if _conv_timer["on"]:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-    call("egaze_conv3x3_tc", act.hi, act.lo if precise else None, w_hi, w_lo if precise else None, N, H, W, Cin_p, Cout,
+    call("egaze_conv3x3_tc", act.hi, x_lo, w_hi, w_lo if use_wlo else None, N, H, W, Cin_p, Cout,
          bias, scale, shift, int(relu), int(reduce), int(ups), mask, int(mask_ups), out_f32,
          out_act.hi if out_act is not None else None, out_act.lo if out_act is not None else None,
-         st[0] if st else None, st[1] if st else None, colsum, int(precise), stream_ptr())
+         out_act.xb if out_act is not None else None,
+         st[0] if st else None, st[1] if st else None, colsum, fmt, fmt, (1.0 / f16_weight_scale()) if fmt else 1.0, stream_ptr())
     if _conv_timer["on"]:
         ev1.record()
         _conv_timer["events"].append((ev0, ev1, ("conv", N, H, W, Cin_p, Cout, int(reduce), int(ups), bool(stats))))
@@ -321,14 +390,17 @@ def col_stats(x2d):
     return partial, cnt, 1, C
 
 
-def bn_apply(x_nhwc, scale, shift, relu=True, pool=False, want_f32=False, want_split=True):
+def bn_apply(x_nhwc, scale, shift, relu=True, pool=False, want_f32=False, want_split=True, xb=False):
+    """Normalise (+ReLU, +2x2 max-pool) a raw conv output into the next conv's operand (forward format of the current mode)."""
     N, H, W, C = x_nhwc.shape
     Ho, Wo = (H // 2, W // 2) if pool else (H, W)
     dev = x_nhwc.device
-    out_act = empty_act(N, Ho, Wo, C, C, dev, lo=True) if want_split else None
+    fmt = mode()["fwd_fmt"]
+    out_act = empty_act(N, Ho, Wo, C, C, dev, lo=True, fmt=fmt, xb=xb and fmt == 1) if want_split else None
     out_f32 = torch.empty((N, Ho, Wo, C), dtype=F32, device=dev) if want_f32 else None
     call("egaze_bn_apply", x_nhwc, N, H, W, C, scale, shift, int(relu), int(pool), out_f32,
-         out_act.hi if out_act is not None else None, out_act.lo if out_act is not None else None, stream_ptr())
+         out_act.hi if out_act is not None else None, out_act.lo if out_act is not None else None,
+         out_act.xb if out_act is not None else None, fmt, stream_ptr())
     return out_act, out_f32
 
 
@@ -346,8 +418,8 @@ def head_fwd(act, w, b, want_logit=False):
     out = torch.empty((N, 1, H, W), dtype=F32, device=act.hi.device)
     logit = torch.empty((N, 1, H, W), dtype=F32, device=act.hi.device) if want_logit else None
     wf = w.detach().reshape(-1).contiguous().float()
-    call("egaze_head_fwd", act.hi, act.lo, wf, b.detach() if b is not None else None, wf.numel(), act.Cp, N * H * W, out,
-         logit, stream_ptr())
+    call("egaze_head_fwd", act.hi, act.lo, act.fmt, wf, b.detach() if b is not None else None, wf.numel(), act.Cp, N * H * W,
+         out, logit, stream_ptr())
     return (out, logit) if want_logit else out
 
 
@@ -356,20 +428,36 @@ def repad(act, Cp):
     """Same activation with the channel stride padded (zeros) to Cp (wgrad needs 64-channel K chunks)."""
     if act.Cp == Cp:
         return act
-    hi = torch.zeros((act.N, act.H, act.W, Cp), dtype=BF16, device=act.hi.device)
-    hi[..., :act.Cp].copy_(act.hi)
-    lo = None
-    if act.lo is not None:
-        lo = torch.zeros((act.N, act.H, act.W, Cp), dtype=BF16, device=act.hi.device)
-        lo[..., :act.Cp].copy_(act.lo)
-    return Act(hi, lo, act.C)
+
+    def pad(t):
+        if t is None:
+            return None
+        o = torch.zeros((act.N, act.H, act.W, Cp), dtype=t.dtype, device=t.device)
+        o[..., :act.Cp].copy_(t)
+        return o
+    return Act(pad(act.hi), pad(act.lo), act.C, pad(act.xb))
+
+
+def wgrad_operands(x_act, dy_act, precise=None):
+    """The bf16 planes the weight-gradient GEMM multiplies: (x_hi, x_lo | None, dy_hi, dy_lo | None, precise)."""
+    precise = mode()["wgrad_precise"] if precise is None else precise
+    if dy_act.fmt != 0:
+        raise RuntimeError("egaze: gradients are bf16 planes")
+    if x_act.fmt == 1:
+        if x_act.xb is None:
+            raise RuntimeError("egaze: wgrad of an fp16 forward activation needs its bf16 copy (Act.xb)")
+        return x_act.xb, None, dy_act.hi, None, False
+    if precise and (x_act.lo is None or dy_act.lo is None):
+        precise = False
+    return x_act.hi, (x_act.lo if precise else None), dy_act.hi, (dy_act.lo if precise else None), precise
 
 
 def wgrad3x3(x_act, dy_act, Cout, Cin, precise=None):
-    """dW (OIHW fp32 [Cout, Cin, 3, 3]) of a 3x3/pad-1 conv from its input activation and output gradient."""
-    precise = is_precise() if precise is None else precise
+    """dW (OIHW fp32 [Cout, Cin, 3, 3]) of a 3x3/pad-1 conv from its input activation and output gradient (bf16 planes).
+    precise (default: the numeric mode's choice): dY_hi*X_hi + dY_hi*X_lo + dY_lo*X_hi, else dY_hi * bf16(X) (1 MMA)."""
     x_act = repad(x_act, (x_act.Cp + 63) // 64 * 64)
     dy_act = repad(dy_act, (dy_act.Cp + 63) // 64 * 64)
+    x_hi, x_lo, dy_hi, dy_lo, precise = wgrad_operands(x_act, dy_act, precise)
     N, H, W = x_act.N, x_act.H, x_act.W
     dev = x_act.hi.device
     # persistent accumulator per shape: allocated zeroed once, left zeroed again by egaze_unpack_wgrad (clear=1)
@@ -382,8 +470,7 @@ def wgrad3x3(x_act, dy_act, Cout, Cin, precise=None):
     if _conv_timer["on"]:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-    call("egaze_wgrad3x3_tc", x_act.hi, x_act.lo if precise else None, dy_act.hi, dy_act.lo if precise else None, N, H, W,
-         x_act.Cp, dy_act.Cp, dwp, int(precise), stream_ptr())
+    call("egaze_wgrad3x3_tc", x_hi, x_lo, dy_hi, dy_lo, N, H, W, x_act.Cp, dy_act.Cp, dwp, int(precise), stream_ptr())
     if _conv_timer["on"]:
         ev1.record()
         _conv_timer["events"].append((ev0, ev1, ("wgrad", N, H, W, x_act.Cp, dy_act.Cp, 0, 0, False)))
@@ -396,8 +483,9 @@ _dwp_cache = {}
 _bn_bwd_nblk = [None]
 
 
-def bn_bwd(raw, g, scale, shift, mean, invstd, pool, relu, want_f32=False, want_split=True):
+def bn_bwd(raw, g, scale, shift, mean, invstd, pool, relu, want_f32=False, want_split=True, batch_stats=True):
     """BatchNorm(+ReLU)(+MaxPool) backward.  raw: conv output NHWC fp32; g: grad w.r.t. the layer output (pooled res).
+    batch_stats=False: the forward normalised with running statistics (mean / invstd are those).
     -> (draw Act | None, draw f32 | None, dgamma, dbeta)"""
     N, H, W, C = raw.shape
     dev = raw.device
@@ -411,16 +499,17 @@ def bn_bwd(raw, g, scale, shift, mean, invstd, pool, relu, want_f32=False, want_
     g = g.contiguous()
     call("egaze_bn_bwd_reduce", raw, g, N, H, W, C, scale, shift, mean, invstd, int(pool), int(relu), partial, dgamma,
          dbeta, stream_ptr())
-    out_act = empty_act(N, H, W, C, C, dev, lo=True) if want_split else None
+    out_act = empty_act(N, H, W, C, C, dev, lo=mode()["dy_lo"]) if want_split else None
     out_f32 = torch.empty((N, H, W, C), dtype=F32, device=dev) if want_f32 else None
-    call("egaze_bn_bwd_apply", raw, g, N, H, W, C, scale, shift, mean, invstd, dgamma, dbeta, int(pool), int(relu), out_f32,
+    call("egaze_bn_bwd_apply", raw, g, N, H, W, C, scale, shift, mean, invstd, dgamma, dbeta, int(pool), int(relu),
+         int(batch_stats), out_f32,
          out_act.hi if out_act is not None else None, out_act.lo if out_act is not None else None, stream_ptr())
     return out_act, out_f32, dgamma, dbeta
 
 
 def pairmax_bwd(raw2, dmx):
     B2 = raw2.shape[0]
-    act = empty_act(B2, raw2.shape[1], raw2.shape[2], raw2.shape[3], raw2.shape[3], raw2.device, lo=True)
+    act = empty_act(B2, raw2.shape[1], raw2.shape[2], raw2.shape[3], raw2.shape[3], raw2.device, lo=mode()["dy_lo"])
     call("egaze_pairmax_bwd", raw2, dmx.contiguous(), dmx.numel(), act.hi, act.lo, stream_ptr())
     return act
 
@@ -435,11 +524,11 @@ def col_sum(act, C=None):
 def head_bwd(act, w, y, gy, relu_mask=True):
     """Backward of sigmoid(conv1x1(act)).  -> (dx Act, dw [C], db [1])"""
     dev = act.hi.device
-    dx = empty_act(act.N, act.H, act.W, act.Cp, act.C, dev, lo=True)
+    dx = empty_act(act.N, act.H, act.W, act.Cp, act.C, dev, lo=mode()["dy_lo"])
     wf = w.detach().reshape(-1).contiguous().float()
     dw = torch.zeros((wf.numel(),), dtype=F32, device=dev)
     db = torch.zeros((1,), dtype=F32, device=dev)
-    call("egaze_head_bwd", act.hi, act.lo, wf, wf.numel(), act.Cp, act.N * act.H * act.W, y.contiguous(),
+    call("egaze_head_bwd", act.hi, act.lo, act.fmt, wf, wf.numel(), act.Cp, act.N * act.H * act.W, y.contiguous(),
          gy.contiguous().float(), int(relu_mask), dx.hi, dx.lo, dw, db, stream_ptr())
     return dx, dw, db
 

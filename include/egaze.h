@@ -11,8 +11,11 @@
  *     allocates or frees caller-visible memory.  `stream` is a cudaStream_t passed as void*.
  *   - launches are asynchronous and stream-ordered; no host synchronisation inside any entry point.
  *   - there is NO CPU fallback: a non-sm_100 device is an error (egaze_check_device).
- *   - "split" activations: NHWC bf16 planes hi and lo with x ~= hi + lo (16 mantissa bits).  lo may be NULL
- *     where documented ("fast" single-pass mode).
+ *   - "split" activations: two NHWC 16-bit planes hi and lo with x ~= hi + lo.  `fmt` / `*_f16` arguments name the element
+ *     format: 0 = bf16 (16 significand bits in all, fp32's exponent range: gradients), 1 = fp16 (22 bits: the forward
+ *     operands -- train-mode BatchNorm needs >= 19 for the 1e-3 parity gate).  lo may be NULL where
+ *     documented.  An "xb" plane is bf16(x): the copy the weight-gradient GEMM reads when hi / lo are fp16 (kind::f16 tensor
+ *     core instructions need both operands in the same format, and gradients stay bf16).
  */
 #ifndef EGAZE_H_
 #define EGAZE_H_
@@ -29,17 +32,20 @@ int egaze_sm_count(int* out);
 
 /* ---- layout (API tensors are NCHW fp32: reference SURVEY 8b "Tensor conventions") ---------------------------- */
 /* x [N][C][H][W] fp32 -> hi/lo [N][H][W][Cp] bf16, channels C..Cp-1 zero.  (input side of utils.py:70 / model_SP.py:36-37) */
-int egaze_nchw_to_nhwc_split(const float* x, int N, int C, int H, int W, int Cp, void* hi, void* lo, void* stream);
+int egaze_nchw_to_nhwc_split(const float* x, int N, int C, int H, int W, int Cp, void* hi, void* lo, void* xb, int fmt,
+                             void* stream);
 /* (hi[,lo]) or f32, NHWC with channel stride Cs -> out [N][C][H][W] fp32 (what forward hooks / callers see: AT.py:22,226) */
-int egaze_nhwc_to_nchw(const void* hi, const void* lo, const float* f32, int N, int C, int H, int W, int Cs, float* out,
-                       void* stream);
+int egaze_nhwc_to_nchw(const void* hi, const void* lo, const float* f32, int N, int C, int H, int W, int Cs, int fmt,
+                       float* out, void* stream);
 int egaze_nchw_to_nhwc_f32(const float* x, int N, int C, int H, int W, float* out, void* stream);
-int egaze_f32_to_split(const float* x, long long n, void* hi, void* lo, void* stream);
-/* nn.Conv2d weight OIHW fp32 -> packed split bf16.  mode 0 (fprop): [9][Cout][cols_p>=Cin];
- * mode 1 (dgrad): taps flipped, [9][Cin][cols_p>=Cout].  (weights of utils.py:70, model_SP.py:10,13-30, late_fusion.py:10-12) */
-int egaze_pack_w3x3(const float* w_oihw, int Cout, int Cin, int cols_p, int mode, void* hi, void* lo, void* stream);
+int egaze_f32_to_split(const float* x, long long n, void* hi, void* lo, int fmt, void* stream);
+/* nn.Conv2d weight OIHW fp32 -> packed split planes.  mode 0 (fprop): [9][Cout][cols_p>=Cin];
+ * mode 1 (dgrad): taps flipped, [9][Cin][cols_p>=Cout].  fmt 1: fp16 planes of w * egaze_f16_weight_scale (the conv is then
+ * called with acc_scale = 1 / that).  (weights of utils.py:70, model_SP.py:10,13-30) */
+int egaze_f16_weight_scale(float* out);
+int egaze_pack_w3x3(const float* w_oihw, int Cout, int Cin, int cols_p, int mode, int fmt, void* hi, void* lo, void* stream);
 /* egaze_pack_w3x3 for many weights in ONE launch.  jobs: device array of njobs 48-byte records
- * {const float* w; void* hi; void* lo; int Cout, Cin, rows, cols_p, mode, pad;} (rows = Cout for mode 0, Cin for mode 1). */
+ * {const float* w; void* hi; void* lo; int Cout, Cin, rows, cols_p, mode, fmt;} (rows = Cout for mode 0, Cin for mode 1). */
 int egaze_pack_w3x3_multi(const void* jobs, int njobs, void* stream);
 /* wgrad accumulator [9][Cout_p][Cin_p] fp32 -> OIHW grad, gw = beta*gw + dw; clear != 0 zeroes the accumulator afterwards */
 int egaze_unpack_wgrad(float* dwp, int Cout, int Cin, int Cout_p, int Cin_p, float beta, int clear, float* gw_oihw, void* stream);
@@ -56,17 +62,22 @@ int egaze_conv3x3_set_prof(void* buf);
 /* y = epilogue(conv3x3(x, w)):  v = acc + bias; v = v*scale + shift; relu; 2x2 reduce (1 max = MaxPool2d utils.py:68,
  * 2 sum = grad of nn.Upsample); mask (zero where mask <= 0: ReLU backward; mask_ups: the mask tensor is stored 2x upsampled);
  * 2x nearest replicate (ups: model_SP.py:16,20,24,27).
- *   x_hi/x_lo : [N][H][W][Cin_p] bf16        w_hi/w_lo : [9][Cout][Cin_p] bf16 (egaze_pack_w3x3)
- *   out_f32 / out_hi / out_lo : NHWC [N][Ho][Wo][Cout] (any non-NULL subset is written)
+ *   x_hi/x_lo : [N][H][W][Cin_p]             w_hi/w_lo : [9][Cout][Cin_p] (egaze_pack_w3x3); all four in the format in_f16
+ *   operand modes (MMAs per product): x_hi,x_lo,w_hi,w_lo -> hi*hi + hi*lo + lo*hi (3);  x_lo NULL -> x_hi*[w_hi|w_lo] (2:
+ *   the data-gradient mode);  x_lo and w_lo NULL -> 1
+ *   out_f32 / out_hi / out_lo / out_xb : NHWC [N][Ho][Wo][Cout] (any non-NULL subset is written; out_hi / out_lo in the format
+ *   out_f16, out_lo optional for bf16; out_xb = bf16(v), fp16 outputs only)
+ *   acc_scale : the accumulators are multiplied by it first (1 / egaze_f16_weight_scale for fp16 weights, else 1)
  *   stats / stats_cnt : per-CTA (mean, M2, n) partials of (acc + bias) for BatchNorm batch statistics (egaze_conv3x3_stats_shape)
  *   colsum : optional [Cout] fp32, ACCUMULATED: += sum over all output pixels of the final (masked) values.  When the
  *            kernel computes a data gradient this is the bias gradient of the conv that produced the masked activation,
  *            so no separate reduction pass over the gradient tensor is needed.
- *   precise != 0 : hi*hi + hi*lo + lo*hi (3 MMAs), needs x_lo and w_lo;  0 : single bf16 pass. */
+ */
 int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, int N, int H, int W,
                      int Cin_p, int Cout, const float* bias, const float* scale, const float* shift, int relu,
                      int reduce, int ups, const void* mask, int mask_ups, float* out_f32, void* out_hi, void* out_lo,
-                     float* stats, float* stats_cnt, float* colsum, int precise, void* stream);
+                     void* out_xb, float* stats, float* stats_cnt, float* colsum, int in_f16, int out_f16, float acc_scale,
+                     void* stream);
 /* Weight gradient: dwp[9][Cout][Cin_p] (fp32, ACCUMULATED: zero first) += sum_pixels dY (x) X-window; tcgen05 GEMM with the
  * pixel axis as K, MN-major operands straight from NHWC.  Cin_p % 64 == 0, Cout % 64 == 0.  (loss.backward(): SP.py:136) */
 int egaze_wgrad3x3_tc(const void* x_hi, const void* x_lo, const void* dy_hi, const void* dy_lo, int N, int H, int W,
@@ -83,7 +94,7 @@ int egaze_bn_fold(const float* gamma, const float* beta, const float* running_me
 int egaze_col_stats(const float* x, long long rows, int C, float* partial, float* cnt, void* stream);
 /* y = relu?(x*scale+shift) [-> MaxPool2d(2,2)] ; x NHWC fp32, outputs NHWC */
 int egaze_bn_apply(const float* x, int N, int H, int W, int C, const float* scale, const float* shift, int relu,
-                   int pool, float* out_f32, void* out_hi, void* out_lo, void* stream);
+                   int pool, float* out_f32, void* out_hi, void* out_lo, void* out_xb, int fmt, void* stream);
 /* out[b] = max(x[b], x[b+B]) : Conv3d(1,3,3)+MaxPool3d((2,1,1)) second half (model_SP.py:11,43) */
 int egaze_pairmax(const float* x, long long per_stream, float* out, void* stream);
 /* backward pieces (autograd of the modules above; loss.backward() in SP.py:136, LF.py:98, spatialstream.py:140) */
@@ -91,16 +102,20 @@ int egaze_bn_bwd_blocks(int* nblk);
 int egaze_bn_bwd_reduce(const float* raw, const float* g, int N, int H, int W, int C, const float* scale,
                         const float* shift, const float* mean, const float* invstd, int pool, int relu, float* partial,
                         float* dgamma, float* dbeta, void* stream);
+/* batch_stats = 0: the BatchNorm ran on its running statistics (eval mode): d(raw) = scale * gz, mean / invstd are the
+ * running mean and 1/sqrt(running_var + eps).  out_hi / out_lo: bf16 planes (out_lo may be NULL). */
 int egaze_bn_bwd_apply(const float* raw, const float* g, int N, int H, int W, int C, const float* scale,
                        const float* shift, const float* mean, const float* invstd, const float* dgamma,
-                       const float* dbeta, int pool, int relu, float* out_f32, void* out_hi, void* out_lo, void* stream);
+                       const float* dbeta, int pool, int relu, int batch_stats, float* out_f32, void* out_hi, void* out_lo,
+                       void* stream);
 int egaze_pairmax_bwd(const float* x, const float* g, long long per_stream, void* hi, void* lo, void* stream);
 int egaze_col_sum_split(const void* hi, const void* lo, long long rows, int C, float* out, void* stream);
 
 /* ---- 1x1 conv to one channel + sigmoid (model_SP.py:30,32 ; late_fusion.py:13,15) ---------------------------- */
-int egaze_head_fwd(const void* x_hi, const void* x_lo, const float* w, const float* b, int C, int Cs, long long P,
+int egaze_head_fwd(const void* x_hi, const void* x_lo, int fmt, const float* w, const float* b, int C, int Cs, long long P,
                    float* out, float* logit_out, void* stream);
-int egaze_head_bwd(const void* x_hi, const void* x_lo, const float* w, int C, int Cs, long long P, const float* y,
+/* dx_hi / dx_lo: bf16 planes of the gradient w.r.t. x (dx_lo may be NULL) */
+int egaze_head_bwd(const void* x_hi, const void* x_lo, int fmt, const float* w, int C, int Cs, long long P, const float* y,
                    const float* gy, int relu_mask, void* dx_hi, void* dx_lo, float* dw, float* db, void* stream);
 
 /* ---- late fusion (models/late_fusion.py:6-23): cat(f, g) -> [conv3x3 + BN + ReLU] x3 (2->32->32->8) -> conv1x1 -> sigmoid ---

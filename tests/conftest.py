@@ -22,3 +22,11 @@ def cuda_dev():
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
     return torch.device("cuda:0")
+
+
+@pytest.fixture(params=["precise", "precise3"])
+def numeric_mode(request, monkeypatch):
+    """Kernel-level tests run in both gated numeric modes (EGAZE_PRECISION): fp16-split forward + cheaper backward (default),
+    and the round-1 bf16-split scheme."""
+    monkeypatch.setenv("EGAZE_PRECISION", request.param)
+    return request.param

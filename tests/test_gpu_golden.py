@@ -48,7 +48,9 @@ def test_model_sp_train_forward_vs_reference_golden(cuda_dev):
     for k, v in m.state_dict().items():
         if "running_" in k:
             assert np.abs(v.cpu().numpy() - g["buf/" + k]).max() <= 1e-4, k
-    assert np.abs(y.cpu().numpy() - g["y"]).max() <= 5e-3   # train-mode gate, fp32 itself is 2e-4 here
+    err = np.abs(y.cpu().numpy() - g["y"]).max()
+    print("train-mode gaze map max-abs err vs the reference's golden output: %.3e" % err)
+    assert err <= 1e-3   # north_star's bar, train mode included (fp32 itself is 2e-4 from fp64 here)
     assert abs(loss.item() - float(g["loss"])) <= 1e-3 * abs(float(g["loss"]))
 
 

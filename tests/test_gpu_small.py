@@ -16,6 +16,12 @@ def test_layout_roundtrip(cuda_dev):
         assert act.Cp % 16 == 0 and act.Cp >= shape[1]
         y = ops.from_split(act)
         assert (x - y).abs().max().item() <= 2.0 ** -16 * x.abs().max().item()
+        for fmt, bits in ((0, 16), (1, 21)):   # bf16 split: 16 significand bits; fp16 split: 22 (21 gated)
+            act_f = ops.to_split(x, fmt=fmt, xb=bool(fmt))
+            assert act_f.fmt == fmt
+            assert (x - ops.from_split(act_f)).abs().max().item() <= 2.0 ** -bits * x.abs().max().item()
+            if fmt:
+                assert torch.equal(act_f.xb[..., :shape[1]].float(), x.permute(0, 2, 3, 1).bfloat16().float())
         if act.Cp > shape[1]:
             assert act.hi[..., shape[1]:].float().abs().max().item() == 0.0
         z = ops.nhwc_f32_to_nchw(ops.nchw_to_nhwc_f32(x))
@@ -26,16 +32,22 @@ def test_layout_roundtrip(cuda_dev):
 def test_pack_weights(cuda_dev):
     from egaze import ops
     w = torch.randn(24, 10, 3, 3, device=cuda_dev)
-    hi, lo, rows, cp = ops.pack_cache.get(w, 0)
+    hi, lo, rows, cp, _ = ops.pack_cache.get(w, 0, fmt=0)
     got = (hi.float() + lo.float())  # [9][24][16]
     ref = w.permute(2, 3, 0, 1).reshape(9, 24, 10)
     assert cp == 16 and rows == 24
     assert (got[:, :, :10] - ref).abs().max().item() <= 2.0 ** -16 * ref.abs().max().item()
     assert got[:, :, 10:].abs().max().item() == 0
-    hi, lo, rows, cp = ops.pack_cache.get(w, 1)
+    hi, lo, rows, cp, _ = ops.pack_cache.get(w, 1)
     got = (hi.float() + lo.float())  # [9][10][32]
     ref = torch.flip(w, (2, 3)).permute(2, 3, 1, 0).reshape(9, 10, 24)
     assert (got[:, :, :24] - ref).abs().max().item() <= 2.0 ** -16 * ref.abs().max().item()
+    # fp16 forward operand: planes hold w * scale, 22 significand bits
+    hi, lo, rows, cp, fmt = ops.pack_cache.get(w, 0, fmt=1)
+    assert fmt == 1 and hi.dtype == torch.float16
+    got = (hi.float() + lo.float()) / ops.f16_weight_scale()
+    ref = w.permute(2, 3, 0, 1).reshape(9, 24, 10)
+    assert (got[:, :, :10] - ref).abs().max().item() <= 2.0 ** -21 * ref.abs().max().item()
 
 
 @pytest.mark.parametrize("C,Cs", [(64, 64), (8, 16)])

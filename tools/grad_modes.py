@@ -1,14 +1,10 @@
 #!/usr/bin/env python
 """How much gradient accuracy does a cheaper backward cost?  
 
-Runs one model_SP train step (forward + floss + backward) per backward mode on the SAME parameters and inputs and reports, per
-parameter tensor, rel-L2 against (a) the 3-pass split-bf16 backward of the same forward (isolates the backward's own rounding:
-the forward, hence every ReLU / max-pool routing decision, is identical) and (b) stock torch autograd in fp64.  Stock fp32
-autograd vs fp64 is printed beside it as the noise floor.  Modes are emulated numerically with the existing kernels (a zeroed lo
-plane == a skipped MMA):
-    dgrad_hi      data gradient from dY_hi x [W_hi | W_lo]      (2 MMAs per product)
-    wgrad_1pass   weight gradient from dY_hi x X_hi             (1 MMA)
-    wgrad_xhi     weight gradient from [dY_hi; dY_lo] x X_hi    (2 MMAs)
+Runs one model_SP train step (forward + floss + backward) per numeric mode (EGAZE_PRECISION = precise3 | precise | fast, see
+egaze/ops.py) on the SAME parameters and inputs and reports the train-mode gaze map error and, per parameter tensor, the
+gradient's rel-L2 against stock torch autograd in fp64.  Stock fp32 autograd vs fp64 is printed beside it as the noise floor
+(ReLU / max-pool routing flips make fp32 itself ~1e-2 from fp64 on this step).
 """
 import copy
 import os
@@ -53,38 +49,37 @@ def main():
     o64 = torch_ref.model_sp_forward(m64, x_s.double(), x_t.double())
     F.binary_cross_entropy(o64, gt.double(), weight=torch_ref.floss_weight(gt).double()).backward()
 
-    modes = [("3pass", {}),
-             ("dgrad_hi", {"EGAZE_EMU_DGRAD_HI": "1"}),
-             ("wgrad_1pass", {"EGAZE_EMU_WGRAD_1PASS": "1"}),
-             ("wgrad_xhi", {"EGAZE_EMU_WGRAD_XHI": "1"}),
-             ("dgrad_hi+wgrad_1pass", {"EGAZE_EMU_DGRAD_HI": "1", "EGAZE_EMU_WGRAD_1PASS": "1"}),
-             ("dgrad_hi+wgrad_xhi", {"EGAZE_EMU_DGRAD_HI": "1", "EGAZE_EMU_WGRAD_XHI": "1"})]
-    grads = {}
+    modes = [("precise3", {"EGAZE_PRECISION": "precise3"}), ("precise", {"EGAZE_PRECISION": "precise"}),
+             ("fast", {"EGAZE_PRECISION": "fast"})]
+    grads, outs = {}, {}
     for name, env in modes:
-        for k in ("EGAZE_EMU_DGRAD_HI", "EGAZE_EMU_WGRAD_1PASS", "EGAZE_EMU_WGRAD_XHI"):
-            os.environ.pop(k, None)
         os.environ.update(env)
         mm = copy.deepcopy(m32)
         mm.zero_grad(set_to_none=True)
-        floss_mod.floss()(mm(x_s, x_t), gt).backward()
+        out = mm(x_s, x_t)
+        floss_mod.floss()(out, gt).backward()
+        outs[name] = out.detach()
         grads[name] = {k: p.grad.detach().clone() for k, p in mm.named_parameters()}
+    os.environ.pop("EGAZE_PRECISION", None)
+    o32 = torch_ref.model_sp_forward(copy.deepcopy(m32), x_s, x_t).detach()
+    print("train-mode gaze map max-abs vs fp64: stock fp32 %.2e | %s" % (
+        (o32.double() - o64.detach()).abs().max().item(),
+        " | ".join("%s %.2e" % (n, (outs[n].double() - o64.detach()).abs().max().item()) for n, _ in modes)))
     names = [k for k, p in m64.named_parameters() if p.grad.norm().item() >= 1e-7]
     noise = {k: rel_l2(dict(m32.named_parameters())[k].grad, dict(m64.named_parameters())[k].grad) for k in names}
     print("B=%d S=%d  stock fp32 vs fp64: median %.2e  max %.2e" % (B, S, np.median(list(noise.values())), max(noise.values())))
     for name, _ in modes:
-        vs3 = [rel_l2(grads[name][k], grads["3pass"][k]) for k in names]
+        vs3 = [rel_l2(grads[name][k], grads["precise3"][k]) for k in names]
         vs64 = [rel_l2(grads[name][k], dict(m64.named_parameters())[k].grad) for k in names]
         ratio = [a / max(noise[k], 1e-12) for a, k in zip(vs64, names)]
         iw = int(np.argmax(vs3))
-        print("%-22s vs 3pass: median %.2e max %.2e (%s) | vs fp64: median %.2e max %.2e | max ratio to stock-fp32 noise %.1f"
+        print("%-22s vs precise3: median %.2e max %.2e (%s) | vs fp64: median %.2e max %.2e | max ratio to stock-fp32 noise %.1f"
               % (name, np.median(vs3), max(vs3), names[iw], np.median(vs64), max(vs64), max(ratio)))
-    # per-group detail for the combined mode
-    for name in ("dgrad_hi+wgrad_1pass",):
-        print("-- %s, per tensor (vs 3pass | vs fp64 | stock noise)" % name)
-        for k in names:
-            if k.endswith("weight") and ("features" in k or "decoder" in k or "fusion" in k):
-                print("   %-28s %.2e | %.2e | %.2e" % (k, rel_l2(grads[name][k], grads["3pass"][k]),
-                                                     rel_l2(grads[name][k], dict(m64.named_parameters())[k].grad), noise[k]))
+    print("-- per tensor: precise vs fp64 | precise3 vs fp64 | stock fp32 vs fp64")
+    for k in names:
+        if k.endswith("weight") and ("features" in k or "decoder" in k or "fusion" in k):
+            g64 = dict(m64.named_parameters())[k].grad
+            print("   %-28s %.2e | %.2e | %.2e" % (k, rel_l2(grads["precise"][k], g64), rel_l2(grads["precise3"][k], g64), noise[k]))
 
 
 if __name__ == "__main__":
