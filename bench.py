@@ -178,6 +178,9 @@ class Workload(object):
         self.dev = [t.to(device) for t in self.host]
         self.h2d_bytes = sum(t.numel() * 4 for t in self.host[:2]) + (self.host[2].numel() * 4 if name == "sp_train" else 0)
         self.flat = None
+        self.flat_lf = None
+        self.reducer = None
+        self.ddp_kind = None
         if name == "sp_train":
             self.model.train()
             self._make_optimizers(False)
@@ -233,18 +236,38 @@ class Workload(object):
             raise SystemExit("unknown workload %r" % name)
 
     def _make_flat_grads(self, params=None):
-        """All weight grads live in ONE flat fp32 buffer so the per-step NCCL allreduce needs no pack/copy."""
-        from egaze.ddp import FlatGradBucket, broadcast_parameters
+        """Data-parallel gradient averaging.  model_SP: egaze.ddp.OverlappedGradReducer -- the backward node all-reduces each
+        segment of its flat fp32 gradient buffer (decoder -> fusion/bn -> deep trunk layers -> the rest) on a communication
+        stream as soon as that segment is final, and the optimiser reads the averaged values in place.  The 49 KB of late-fusion
+        gradients go through one small flat bucket after the LF backward.  EGAZE_BENCH_DDP=flat: round-1 scheme (ONE all-reduce
+        of one flat buffer after the whole backward)."""
+        from egaze.ddp import FlatGradBucket, attach_reducer, broadcast_parameters
         broadcast_parameters(self.model, 0)
         if params is not None:
             broadcast_parameters(self.lf, 0)
-        self.flat = FlatGradBucket(self.model.parameters() if params is None else params, self.device)
+        if os.environ.get("EGAZE_BENCH_DDP", "overlap") == "flat":
+            self.flat = FlatGradBucket(self.model.parameters() if params is None else params, self.device)
+            self.ddp_kind = "one flat all-reduce after the backward"
+        else:
+            self.reducer = attach_reducer(self.model)
+            self.flat_lf = FlatGradBucket(self.lf.parameters(), self.device) if params is not None else None
+            self.ddp_kind = "segmented all-reduce overlapped with the backward (4 segments) + 1 small LF bucket"
 
-    def _make_optimizers(self, capturable):
-        kw = {"capturable": True} if capturable else {}
-        self.opt = torch.optim.Adam(self.model.parameters(), lr=1e-7, **kw)   # gaze_full.py:11 default lr, SP.py:113
+    def _make_optimizers(self, capturable, stock=False):
+        """Adam as the reference builds it (gaze_full.py:11 default lr, SP.py:113, LF.py:77).  The bench's own loops use the fused
+        multi-tensor egaze.optim.Adam (same arguments, state and arithmetic; EGAZE_BENCH_ADAM=torch: stock torch.optim.Adam);
+        the drop-in loop (stock=True) always steps stock torch.optim.Adam like the reference."""
+        if not stock and os.environ.get("EGAZE_BENCH_ADAM", "fused") == "fused":
+            from egaze.optim import Adam
+            kw = {}
+            self.adam_kind = "egaze.optim.Adam (fused multi-tensor, maintains the packed weight copies)"
+        else:
+            Adam = torch.optim.Adam
+            kw = {"capturable": True} if capturable else {}
+            self.adam_kind = "torch.optim.Adam"
+        self.opt = Adam(self.model.parameters(), lr=1e-7, **kw)
         if self.name == "full_train":
-            self.opt_lf = torch.optim.Adam(self.lf.parameters(), lr=1e-7, **kw)  # LF.py:77
+            self.opt_lf = Adam(self.lf.parameters(), lr=1e-7, **kw)
 
     def capture(self):
         """Capture one whole training step (forward, floss, backward on all streams, the AT step and the LF train step on
@@ -322,6 +345,8 @@ class Workload(object):
         loss.backward()
         if self.flat is not None:
             self.flat.allreduce()
+        if self.flat_lf is not None:
+            self.flat_lf.allreduce()
         self.opt_lf.step()
         return 3
 
@@ -335,7 +360,7 @@ class Workload(object):
                 self.opt.zero_grad(set_to_none=True)
             out = self.model(x_s, x_t)
             loss = self.crit(out, gt.view(out.size()))
-            loss.backward()
+            loss.backward()          # (with an attached OverlappedGradReducer the gradients come back already averaged)
             if self.flat is not None:
                 self.flat.allreduce()
             self.opt.step()
@@ -345,7 +370,10 @@ class Workload(object):
                 self.flat.zero()
             else:
                 self.opt.zero_grad(set_to_none=True)
-                self.opt_lf.zero_grad(set_to_none=True)
+                if self.flat_lf is not None:
+                    self.flat_lf.zero()
+                else:
+                    self.opt_lf.zero_grad(set_to_none=True)
             self.feats.clear()
             out = self.model(x_s, x_t)                                         # SP.py:132
             gtv = gt.view(out.size())
@@ -381,6 +409,8 @@ class Workload(object):
                 loss_lf.record_stream(main)
             if self.flat is not None:
                 self.flat.allreduce()
+            if self.flat_lf is not None:
+                self.flat_lf.allreduce()
             self.opt.step()
             self.opt_lf.step()
             return torch.stack((loss.detach(), loss_lf.detach()))
@@ -690,6 +720,7 @@ def main():
     ms_dropin, dropin_syncs, dropin_host_ms = None, 0, None
     if training and not args.no_dropin:
         sample = {"image": wl.host[0], "flow": wl.host[1], "gt": wl.host[2]}
+        wl._make_optimizers(False, stock=True)
         for _ in range(2):
             wl.dropin_step(sample)
         barrier()
@@ -699,6 +730,8 @@ def main():
         torch.cuda.synchronize()
         ms_dropin = (time.perf_counter() - t0) * 1e3 / K   # every step ends in a host sync: wall clock == device time
         barrier()
+        wl._make_optimizers(False)
+    adam_kind = wl.adam_kind if training else None
 
     # ---- roofline pass: duration of every tcgen05 conv / wgrad launch ------------------------------------------------------
     # Same workload, same process, with a CUDA-event pair around every launch on the stream it is launched on.  The
@@ -763,7 +796,7 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": ops.dtype_string(), "data": "synthetic",
         "config": cfg,
-        "detail": {"precision_mode": ops.precision(),
+        "detail": {"precision_mode": ops.precision(), "optimizer": adam_kind, "gradient_averaging": wl.ddp_kind,
                    "device_loop": "CUDA graph replay of the whole step" if graphed else "eager launches"},
         "clocks": clocks,
         "e2e": {"value": frames / ms_e2e * 1e3, "unit": UNIT, "h2d_bytes_per_step": wl.h2d_bytes,

@@ -97,7 +97,8 @@ def _cur_device():
 # kernels launched per C-ABI call (bench.py's `gpu_launches` claim); entries not listed launch nothing
 _LAUNCHES = {"egaze_floss_fwd": 2, "egaze_conv3x3_tiles": 0, "egaze_check_device": 0, "egaze_sm_count": 0,
              "egaze_bn_bwd_blocks": 0, "egaze_conv3x3_stats_shape": 0, "egaze_bn_bwd_reduce": 2,
-             "egaze_conv3x3_set_prof": 0, "egaze_lf_scratch": 0, "egaze_lf_fwd": 7, "egaze_lf_bwd": 12}
+             "egaze_conv3x3_set_prof": 0, "egaze_lf_scratch": 0, "egaze_lf_fwd": 7, "egaze_lf_bwd": 12,
+             "egaze_adam_job_bytes": 0, "egaze_adam_multi": 2, "egaze_f16_weight_scale": 0}
 _launch_count = 0
 
 
@@ -127,17 +128,20 @@ def call(name, *args):
             cargs.append(a.data_ptr())
         else:
             cargs.append(a)
-    cur = _cur_device()
-    if dev is None:
-        dev = cur
-    for i, a in enumerate(cargs):
-        if a is STREAM:
-            cargs[i] = _raw_stream(dev)
-    if dev != cur:
-        with torch.cuda.device(dev):
-            rc = fn(*cargs)
+    if dev is None and not any(a is STREAM for a in cargs):
+        rc = fn(*cargs)          # host-only entry point (sizes, versions, ...): no device involved
     else:
-        rc = fn(*cargs)
+        cur = _cur_device()
+        if dev is None:
+            dev = cur
+        for i, a in enumerate(cargs):
+            if a is STREAM:
+                cargs[i] = _raw_stream(dev)
+        if dev != cur:
+            with torch.cuda.device(dev):
+                rc = fn(*cargs)
+        else:
+            rc = fn(*cargs)
     if name == "egaze_lstm_seq_fwd":
         _launch_count += int(args[9]) + 2  # T+1 wavefront launches (layer 0 at t | layer 1 at t-1) + one Linear over all steps
     elif name == "egaze_lstm_seq_bwd":

@@ -32,6 +32,13 @@ def _use_side_stream():
     return os.environ.get("EGAZE_WGRAD_STREAM", "1") != "0"
 
 
+def _get_side_stream(dev):
+    side = _side_streams.get(dev)
+    if side is None:
+        side = _side_streams[dev] = torch.cuda.Stream(device=dev)
+    return side
+
+
 def _wgrad(x_act, dy_act, cout, cin):
     return _wgrad_impl(ops.wgrad3x3, x_act, dy_act, cout, cin)
 
@@ -40,9 +47,7 @@ def _wgrad_impl(wg, x_act, dy_act, cout, cin):
     if not _use_side_stream():
         return wg(x_act, dy_act, cout, cin)
     dev = x_act.hi.device
-    side = _side_streams.get(dev)
-    if side is None:
-        side = _side_streams[dev] = torch.cuda.Stream(device=dev)
+    side = _get_side_stream(dev)
     main = torch.cuda.current_stream(dev)
     side.wait_stream(main)                      # the operands were produced on the main stream
     with torch.cuda.stream(side):
@@ -109,7 +114,10 @@ def _any_req(mods):
     return any(p.requires_grad for m in mods for p in m.parameters())
 
 
-def _bn_chain_steps(specs, saved, g, bag, need_input_grad, result):
+from .ddp import DEEP_FROM as _DEEP_FROM   # trunk layer index of conv3_1 (layers [4:] hold 98 % of a trunk's parameters)
+
+
+def _bn_chain_steps(specs, saved, g, bag, need_input_grad, result, at=None):
     """Generator: one conv+BN+ReLU(+pool) layer of the backward chain per step (so that two independent chains -- the two
     trunks of model_SP -- can be enqueued alternately on two streams).  result[0] receives the gradient w.r.t. the chain
     input (or None)."""
@@ -139,13 +147,18 @@ def _bn_chain_steps(specs, saved, g, bag, need_input_grad, result):
             g = None
         result[0] = g
         yield
+        if at is not None and at[1] is not None and i == at[0]:
+            # Called after the step that processed layer at[0] has been enqueued.  When two chains alternate (_alternate drives
+            # this generator first), the other chain's same layer is enqueued right after this yield returns control, i.e. before
+            # this generator resumes here -- so both chains' layers >= at[0] are enqueued when the callback runs.
+            at[1]()
 
 
-def bn_sequential_backward(specs, saved, g, bag, need_input_grad):
+def bn_sequential_backward(specs, saved, g, bag, need_input_grad, at=None):
     """Backward through a conv+BN+ReLU(+pool) chain.  g: NHWC fp32 gradient w.r.t. the chain output.
     Returns the NHWC fp32 gradient w.r.t. the chain input (or None)."""
     result = [None]
-    for _ in _bn_chain_steps(specs, saved, g, bag, need_input_grad, result):
+    for _ in _bn_chain_steps(specs, saved, g, bag, need_input_grad, result, at=at):
         pass
     return result[0]
 
@@ -282,6 +295,13 @@ class _ModelSPFn(torch.autograd.Function):
         trunk_need = _any_req([model.features_s, model.features_t]) or any(ctx.need_x)
         upstream_need = trunk_need or _any_req([model.fusion, model.bn])
         g = relu_sequential_backward(dspecs, dsaved, gpre, bag, upstream_need)
+        # data-parallel gradient averaging overlapped with the rest of the backward (egaze.ddp.OverlappedGradReducer): each
+        # segment is reduced on a communication stream as soon as its weight gradients are enqueued
+        reducer = getattr(model, "_egaze_reducer", None)
+        side = _get_side_stream(gout.device) if _use_side_stream() else None
+        if reducer is not None:
+            reducer.begin()
+            reducer.reduce(bag, "decoder", (side,))
         if upstream_need:
             bn = model.bn
             evalbn = bool(tail.get("eval"))
@@ -298,21 +318,27 @@ class _ModelSPFn(torch.autograd.Function):
                     bag.put(fus.bias, tail["scale"] * dbeta)
                 else:
                     bag.put(fus.bias, torch.zeros_like(fus.bias))  # feeds model_SP.bn in batch-stat mode: exactly zero
+            if reducer is not None:
+                reducer.reduce(bag, "fusion_bn", (side,))
             if trunk_need:
                 wpack = ops.pack_cache.get(fus.weight, 1, cols_p=d2.Cp)
                 _, gf, _ = ops.conv3x3(d2, wpack, want_f32=True, want_split=False)
                 B = gf.shape[0] // 2
                 g_s, g_t = gf[:B], gf[B:]
                 ts = _trunk_stream(gf.device)
+                # the deep trunk layers (conv3_1 and up: 98 % of the trunk parameters) are final long before the backward ends
+                def deep_done():
+                    if reducer is not None:
+                        reducer.reduce(bag, "trunk_deep", (side, ts))
                 if ts is None:
-                    gx_s = bn_sequential_backward(specs_s, saved_s, g_s, bag, ctx.need_x[0])
-                    gx_t = bn_sequential_backward(specs_t, saved_t, g_t, bag, ctx.need_x[1])
+                    gx_s = bn_sequential_backward(specs_s, saved_s, g_s, bag, ctx.need_x[0], at=(_DEEP_FROM, None))
+                    gx_t = bn_sequential_backward(specs_t, saved_t, g_t, bag, ctx.need_x[1], at=(_DEEP_FROM, deep_done))
                 else:
                     main = torch.cuda.current_stream(gf.device)
                     ts.wait_stream(main)               # g_t comes from the fusion dgrad on the main stream
                     gf.record_stream(ts)
                     res_s, res_t = [None], [None]
-                    _alternate(_bn_chain_steps(specs_s, saved_s, g_s, bag, ctx.need_x[0], res_s),
+                    _alternate(_bn_chain_steps(specs_s, saved_s, g_s, bag, ctx.need_x[0], res_s, at=(_DEEP_FROM, deep_done)),
                                _bn_chain_steps(specs_t, saved_t, g_t, bag, ctx.need_x[1], res_t), ts)
                     main.wait_stream(ts)
                     gx_s, gx_t = res_s[0], res_t[0]
@@ -326,6 +352,9 @@ class _ModelSPFn(torch.autograd.Function):
         gx_t = ops.nhwc_f32_to_nchw(gx_t, specs_t[0].conv.in_channels) if (gx_t is not None and ctx.need_x[1]) else None
         ctx.rec = None
         _join_side_stream()
+        if reducer is not None:
+            reducer.reduce_rest(bag)     # the shallow trunk layers, and whatever a pruned backward did not reach
+            reducer.finish()
         return (None, gx_s, gx_t) + _ret_grads(bag, _params(model))
 
 

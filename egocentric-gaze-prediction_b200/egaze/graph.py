@@ -44,6 +44,7 @@ class GraphedStep(object):
         inputs = list(inputs)
         if not inputs or not all(torch.is_tensor(t) and t.is_cuda for t in inputs):
             raise ValueError("GraphedStep: inputs must be CUDA tensors")
+        optimizers = list(optimizers)
         for opt in optimizers:
             if "capturable" in opt.defaults and not all(g.get("capturable", False) for g in opt.param_groups):
                 raise ValueError("GraphedStep: %s must be built with capturable=True" % type(opt).__name__)
@@ -63,17 +64,24 @@ class GraphedStep(object):
         saved = [t.detach().clone() for t in tensors]
         saved_opt = {k: v.detach().clone() for k, v in _state_tensors(optimizers)} if restore else None
 
+        # An optimiser that rewrites the packed weight copies itself (egaze.optim.Adam) leaves them current at the end of every
+        # step, so the captured step needs no re-pack pass; with any other optimiser the capture must contain the re-pack an
+        # optimiser step makes necessary, whatever the cache holds at capture time.
+        from .optim import Adam as _FusedAdam
+        optimizers = list(optimizers)
+        self._packs_maintained = bool(optimizers) and all(isinstance(o, _FusedAdam) for o in optimizers)
         cur = torch.cuda.current_stream(self.device)
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             for _ in range(max(1, int(warmup))):
-                ops.pack_cache.mark_stale()   # same re-pack set (and launch table) as the capture below
+                if not self._packs_maintained:
+                    ops.pack_cache.mark_stale()   # same re-pack set (and launch table) as the capture below
                 fn(*self.static_inputs)
         cur.wait_stream(side)
         torch.cuda.synchronize(self.device)
-        # the capture must contain the weight re-pack an optimiser step makes necessary, whatever the cache holds now
-        ops.pack_cache.mark_stale()
+        if not self._packs_maintained:
+            ops.pack_cache.mark_stale()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             out = fn(*self.static_inputs)
@@ -93,6 +101,8 @@ class GraphedStep(object):
                     else:
                         v.zero_()
             ops.pack_cache.mark_stale()
+            if self._packs_maintained:
+                ops.pack_cache.refresh(min_stale=1)   # the restored weights' copies: the graph itself does not re-pack
             torch.cuda.synchronize(self.device)
 
     def __call__(self, *inputs):

@@ -226,6 +226,25 @@ class _PackCache(object):
         self._d[key] = (weakref.ref(w), ver, w.data_ptr(), val)
         return val
 
+    def entries_for(self, w):
+        """Packed copies of weight w the fused optimiser can maintain: [(mode, rows_p, cols_p, fmt, hi, lo)] (one per mode; copies
+        with padded rows are excluded -- their padding is written by get() only)."""
+        out = []
+        for (wid, mode, rp, cp, fmt), ent in self._d.items():
+            if wid == id(w) and ent[0]() is w and ent[2] == w.data_ptr():
+                rows = int(w.shape[0]) if mode == 0 else int(w.shape[1])
+                if rp == rows and not any(o[0] == mode for o in out):
+                    out.append((mode, rp, cp, fmt, ent[3][0], ent[3][1]))
+        return out
+
+    def mark_current(self, w, entries):
+        """The copies in `entries` (from entries_for) were just rewritten from w's current values (egaze.optim.Adam)."""
+        for mode, rp, cp, fmt, _, _ in entries:
+            key = (id(w), mode, rp, cp, fmt)
+            ent = self._d.get(key)
+            if ent is not None:
+                self._d[key] = (ent[0], w._version, ent[2], ent[3])
+
     def held_tables(self):
         """Every job table currently alive (egaze/graph.py keeps the list next to a captured graph so that the memory a
         captured re-pack launch reads can never be recycled while the graph exists)."""
@@ -237,9 +256,10 @@ class _PackCache(object):
         for key, ent in list(self._d.items()):
             self._d[key] = (ent[0], -1, ent[2], ent[3])
 
-    def refresh(self):
+    def refresh(self, min_stale=2):
         """Re-pack, in ONE launch, every cached copy whose weight changed since it was packed (after an optimiser step that is
-        all of them: 76 small launches per SP training step otherwise).  Copies of dead or re-allocated weights are dropped."""
+        all of them: 76 small launches per SP training step otherwise).  Copies of dead or re-allocated weights are dropped.
+        With fewer than min_stale stale copies nothing happens (get() re-packs a single one lazily)."""
         stale = []
         for key, ent in list(self._d.items()):
             w = ent[0]()
@@ -250,7 +270,7 @@ class _PackCache(object):
             Co, Ci, rows, _, _ = self._dims(w, mode, rp, cp)
             if ent[1] != w._version and rp == rows and w.is_contiguous() and w.dtype == F32:
                 stale.append((key, ent, w, Co, Ci, rows))
-        if len(stale) < 2:
+        if len(stale) < max(1, min_stale):
             return
         tkey = tuple((k, e[2], e[3][0].data_ptr()) for k, e, _, _, _, _ in stale)
         table = self._tables.get(tkey)

@@ -143,6 +143,18 @@ int egaze_lf_bwd(const float* f, const float* g, int B, int H, int W, const floa
                  const float* gout, float* g1, float* g2, float* scratch, float* const* dw, float* dbh,
                  float* const* dgamma, float* const* dbeta, float* gf, float* gg, int precise, void* stream);
 
+/* ---- fused multi-tensor Adam (torch.optim.Adam semantics: SP.py:110-113,137; LF.py:77,99) that also rewrites the packed
+ * operand copies of every conv weight it updates.  jobs: DEVICE array of njobs records (egaze_adam_job_bytes each):
+ *   { float* w; const float* g; float* exp_avg; float* exp_avg_sq; float* step;          -- step: device scalar, incremented here
+ *     void* p0_hi, *p0_lo;   -- forward copy  [9][rows0][cols0] in format fmt0 (fp16 copies hold w * f16_scale), or NULL
+ *     void* p1_hi, *p1_lo;   -- data-gradient copy [9][rows1][cols1] bf16, taps flipped, or NULL
+ *     long long n; int Co, Ci;  -- conv weight [Co][Ci][3][3]; Ci == 0: flat tensor of n elements (biases, BatchNorm, 1x1)
+ *     int rows0, cols0, fmt0, rows1, cols1, pad; }
+ * Two launches whatever the number of parameters. */
+int egaze_adam_job_bytes(int* out);
+int egaze_adam_multi(const void* jobs, int njobs, float lr, float beta1, float beta2, float eps, float weight_decay,
+                     float f16_scale, void* stream);
+
 /* ---- floss (floss.py:9-41) ----------------------------------------------------------------------------------- */
 int egaze_floss_centroid(const float* target, int B, int H, int W, double* centroid, void* stream);
 int egaze_floss_weight(const double* centroid, int B, int H, int W, float* weights, void* stream);

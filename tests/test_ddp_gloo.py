@@ -60,3 +60,84 @@ def test_flat_bucket_allreduce_matches_full_batch(tmp_path):
     ref = torch.cat([p.grad.reshape(-1) for p in m.parameters()])
     assert torch.allclose(res["flat"], ref, rtol=1e-5, atol=1e-7)
     assert res["seeds"] == [1234, 1235]
+
+
+class _Bag(object):
+    """The gradient bag of egaze.autograd (gradients by parameter identity)."""
+
+    def __init__(self):
+        self.d = {}
+
+    def put(self, p, g):
+        self.d[id(p)] = g
+
+    def get(self, p):
+        return self.d.get(id(p))
+
+
+def _reducer_worker(rank, world, port, out):
+    sys.path.insert(0, os.path.join(ROOT, "egocentric-gaze-prediction_b200"))
+    from egaze.ddp import OverlappedGradReducer
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        ps = [torch.nn.Parameter(torch.zeros(s)) for s in ((4, 3), (5,), (2, 2, 2), (7,), (3,))]
+        ps[3].requires_grad_(False)                      # frozen: not part of the buffer at all
+        # the segments deliberately do NOT follow the parameters' registration order; "rest" repeats them all
+        r = OverlappedGradReducer([("late", [ps[2], ps[4]]), ("early", [ps[0], ps[1], ps[3]]), ("rest", ps)])
+        assert [n for n, _ in r.segments] == ["late", "early"] and r.numel == 8 + 3 + 12 + 5
+        results = []
+        for step in range(2):
+            bag = _Bag()
+            for i, p in enumerate(ps):
+                if p.requires_grad and not (step == 1 and i == 4):      # step 1: one parameter gets no gradient
+                    bag.put(p, torch.full(p.shape, float((rank + 1) * (i + 1) * (step + 1))))
+            r.begin()
+            r.reduce(bag, "late")
+            assert bag.get(ps[0]).data_ptr() != r.view(ps[0]).data_ptr()      # not reduced yet
+            r.reduce(bag, "late")                                               # idempotent within a step
+            r.reduce_rest(bag)
+            r.finish()
+            for p in ps:
+                if p.requires_grad:
+                    assert bag.get(p).data_ptr() == r.view(p).data_ptr() and bag.get(p).shape == p.shape
+            results.append([bag.get(p).clone() if p.requires_grad else None for p in ps])
+        if rank == 0:
+            torch.save({"results": results, "calls": r.calls}, out)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_overlapped_reducer_segments_average_and_alias(tmp_path):
+    """egaze.ddp.OverlappedGradReducer on CPU / gloo: segment-ordered flat layout, averaged values, gradients replaced by
+    views of the buffer, a parameter without gradient contributes zeros, frozen parameters are left out."""
+    out = str(tmp_path / "red.pt")
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_reducer_worker, args=(2, port, out), nprocs=2, join=True)
+    res = torch.load(out)
+    assert res["calls"] == 4
+    for step, grads in enumerate(res["results"]):
+        for i, g in enumerate(grads):
+            if i == 3:
+                assert g is None
+            elif step == 1 and i == 4:
+                assert float(g.abs().max()) == 0.0
+            else:
+                assert torch.allclose(g, torch.full_like(g, 1.5 * (i + 1) * (step + 1)))
+
+
+def test_sp_segments_cover_every_parameter_once():
+    sys.path.insert(0, os.path.join(ROOT, "egocentric-gaze-prediction_b200"))
+    from egaze.ddp import OverlappedGradReducer, sp_segments, DEEP_FROM
+    from utils import make_layers, cfg
+    from models.model_SP import model_SP
+    m = model_SP(make_layers(cfg['D'], 3), make_layers(cfg['D'], 20))
+    r = OverlappedGradReducer(sp_segments(m), device=torch.device("cpu"))
+    assert sorted(id(p) for p in r.params) == sorted(id(p) for p in m.parameters())
+    names = [n for n, _ in r.segments]
+    assert names == ["decoder", "fusion_bn", "trunk_deep", "trunk_shallow"]      # "rest" is empty: nothing was missed
+    sizes = {n: sum(p.numel() for p in ps) for n, ps in r.segments}
+    assert sizes["trunk_deep"] > 0.95 * (sizes["trunk_deep"] + sizes["trunk_shallow"]) and DEEP_FROM == 4
+    assert r.numel == sum(p.numel() for p in m.parameters())

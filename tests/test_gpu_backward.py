@@ -117,8 +117,8 @@ def _grad_errors(m, m32, m64):
 @pytest.mark.parametrize("B,S,gain", [(2, 64, 1.0), (2, 64, 0.8), (2, 224, 0.8)])
 def test_model_sp_train_step_vs_autograd(cuda_dev, B, S, gain):
     """Train step (forward + floss + backward) vs PyTorch autograd over the same parameters.
-    Truth = stock ops in fp64.  Gate: per-tensor rel-L2(egaze, fp64) <= 6e-2, cos >= 0.998; median <= 8 x stock-fp32 median
-    (see the module docstring for why stock fp32 itself is ~1e-2 from fp64 here)."""
+    Truth = stock ops in fp64.  Gates are relative to what stock fp32 autograd loses against fp64 on the same step (see the
+    module docstring for why stock fp32 itself is ~1e-2 from fp64 here)."""
     import floss as floss_mod
     m, m32 = _sp_pair(cuda_dev, 0, gain)
     m64 = copy.deepcopy(m32).double()
@@ -134,15 +134,19 @@ def test_model_sp_train_step_vs_autograd(cuda_dev, B, S, gain):
     assert abs(loss.item() - l64.item()) <= 1e-3 * abs(l64.item())
     rows = _grad_errors(m, m32, m64)
     worst = max(rows, key=lambda r: r[1])
-    print("gain %.1f: worst egaze-vs-fp64 %.2e (%s), worst fp32-vs-fp64 %.2e" % (gain, worst[1], worst[0], max(r[2] for r in rows)))
     med_e = float(np.median([r[1] for r in rows])), float(np.median([r[2] for r in rows]))
+    print("B=%d S=%d gain %.1f: egaze-vs-fp64 median %.2e worst %.2e (%s) | stock fp32-vs-fp64 median %.2e worst %.2e"
+          % (B, S, gain, med_e[0], worst[1], worst[0], med_e[1], max(r[2] for r in rows)))
+    # per tensor: within 3x (4x at the tiny 64x64 shapes, whose deep BatchNorms see only 32 values per channel) of what stock
+    # fp32 autograd itself loses against fp64 on this step -- on that tensor or in the median --, floored at 1e-2
+    k_noise = 3.0 if S >= 224 else 4.0
     for k, e, n in rows:
-        assert e <= 6e-2, "%s: egaze-vs-fp64 %.3e, stock fp32-vs-fp64 %.3e" % (k, e, n)
-    assert med_e[0] <= max(1e-2, 8 * med_e[1]), "median egaze-vs-fp64 %.3e vs 8 x median stock fp32-vs-fp64 %.3e" % med_e
+        assert e <= max(1e-2, k_noise * max(n, med_e[1])), "%s: egaze-vs-fp64 %.3e, stock fp32-vs-fp64 %.3e" % (k, e, n)
+    assert med_e[0] <= max(1e-2, 2 * med_e[1]), "median egaze-vs-fp64 %.3e vs median stock fp32-vs-fp64 %.3e" % med_e
     for (k, p), (_, r) in zip(m.named_parameters(), m64.named_parameters()):
         if r.grad.double().norm().item() >= 1e-7:
             cos = F.cosine_similarity(p.grad.double().reshape(1, -1), r.grad.reshape(1, -1)).item()
-            assert cos >= 0.998, "%s: cosine %.5f" % (k, cos)
+            assert cos >= 0.999, "%s: cosine %.5f" % (k, cos)
 
 
 def test_model_sp_frozen_trunks(cuda_dev):
@@ -321,16 +325,25 @@ def test_model_sp_eval_mode_backward(cuda_dev, frozen_stats_only):
                     mod.eval()
         else:
             mm.eval()
+    m64 = copy.deepcopy(m_ref).double()
+    if frozen_stats_only:
+        for mod in m64.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.eval()
     x_s, x_t, gt = [torch.from_numpy(a).to(cuda_dev) for a in orc.synth_sp_inputs(2, 64, 9)]
     floss_mod.floss()(m(x_s, x_t), gt).backward()
     torch_ref.floss_loss(torch_ref.model_sp_forward(m_ref, x_s, x_t), gt).backward()
-    worst = 0.0
-    for (k, p), (_, q) in zip(m.named_parameters(), m_ref.named_parameters()):
+    o64 = torch_ref.model_sp_forward(m64, x_s.double(), x_t.double())
+    F.binary_cross_entropy(o64, gt.double(), weight=torch_ref.floss_weight(gt).double()).backward()
+    rows = []
+    for (k, p), (_, q), (_, r) in zip(m.named_parameters(), m_ref.named_parameters(), m64.named_parameters()):
         assert p.grad is not None, k
-        e = rel_l2(p.grad, q.grad)
-        worst = max(worst, e)
-        assert e <= 3e-2, "%s: %.3e" % (k, e)
-    print("eval-mode BatchNorm backward: worst rel-L2 vs stock fp32 %.2e" % worst)
+        rows.append((k, rel_l2(p.grad, r.grad), rel_l2(q.grad, r.grad)))
+    med = float(np.median([r[2] for r in rows]))
+    print("eval-mode BatchNorm backward: egaze-vs-fp64 median %.2e worst %.2e | stock fp32-vs-fp64 median %.2e worst %.2e"
+          % (np.median([r[1] for r in rows]), max(r[1] for r in rows), med, max(r[2] for r in rows)))
+    for k, e, n in rows:
+        assert e <= max(1e-2, 4 * max(n, med)), "%s: egaze-vs-fp64 %.3e, stock fp32-vs-fp64 %.3e" % (k, e, n)
     # running statistics untouched
     for (k, v), (_, r) in zip(m.state_dict().items(), m_ref.state_dict().items()):
         if "running_" in k or "num_batches" in k:

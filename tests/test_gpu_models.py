@@ -93,12 +93,12 @@ def test_model_sp_train_forward(cuda_dev):
 
 def test_headline_shape_vs_stock_fp32(cuda_dev):
     """The benchmarked shape itself -- batch 32, 224x224, BASELINE configs[1] -- against the same parameters executed by stock
-    PyTorch fp32 ops on the GPU (cuDNN, TF32 off): eval gaze map, train-mode gaze map + loss + every BatchNorm running
-    statistic, and the parameter gradients of one training step.  Gradient gate per tensor: rel-L2 to stock fp32 within
-    3x the distance by which two stock-fp32 runs of the SAME step differ when cuDNN picks other algorithms (measured here by
-    re-running the stock step with cudnn.benchmark flipped and deterministic algorithms: ReLU / max-pool routing flips make
-    fp32 itself that noisy), floored at 1e-2."""
+    PyTorch ops on the GPU (cuDNN, TF32 off): eval gaze map, train-mode gaze map + loss + every BatchNorm running statistic
+    against stock fp32 (the arithmetic the reference executes; north_star's 1e-3 max-abs bar), and the parameter gradients of
+    one training step against stock autograd in fp64, gated per tensor at 3x the distance stock fp32 autograd itself has from
+    fp64 on that tensor (ReLU / max-pool routing flips make fp32 that noisy), floored at 1e-2."""
     import copy
+    import numpy as np
     import floss as floss_mod
     from oracle import egaze_oracle as orc
     B, S = 32, 224
@@ -115,10 +115,10 @@ def test_headline_shape_vs_stock_fp32(cuda_dev):
         ref = torch_ref.model_sp_forward(m, x_s, x_t)
     e_eval = (got - ref).abs().max().item()
     del got, ref
-    # train step
+    # train step: egaze, stock fp32, stock fp64
     m.train()
     m_ref = copy.deepcopy(m)
-    m_ref2 = copy.deepcopy(m)
+    m64 = copy.deepcopy(m).double()
     out = m(x_s, x_t)
     loss = floss_mod.floss()(out, gt)
     loss.backward()
@@ -130,30 +130,25 @@ def test_headline_shape_vs_stock_fp32(cuda_dev):
     sd, sr = m.state_dict(), m_ref.state_dict()
     e_stats = max((sd[k] - sr[k]).abs().max().item() for k in sd if "running_" in k)
     del out, out_r
-    # the stock step again with other cuDNN algorithm choices: fp32's own run-to-run distance
-    torch.backends.cudnn.benchmark = True
-    try:
-        torch_ref.floss_loss(torch_ref.model_sp_forward(m_ref2, x_s, x_t), gt).backward()
-    finally:
-        torch.backends.cudnn.benchmark = False
+    o64 = torch_ref.model_sp_forward(m64, x_s.double(), x_t.double())
+    torch.nn.functional.binary_cross_entropy(o64, gt.double(), weight=torch_ref.floss_weight(gt).double()).backward()
+    del o64
     rel = lambda a, b: ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
     rows = []
-    for (k, p), (_, q), (_, q2) in zip(m.named_parameters(), m_ref.named_parameters(), m_ref2.named_parameters()):
-        if q.grad.double().norm().item() < 1e-7:
+    for (k, p), (_, q), (_, r) in zip(m.named_parameters(), m_ref.named_parameters(), m64.named_parameters()):
+        if r.grad.norm().item() < 1e-7:
             assert p.grad.double().norm().item() < 1e-4, k
             continue
-        rows.append((k, rel(p.grad, q.grad), rel(q2.grad, q.grad)))
-    worst = max(rows, key=lambda r: r[1])
-    import numpy as np
-    print("B=32x224: eval max-abs %.2e | train max-abs %.2e | loss rel %.2e | BN stats %.2e | grads vs stock fp32: median %.2e "
-          "worst %.2e (%s) | stock-vs-stock: median %.2e worst %.2e"
-          % (e_eval, e_train, e_loss, e_stats, np.median([r[1] for r in rows]), worst[1], worst[0],
-             np.median([r[2] for r in rows]), max(r[2] for r in rows)))
+        rows.append((k, rel(p.grad, r.grad), rel(q.grad, r.grad)))
+    worst = max(rows, key=lambda r: r[1] / max(r[2], 1e-12))
+    print("B=32x224: eval max-abs %.2e | train max-abs %.2e | loss rel %.2e | BN stats %.2e | grads vs fp64: egaze median %.2e "
+          "max %.2e, stock fp32 median %.2e max %.2e; worst ratio %.2f (%s)"
+          % (e_eval, e_train, e_loss, e_stats, np.median([r[1] for r in rows]), max(r[1] for r in rows),
+             np.median([r[2] for r in rows]), max(r[2] for r in rows), worst[1] / max(worst[2], 1e-12), worst[0]))
     assert e_eval <= 1e-3 and e_train <= 1e-3, (e_eval, e_train)
     assert e_loss <= 1e-4 and e_stats <= 1e-4, (e_loss, e_stats)
-    floor = max(1e-2, 3 * float(np.median([r[2] for r in rows])))
     for k, e, n in rows:
-        assert e <= max(floor, 3 * n), "%s: rel-L2 to stock fp32 %.3e (stock run-to-run %.3e)" % (k, e, n)
+        assert e <= max(1e-2, 3 * n), "%s: rel-L2 to fp64 %.3e, stock fp32 %.3e" % (k, e, n)
 
 
 @pytest.mark.parametrize("train", [False, True])
