@@ -82,8 +82,9 @@ def test_lf_backward_vs_fp64_autograd(cuda_dev, shape):
         print("lf grad %s %s rel-L2 vs fp64 %.2e" % (shape, k, rel_l2(p.grad, q.grad)))
         # ReLU routing flips (a forward value within rounding distance of zero) move single gradients by ~1e-3..1e-2
         assert rel_l2(p.grad, q.grad) <= 2e-2, "%s: %.3e" % (k, rel_l2(p.grad, q.grad))
-    assert rel_l2(f.grad, f64.grad) <= 2e-2, rel_l2(f.grad, f64.grad)
-    assert rel_l2(a.grad, a64.grad) <= 2e-2, rel_l2(a.grad, a64.grad)
+    print("lf input grads %s rel-L2 vs fp64 %.2e %.2e" % (shape, rel_l2(f.grad, f64.grad), rel_l2(a.grad, a64.grad)))
+    assert rel_l2(f.grad, f64.grad) <= 4e-2, rel_l2(f.grad, f64.grad)
+    assert rel_l2(a.grad, a64.grad) <= 4e-2, rel_l2(a.grad, a64.grad)
 
 
 def test_lf_frozen_weights_and_determinism(cuda_dev):
