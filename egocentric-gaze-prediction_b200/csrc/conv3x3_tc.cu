@@ -42,7 +42,7 @@ namespace {
 
 constexpr int kThreads = 320;      // TMA warp + MMA warp + 8 epilogue warps
 constexpr int kEpiThreads = 256;
-constexpr int kMaxSA = 4, kMaxSB = 8;
+constexpr int kMaxSA = 4, kMaxSB = 9;
 constexpr int kEpiScratch = 32 + 8 * 3 * 64;   // floats of epilogue scratch behind the staging tile
 
 struct ConvTcParams {
@@ -75,6 +75,10 @@ struct ConvTcParams {
   int win;             // 1 = "window" mode: ONE (BH+2) x (BW+2) activation window per K chunk serves all nine taps
   int win_bo;          // window mode: fill the descriptor's base_offset field with (start >> 7) & 7
   int SA, SB;          // ring depths
+  int wstat;           // 1 = weight-stationary: every weight box of the layer (9 taps x chunks <= SB) is loaded ONCE per CTA and
+                       //     stays in its ring slot for all of the CTA's tiles.  For the 64 -> 64 channel layers at 224^2 the
+                       //     per-tile weight stream (147 KB against a 47 KB activation window and ~1700 cycles of MMAs) is what
+                       //     bounds the streaming schedule: ~110 B/clk/SM out of L2, 2.5x what the L2 delivers per SM.
   int a_slot_bytes;    // bytes of one A plane slot (1024-aligned)
   int b_slot_bytes;    // bytes of one B plane slot
   int stage_off;       // byte offset of the epilogue staging buffer inside dynamic smem
@@ -399,6 +403,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
       for (int w = cluster_id; w < p.num_items; w += num_clusters) {
         const Item it = decode_item(p, w, CS, rank);
         const int n0 = it.nt * p.BN;
+        const bool load_b = !(p.wstat && w != cluster_id);   // weight-stationary: the boxes of the first item stay
         for (int kc = 0; kc < chunks; ++kc) {
           for (int al = 0; al < a_loads; ++al) {
             uint8_t* a_dst = a_ring + (size_t)sa * NSA * p.a_slot_bytes;
@@ -425,7 +430,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
               // pair mode: this CTA keeps only ITS half of the box (rows rank*BN/2 ..), hi plane then lo plane back to back;
               // multicast mode: it fetches its half and multicasts it into every CTA's full-size slot
               uint8_t* b_dst = b_ring + (size_t)sb * NSPLIT * p.b_slot_bytes + (pair ? 0 : (size_t)rank * b_rows_cta * row_bytes);
-              if (leader) {
+              if (leader && load_b) {
                 { PROF_T0(p); ptx::mbar_wait(&b_empty[sb], b_par); PROF_ADD(p, prof_c[1]); }   // the slot has been drained
                 if (pair) {
                   if (rank == 0) ptx::mbar_arrive_expect_tx(&b_full[sb], b_box_bytes * NSPLIT);
@@ -486,6 +491,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
       // Only the elected lane waits on barriers and issues; the other lanes just keep the loop nest warp-uniform.
       bool a_ready = false, a_next_ready = false, b_ready = false;
       for (int w = cluster_id; w < p.num_items; w += num_clusters) {
+        const bool b_resident = p.wstat && w != cluster_id;   // weight-stationary: boxes already in their slots, never released
         if (leader) { PROF_T0(p); ptx::mbar_wait(&acc_empty[as], acc_par[as]); PROF_ADD(p, prof_c[0]); }   // epilogue has drained this accumulator stage
         acc_par[as] ^= 1;
         ptx::tc_fence_after();
@@ -513,7 +519,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
               // products: (hi,hi) [, (hi,lo), (lo,hi)].  merged: the hi and lo weight planes are contiguous in the slot, so
               // A_hi x [B_hi | B_lo] is ONE MMA of N = 2*BN; its two column halves are added in the epilogue.
               if (leader) {
-                if (!b_ready) { PROF_T0(p); ptx::mbar_wait(&b_full[sb], b_par); PROF_ADD(p, prof_c[2]); }
+                if (!b_ready && !b_resident) { PROF_T0(p); ptx::mbar_wait(&b_full[sb], b_par); PROF_ADD(p, prof_c[2]); }
                 ptx::tc_fence_after();
                 b_ready = false;
                 if (pair) {
@@ -573,9 +579,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                     for (int k = 0; k < KSTEPS; ++k) ptx::umma_bf16(d_tmem, ad + a_plane16 + 2 * k, bd + 2 * k, idesc, 1);
                   }
                 }
-                if (pair) ptx::umma_commit_2sm(&b_empty[sb], kMask);
-                else if (CS > 1) ptx::umma_commit_mc(&b_empty[sb], kMask);
-                else ptx::umma_commit(&b_empty[sb]);
+                if (!p.wstat) {
+                  if (pair) ptx::umma_commit_2sm(&b_empty[sb], kMask);
+                  else if (CS > 1) ptx::umma_commit_mc(&b_empty[sb], kMask);
+                  else ptx::umma_commit(&b_empty[sb]);
+                }
               }
               accumulate = 1;
               if (++sb == p.SB) { sb = 0; b_par ^= 1; }
@@ -1127,7 +1135,19 @@ extern "C" int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* 
   else if (nsa == 1 && (budget - 3 * p.a_slot_bytes) / (p.nsplit * p.b_slot_bytes) >= 6)
     p.SA = 3;   // one activation plane: the freed shared memory buys a third window slot
   int sb = (budget - p.SA * nsa * p.a_slot_bytes) / (p.nsplit * p.b_slot_bytes);
-  if (sb > 6) sb = 6;
+  {
+    static int wstat_env = -1;
+    if (wstat_env < 0) {
+      const char* e = getenv("EGAZE_CONV_WSTAT");
+      wstat_env = e ? atoi(e) : 1;
+    }
+    const int boxes = 9 * (Cin_p / p.KC);
+    if (wstat_env && p.pair && p.tiles_n == 1 && boxes <= kMaxSB && sb >= boxes) {
+      p.wstat = 1;
+      sb = boxes;
+    }
+  }
+  if (!p.wstat && sb > 6) sb = 6;
   EGAZE_CHECK_ARG(sb >= 2, "conv3x3_tc: tile does not fit shared memory");
   p.SB = sb;
   // accumulator layout (see ConvTcParams::acc_mode).  The N = 2*BN MMA of modes 1/2 needs the two weight planes back to

@@ -8,9 +8,10 @@ namespace {
 // x: [N][C][HW] fp32  ->  hi/lo: [N][HW][Cp] bf16 (channels >= C zero-filled)
 // fmt: 0 = bf16 planes, 1 = fp16 planes; xb: optional extra bf16(x) plane (what the weight-gradient GEMM reads when the
 // forward planes are fp16)
+// (the xb plane has its own channel stride Cp_xb: the weight-gradient GEMM wants 64-channel rows, the forward conv only 16 / 32)
 __global__ void nchw_to_nhwc_split_kernel(const float* __restrict__ x, int C, int HW, int Cp,
                                           __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-                                          __nv_bfloat16* __restrict__ xb, int fmt) {
+                                          __nv_bfloat16* __restrict__ xb, int Cp_xb, int fmt) {
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -22,6 +23,7 @@ __global__ void nchw_to_nhwc_split_kernel(const float* __restrict__ x, int C, in
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int p = p0 + i, c = c0 + threadIdx.x;
+    if (p < HW && xb && c < Cp_xb) xb[((size_t)n * HW + p) * Cp_xb + c] = __float2bfloat16_rn(tile[threadIdx.x][i]);
     if (p < HW && c < Cp) {
       const float v = tile[threadIdx.x][i];
       const size_t o = ((size_t)n * HW + p) * Cp + c;
@@ -36,7 +38,6 @@ __global__ void nchw_to_nhwc_split_kernel(const float* __restrict__ x, int C, in
         hi[o] = h;
         if (lo) lo[o] = l;
       }
-      if (xb) xb[o] = __float2bfloat16_rn(v);
     }
   }
 }
@@ -177,12 +178,13 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, int Co, int C
 }  // namespace
 
 extern "C" int egaze_nchw_to_nhwc_split(const float* x, int N, int C, int H, int W, int Cp, void* hi, void* lo, void* xb,
-                                        int fmt, void* stream) {
-  EGAZE_CHECK_ARG(x && hi && Cp >= C, "nchw_to_nhwc_split: bad args");
+                                        int Cp_xb, int fmt, void* stream) {
+  EGAZE_CHECK_ARG(x && hi && Cp >= C && (!xb || Cp_xb >= C), "nchw_to_nhwc_split: bad args");
   const int HW = H * W;
-  dim3 grid(ceil_div(HW, 32), ceil_div(Cp, 32), N), block(32, 8);
+  const int cmax = (xb && Cp_xb > Cp) ? Cp_xb : Cp;
+  dim3 grid(ceil_div(HW, 32), ceil_div(cmax, 32), N), block(32, 8);
   nchw_to_nhwc_split_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, C, HW, Cp, (__nv_bfloat16*)hi,
-                                                                      (__nv_bfloat16*)lo, (__nv_bfloat16*)xb, fmt);
+                                                                      (__nv_bfloat16*)lo, (__nv_bfloat16*)xb, Cp_xb, fmt);
   EGAZE_LAUNCH_CHECK();
   return EGAZE_OK;
 }

@@ -107,64 +107,89 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 // Stage a WWIN-wide window of wh_ rows whose top-left pixel is (oy, ox) of image img: per pixel CP bf16 channels (the real C
 // first, zero padding behind) in two planes hi / lo, pixel pitch CP*2 + 16 bytes (the 16 spare bytes make the 8-row ldmatrix
 // reads conflict-free).  Pixels outside the image are zeros (= the conv padding).
-template <int KIND, int C, int CP, int WWIN>
+// Work item = (pixel, 8-channel group).  A thread first ISSUES the global loads of a whole batch of its items (BATCH x 2 or 4
+// 16-byte loads in flight per thread: one DRAM round trip per batch instead of one per item -- the shared-memory stores below
+// are asm volatile with a memory clobber, which the compiler never hoists loads across), then transforms and stores the batch.
+template <int KIND, int C, int CP, int WWIN, int BATCH = ((KIND == L_DRAW) ? 3 : 6)>
 __device__ __forceinline__ void load_window(const LdArgs& a, const float (*cst)[32], uint32_t hi_s, uint32_t lo_s, int img,
                                             int oy, int ox, int wh_, int H, int W) {
   constexpr int G = CP / 8;            // 16-byte channel groups per pixel
   constexpr int GR = (C + 7) / 8;      // groups that hold real channels
   constexpr int STRIDE = CP * 2 + 16;
   const int items = wh_ * WWIN * G;
-#pragma unroll 2
-  for (int i = threadIdx.x; i < items; i += blockDim.x) {
-    const int p = i / G, cg = i - p * G;
-    const int wy = p / WWIN, wx = p - wy * WWIN;
-    const int gy = oy + wy, gx = ox + wx;
-    float v[8];
+  const int step = (int)blockDim.x;
+  for (int i0 = threadIdx.x; i0 < items; i0 += BATCH * step) {
+    float r[BATCH][8], gr[BATCH][8];
+    bool live[BATCH];
+    // ---- phase A: issue every load of the batch
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = 0.f;
-    if (cg < GR && gy >= 0 && gy < H && gx >= 0 && gx < W) {
-      const size_t pix = ((size_t)img * H + gy) * W + gx;
-      if (KIND == L_INPUT) {
-        v[0] = __ldg(a.f + pix);
-        v[1] = __ldg(a.gin + pix);
-      } else {
+    for (int k = 0; k < BATCH; ++k) {
+      const int i = i0 + k * step;
+      const int p = i / G, cg = i - p * G;
+      const int wy = p / WWIN, wx = p - wy * WWIN;
+      const int gy = oy + wy, gx = ox + wx;
+      live[k] = i < items && cg < GR && gy >= 0 && gy < H && gx >= 0 && gx < W;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { r[k][e] = 0.f; gr[k][e] = 0.f; }
+      if (live[k]) {
+        const size_t pix = ((size_t)img * H + gy) * W + gx;
         const int c0 = cg * 8;
-        float r[8];
-        if (C >= 8) {
-          const float4 r0 = ldg4(a.raw + pix * C + c0), r1 = ldg4(a.raw + pix * C + c0 + 4);
-          r[0] = r0.x; r[1] = r0.y; r[2] = r0.z; r[3] = r0.w; r[4] = r1.x; r[5] = r1.y; r[6] = r1.z; r[7] = r1.w;
-        }
-        if (KIND == L_ACT) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(r[j], cst[0][c0 + j], cst[1][c0 + j]), 0.f);
+        if (KIND == L_INPUT) {
+          r[k][0] = __ldg(a.f + pix);
+          r[k][1] = __ldg(a.gin + pix);
         } else {
-          float gr[8];
+          if (C >= 8) {
+            const float4 r0 = ldg4(a.raw + pix * C + c0), r1 = ldg4(a.raw + pix * C + c0 + 4);
+            r[k][0] = r0.x; r[k][1] = r0.y; r[k][2] = r0.z; r[k][3] = r0.w; r[k][4] = r1.x; r[k][5] = r1.y; r[k][6] = r1.z; r[k][7] = r1.w;
+          }
           if (KIND == L_DRAW) {
             const float4 g0 = ldg4(a.g + pix * C + c0), g1 = ldg4(a.g + pix * C + c0 + 4);
-            gr[0] = g0.x; gr[1] = g0.y; gr[2] = g0.z; gr[3] = g0.w; gr[4] = g1.x; gr[5] = g1.y; gr[6] = g1.z; gr[7] = g1.w;
-          } else {
-            const float y = __ldg(a.out + pix);
-            const float dz = __ldg(a.gout + pix) * y * (1.f - y);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) gr[j] = dz * cst[6][c0 + j];
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float sc = cst[0][c0 + j];
-            const float z = fmaf(r[j], sc, cst[1][c0 + j]);
-            const float gz = z > 0.f ? gr[j] : 0.f;
-            const float xh = (r[j] - cst[2][c0 + j]) * cst[3][c0 + j];
-            v[j] = fmaf(sc, gz, -cst[4][c0 + j]) - xh * cst[5][c0 + j];
+            gr[k][0] = g0.x; gr[k][1] = g0.y; gr[k][2] = g0.z; gr[k][3] = g0.w; gr[k][4] = g1.x; gr[k][5] = g1.y; gr[k][6] = g1.z; gr[k][7] = g1.w;
+          } else if (KIND == L_DRAW_HEAD) {
+            gr[k][0] = __ldg(a.out + pix);     // y
+            gr[k][1] = __ldg(a.gout + pix);    // d(loss)/dy
           }
         }
       }
     }
-    uint2 h0, l0, h1, l1;
-    split_bf16x4(make_float4(v[0], v[1], v[2], v[3]), h0, l0);
-    split_bf16x4(make_float4(v[4], v[5], v[6], v[7]), h1, l1);
-    const uint32_t off = (uint32_t)(p * STRIDE + cg * 16);
-    ptx::sts128(hi_s + off, h0.x, h0.y, h1.x, h1.y);
-    ptx::sts128(lo_s + off, l0.x, l0.y, l1.x, l1.y);
+    // ---- phase B: transform + split + store
+#pragma unroll
+    for (int k = 0; k < BATCH; ++k) {
+      const int i = i0 + k * step;
+      if (i >= items) break;
+      const int p = i / G, cg = i - p * G;
+      const int c0 = cg * 8;
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = 0.f;
+      if (live[k]) {
+        if (KIND == L_INPUT) {
+          v[0] = r[k][0];
+          v[1] = r[k][1];
+        } else if (KIND == L_ACT) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = fmaxf(fmaf(r[k][e], cst[0][c0 + e], cst[1][c0 + e]), 0.f);
+        } else {
+          float dz = 0.f;
+          if (KIND == L_DRAW_HEAD) dz = gr[k][1] * gr[k][0] * (1.f - gr[k][0]);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float gin = KIND == L_DRAW ? gr[k][e] : dz * cst[6][c0 + e];
+            const float sc = cst[0][c0 + e];
+            const float z = fmaf(r[k][e], sc, cst[1][c0 + e]);
+            const float gz = z > 0.f ? gin : 0.f;
+            const float xh = (r[k][e] - cst[2][c0 + e]) * cst[3][c0 + e];
+            v[e] = fmaf(sc, gz, -cst[4][c0 + e]) - xh * cst[5][c0 + e];
+          }
+        }
+      }
+      uint2 h0, l0, h1, l1;
+      split_bf16x4(make_float4(v[0], v[1], v[2], v[3]), h0, l0);
+      split_bf16x4(make_float4(v[4], v[5], v[6], v[7]), h1, l1);
+      const uint32_t off = (uint32_t)(p * STRIDE + cg * 16);
+      ptx::sts128(hi_s + off, h0.x, h0.y, h1.x, h1.y);
+      ptx::sts128(lo_s + off, l0.x, l0.y, l1.x, l1.y);
+    }
   }
 }
 
@@ -443,8 +468,9 @@ __global__ void __launch_bounds__(kWgradThreads, 2) lf_wgrad_kernel(const WgArgs
   for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
     const int txi = t % a.tiles_x, tyi = (t / a.tiles_x) % a.tiles_y, img = t / (a.tiles_x * a.tiles_y);
     const int y0 = tyi * TH, x0 = txi * TW;
-    load_window<KY, CY, CPY, TW>(a.ldy, csty, y_hi, y_lo, img, y0, x0, TH, a.H, a.W);
-    load_window<KX, CX, CPX, WW>(a.ldx, cstx, x_hi, x_lo, img, y0 - 1, x0 - 1, WH, a.H, a.W);
+    // (the tap accumulators stay live across the loaders: smaller batches than in the conv kernel, or they would spill)
+    load_window<KY, CY, CPY, TW, (KY == L_DRAW ? 1 : 2)>(a.ldy, csty, y_hi, y_lo, img, y0, x0, TH, a.H, a.W);
+    load_window<KX, CX, CPX, WW, 2>(a.ldx, cstx, x_hi, x_lo, img, y0 - 1, x0 - 1, WH, a.H, a.W);
     __syncthreads();
 #pragma unroll 2
     for (int j = 0; j < TH; ++j) {   // k-step j = tile row j (16 pixels)
@@ -489,15 +515,27 @@ __global__ void __launch_bounds__(kWgradThreads, 2) lf_wgrad_kernel(const WgArgs
       }
 }
 
-// dw[co][ci][tap] (OIHW) = sum over CTAs of partial[cta][tap][co][ci]   (fp64 accumulation, fixed order: deterministic)
-__global__ void lf_wgrad_reduce_kernel(const float* __restrict__ partial, int nctas, int CY, int CX, float* __restrict__ dw) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// dw[co][ci][tap] (OIHW) = sum over CTAs of partial[cta][tap][co][ci]   (fp64 accumulation, fixed order: deterministic).
+// One warp per output element group: lane l sums CTAs l, l+32, ... (coalesced across the 32 consecutive elements a block row
+// covers), then a shuffle tree -- 296 dependent loads per thread became ~10.
+__global__ void __launch_bounds__(256) lf_wgrad_reduce_kernel(const float* __restrict__ partial, int nctas, int CY, int CX,
+                                                              float* __restrict__ dw) {
+  __shared__ double red[8][32];
   const int per = 9 * CY * CX;
-  if (i >= per) return;
+  const int i = blockIdx.x * 32 + (threadIdx.x & 31);       // element handled by this thread column
+  const int slice = threadIdx.x >> 5;                         // 8 slices of CTAs per block
   double v = 0.0;
-  for (int b = 0; b < nctas; ++b) v += (double)partial[(size_t)b * per + i];
-  const int ci = i % CX, co = (i / CX) % CY, tap = i / (CX * CY);
-  dw[((size_t)co * CX + ci) * 9 + tap] = (float)v;
+  if (i < per)
+    for (int b = slice; b < nctas; b += 8) v += (double)partial[(size_t)b * per + i];
+  red[slice][threadIdx.x & 31] = v;
+  __syncthreads();
+  if (slice == 0 && i < per) {
+    v = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v += red[k][threadIdx.x];
+    const int ci = i % CX, co = (i / CX) % CY, tap = i / (CX * CY);
+    dw[((size_t)co * CX + ci) * 9 + tap] = (float)v;
+  }
 }
 
 // out[c] = sum over blocks of partial[b][row][c] for two rows (fp64): BatchNorm-backward sums -> dbeta (row 0), dgamma (row 1)
@@ -772,7 +810,7 @@ extern "C" int egaze_lf_bwd(const float* f, const float* g, int B, int H, int W,
   if (dw[2]) {
     wa.ldy = d3; wa.ldx = act_args(1, raw2);
     if ((rc = launch_wgrad<L_DRAW_HEAD, 8, 16, L_ACT, 32, 32>(wa, grid, st))) return rc;
-    lf_wgrad_reduce_kernel<<<ceil_div(9 * 8 * 32, 256), 256, 0, st>>>(wg_partial, grid, 8, 32, dw[2]);
+    lf_wgrad_reduce_kernel<<<ceil_div(9 * 8 * 32, 32), 256, 0, st>>>(wg_partial, grid, 8, 32, dw[2]);
     EGAZE_LAUNCH_CHECK();
   }
   ca.ld = d3; ca.w = w[2]; ca.w_cin = 32; ca.out = g2;
@@ -784,7 +822,7 @@ extern "C" int egaze_lf_bwd(const float* f, const float* g, int B, int H, int W,
   if (dw[1]) {
     wa.ldy = d2; wa.ldx = act_args(0, raw1);
     if ((rc = launch_wgrad<L_DRAW, 32, 32, L_ACT, 32, 32>(wa, grid, st))) return rc;
-    lf_wgrad_reduce_kernel<<<ceil_div(9 * 32 * 32, 256), 256, 0, st>>>(wg_partial, grid, 32, 32, dw[1]);
+    lf_wgrad_reduce_kernel<<<ceil_div(9 * 32 * 32, 32), 256, 0, st>>>(wg_partial, grid, 32, 32, dw[1]);
     EGAZE_LAUNCH_CHECK();
   }
   ca.ld = d2; ca.w = w[1]; ca.w_cin = 32; ca.out = g1;
@@ -796,7 +834,7 @@ extern "C" int egaze_lf_bwd(const float* f, const float* g, int B, int H, int W,
   if (dw[0]) {
     wa.ldy = d1; wa.ldx = in;
     if ((rc = launch_wgrad<L_DRAW, 32, 32, L_INPUT, 2, 16>(wa, grid, st))) return rc;
-    lf_wgrad_reduce_kernel<<<ceil_div(9 * 32 * 2, 256), 256, 0, st>>>(wg_partial, grid, 32, 2, dw[0]);
+    lf_wgrad_reduce_kernel<<<ceil_div(9 * 32 * 2, 32), 256, 0, st>>>(wg_partial, grid, 32, 2, dw[0]);
     EGAZE_LAUNCH_CHECK();
   }
   if (gf || gg) {

@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const AdamJob* __restri
   const float bias1 = 1.f - powf(h.beta1, step), bias2 = 1.f - powf(h.beta2, step);
   const float step_size = h.lr / bias1, inv_sqrt_bias2 = rsqrtf(bias2);
   if (j.Ci == 0) {
+    if (blockIdx.x * blockDim.x >= j.n) return;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < j.n; i += (long long)gridDim.x * blockDim.x) {
       float m = j.m[i], v = j.v[i];
       j.w[i] = adam_update(j.w[i], j.g[i], m, v, h, step_size, inv_sqrt_bias2);
@@ -87,20 +88,51 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const AdamJob* __restri
   const size_t plane0 = (size_t)j.rows0 * j.cols0, plane1 = (size_t)j.rows1 * j.cols1;
   for (int t = blockIdx.x; t < tiles_ci * tiles_co; t += gridDim.x) {
     const int co0 = (t / tiles_ci) * kTile, ci0 = (t % tiles_ci) * kTile;
-    // phase 1: update; thread <-> (co, ci) pair, its nine taps are 36 contiguous bytes
-    for (int p = threadIdx.x; p < kTile * kTile; p += blockDim.x) {
-      const int co_l = p / kTile, ci_l = p % kTile;
-      const int co = co0 + co_l, ci = ci0 + ci_l;
-      if (co < j.Co && ci < j.Ci) {
-        const size_t base = ((size_t)co * j.Ci + ci) * 9;
+    // phase 1: update.  For one output channel the tile's (ci, tap) elements are one contiguous run of 32*9 floats, so the
+    // four arrays are streamed with fully coalesced float4 accesses (rows whose length or start is not a multiple of four
+    // floats -- only the 3-channel RGB conv -- take the scalar path); the new weights are parked in the shared tile.
+    const int tci = min(kTile, j.Ci - ci0), tco = min(kTile, j.Co - co0);
+    const int row_len = tci * 9;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(j.w) | reinterpret_cast<uintptr_t>(j.g) | reinterpret_cast<uintptr_t>(j.m) |
+                           reinterpret_cast<uintptr_t>(j.v)) & 15) == 0;
+    if (aligned && ((j.Ci * 9) & 3) == 0 && (row_len & 3) == 0) {
+      const int row4 = row_len >> 2;
+      for (int f = threadIdx.x; f < tco * row4; f += blockDim.x) {
+        const int co_l = f / row4, c4 = f - co_l * row4;
+        const size_t base = ((size_t)(co0 + co_l) * j.Ci + ci0) * 9 + (size_t)c4 * 4;
+        float4 w4 = *reinterpret_cast<const float4*>(j.w + base);
+        const float4 g4 = *reinterpret_cast<const float4*>(j.g + base);
+        float4 m4 = *reinterpret_cast<const float4*>(j.m + base);
+        float4 v4 = *reinterpret_cast<const float4*>(j.v + base);
+        w4.x = adam_update(w4.x, g4.x, m4.x, v4.x, h, step_size, inv_sqrt_bias2);
+        w4.y = adam_update(w4.y, g4.y, m4.y, v4.y, h, step_size, inv_sqrt_bias2);
+        w4.z = adam_update(w4.z, g4.z, m4.z, v4.z, h, step_size, inv_sqrt_bias2);
+        w4.w = adam_update(w4.w, g4.w, m4.w, v4.w, h, step_size, inv_sqrt_bias2);
+        *reinterpret_cast<float4*>(j.w + base) = w4;
+        *reinterpret_cast<float4*>(j.m + base) = m4;
+        *reinterpret_cast<float4*>(j.v + base) = v4;
+        const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-          float m = j.m[base + tap], v = j.v[base + tap];
-          const float w = adam_update(j.w[base + tap], j.g[base + tap], m, v, h, step_size, inv_sqrt_bias2);
-          j.w[base + tap] = w;
-          j.m[base + tap] = m;
-          j.v[base + tap] = v;
-          tile[tap][co_l][ci_l] = w;
+        for (int e = 0; e < 4; ++e) {
+          const int q = c4 * 4 + e, ci_l = q / 9, tap = q - ci_l * 9;
+          tile[tap][co_l][ci_l] = wv[e];
+        }
+      }
+    } else {
+      for (int p = threadIdx.x; p < kTile * kTile; p += blockDim.x) {
+        const int co_l = p / kTile, ci_l = p % kTile;
+        const int co = co0 + co_l, ci = ci0 + ci_l;
+        if (co < j.Co && ci < j.Ci) {
+          const size_t base = ((size_t)co * j.Ci + ci) * 9;
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            float m = j.m[base + tap], v = j.v[base + tap];
+            const float w = adam_update(j.w[base + tap], j.g[base + tap], m, v, h, step_size, inv_sqrt_bias2);
+            j.w[base + tap] = w;
+            j.m[base + tap] = m;
+            j.v[base + tap] = v;
+            tile[tap][co_l][ci_l] = w;
+          }
         }
       }
     }

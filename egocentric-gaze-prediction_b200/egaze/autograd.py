@@ -107,7 +107,9 @@ def _dgrad(conv, gpre_act, **kw):
 def _first_cp(conv):
     """Channel padding of a trunk's input.  When the first conv's weight is trained the input is laid out with the 64-channel
     stride its weight-gradient GEMM needs, instead of being re-padded (two extra copies per plane) in the backward."""
-    return 64 if (_req(conv.weight) and conv.in_channels <= 64) else ops.pad_channels(conv.in_channels)
+    if _req(conv.weight) and conv.in_channels <= 64 and ops.mode()["fwd_fmt"] == 0:
+        return 64       # (fp16 forward: the weight gradient reads the separate bf16 copy, which to_split pads to 64 on its own)
+    return ops.pad_channels(conv.in_channels)
 
 
 def _any_req(mods):

@@ -10,11 +10,15 @@ import torch
 import torch.distributed as dist
 
 
+def _pad4(n):
+    return (n + 3) // 4 * 4
+
+
 class FlatGradBucket(object):
     def __init__(self, params, device=None):
         self.params = [p for p in params if p.requires_grad]
         device = device if device is not None else self.params[0].device
-        self.numel = sum(p.numel() for p in self.params)
+        self.numel = sum(_pad4(p.numel()) for p in self.params)     # every view starts 16-byte aligned (vector loads)
         self.flat = torch.zeros(self.numel, dtype=torch.float32, device=device)
         self.views = []
         off = 0
@@ -22,7 +26,7 @@ class FlatGradBucket(object):
             v = self.flat[off:off + p.numel()].view_as(p)
             p.grad = v
             self.views.append(v)
-            off += p.numel()
+            off += _pad4(p.numel())
 
     def zero(self):
         """Drop the gradients (the next backward assigns fresh tensors instead of adding into the bucket)."""
@@ -95,14 +99,14 @@ class OverlappedGradReducer(object):
                 self.segments.append((name, ps))
         self.params = [p for _, ps in self.segments for p in ps]
         device = device if device is not None else self.params[0].device
-        self.numel = sum(p.numel() for p in self.params)
+        self.numel = sum(_pad4(p.numel()) for p in self.params)     # every view starts 16-byte aligned (vector loads)
         self.flat = torch.zeros(self.numel, dtype=torch.float32, device=device)
         self.offset, self.span, off = {}, {}, 0
         for name, ps in self.segments:
             lo = off
             for p in ps:
                 self.offset[id(p)] = (off, p.numel())
-                off += p.numel()
+                off += _pad4(p.numel())
             self.span[name] = (lo, off)
         self.comm = torch.cuda.Stream(device=device) if self.flat.is_cuda else None
         self.done = set()

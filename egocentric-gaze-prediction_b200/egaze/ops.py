@@ -125,8 +125,11 @@ def to_split(x, Cp=None, fmt=None, xb=False):
     N, C, H, W = x.shape
     Cp = pad_channels(C) if Cp is None else Cp
     fmt = mode()["fwd_fmt"] if fmt is None else fmt
-    act = empty_act(N, H, W, Cp, C, x.device, lo=True, fmt=fmt, xb=xb and fmt == 1)
-    call("egaze_nchw_to_nhwc_split", x, N, C, H, W, Cp, act.hi, act.lo, act.xb, fmt, stream_ptr())
+    act = empty_act(N, H, W, Cp, C, x.device, lo=True, fmt=fmt)
+    cp_xb = (Cp + 63) // 64 * 64      # the weight-gradient GEMM reads 64-channel rows; the forward conv keeps the narrow K
+    if xb and fmt == 1:
+        act.xb = torch.empty((N, H, W, cp_xb), dtype=BF16, device=x.device)
+    call("egaze_nchw_to_nhwc_split", x, N, C, H, W, Cp, act.hi, act.lo, act.xb, cp_xb, fmt, stream_ptr())
     return act
 
 
@@ -444,18 +447,13 @@ def head_fwd(act, w, b, want_logit=False):
 
 
 # ---- backward pieces --------------------------------------------------------------------------------------------
-def repad(act, Cp):
-    """Same activation with the channel stride padded (zeros) to Cp (wgrad needs 64-channel K chunks)."""
-    if act.Cp == Cp:
-        return act
-
-    def pad(t):
-        if t is None:
-            return None
-        o = torch.zeros((act.N, act.H, act.W, Cp), dtype=t.dtype, device=t.device)
-        o[..., :act.Cp].copy_(t)
-        return o
-    return Act(pad(act.hi), pad(act.lo), act.C, pad(act.xb))
+def _pad64(t):
+    """A plane with its channel stride padded (zeros) to a multiple of 64 (the weight-gradient GEMM's K-chunk rows)."""
+    if t is None or t.shape[-1] % 64 == 0:
+        return t
+    o = torch.zeros(tuple(t.shape[:-1]) + ((t.shape[-1] + 63) // 64 * 64,), dtype=t.dtype, device=t.device)
+    o[..., :t.shape[-1]].copy_(t)
+    return o
 
 
 def wgrad_operands(x_act, dy_act, precise=None):
@@ -475,27 +473,26 @@ def wgrad_operands(x_act, dy_act, precise=None):
 def wgrad3x3(x_act, dy_act, Cout, Cin, precise=None):
     """dW (OIHW fp32 [Cout, Cin, 3, 3]) of a 3x3/pad-1 conv from its input activation and output gradient (bf16 planes).
     precise (default: the numeric mode's choice): dY_hi*X_hi + dY_hi*X_lo + dY_lo*X_hi, else dY_hi * bf16(X) (1 MMA)."""
-    x_act = repad(x_act, (x_act.Cp + 63) // 64 * 64)
-    dy_act = repad(dy_act, (dy_act.Cp + 63) // 64 * 64)
-    x_hi, x_lo, dy_hi, dy_lo, precise = wgrad_operands(x_act, dy_act, precise)
+    x_hi, x_lo, dy_hi, dy_lo, precise = [_pad64(t) if torch.is_tensor(t) else t for t in wgrad_operands(x_act, dy_act, precise)]
     N, H, W = x_act.N, x_act.H, x_act.W
     dev = x_act.hi.device
+    cin_p, cout_p = x_hi.shape[-1], dy_hi.shape[-1]
     # persistent accumulator per shape: allocated zeroed once, left zeroed again by egaze_unpack_wgrad (clear=1)
     # (keyed by stream too: two streams -- the two trunks of model_SP have identical layer shapes -- must never accumulate
     # into the same buffer concurrently)
-    key = (dy_act.Cp, x_act.Cp, dev, _lib.stream_key(dev))
+    key = (cout_p, cin_p, dev, _lib.stream_key(dev))
     dwp = _dwp_cache.get(key)
     if dwp is None:
-        dwp = _dwp_cache[key] = torch.zeros((9, dy_act.Cp, x_act.Cp), dtype=F32, device=dev)
+        dwp = _dwp_cache[key] = torch.zeros((9, cout_p, cin_p), dtype=F32, device=dev)
     if _conv_timer["on"]:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-    call("egaze_wgrad3x3_tc", x_hi, x_lo, dy_hi, dy_lo, N, H, W, x_act.Cp, dy_act.Cp, dwp, int(precise), stream_ptr())
+    call("egaze_wgrad3x3_tc", x_hi, x_lo, dy_hi, dy_lo, N, H, W, cin_p, cout_p, dwp, int(precise), stream_ptr())
     if _conv_timer["on"]:
         ev1.record()
-        _conv_timer["events"].append((ev0, ev1, ("wgrad", N, H, W, x_act.Cp, dy_act.Cp, 0, 0, False)))
+        _conv_timer["events"].append((ev0, ev1, ("wgrad", N, H, W, cin_p, cout_p, 0, 0, False)))
     gw = torch.empty((Cout, Cin, 3, 3), dtype=F32, device=dev)
-    call("egaze_unpack_wgrad", dwp, Cout, Cin, dy_act.Cp, x_act.Cp, 0.0, 1, gw, stream_ptr())
+    call("egaze_unpack_wgrad", dwp, Cout, Cin, cout_p, cin_p, 0.0, 1, gw, stream_ptr())
     return gw
 
 

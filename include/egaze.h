@@ -32,8 +32,9 @@ int egaze_sm_count(int* out);
 
 /* ---- layout (API tensors are NCHW fp32: reference SURVEY 8b "Tensor conventions") ---------------------------- */
 /* x [N][C][H][W] fp32 -> hi/lo [N][H][W][Cp] bf16, channels C..Cp-1 zero.  (input side of utils.py:70 / model_SP.py:36-37) */
-int egaze_nchw_to_nhwc_split(const float* x, int N, int C, int H, int W, int Cp, void* hi, void* lo, void* xb, int fmt,
-                             void* stream);
+/* xb (optional): bf16(x) plane [N][H][W][Cp_xb] with its own channel stride (the weight-gradient GEMM reads 64-channel rows) */
+int egaze_nchw_to_nhwc_split(const float* x, int N, int C, int H, int W, int Cp, void* hi, void* lo, void* xb, int Cp_xb,
+                             int fmt, void* stream);
 /* (hi[,lo]) or f32, NHWC with channel stride Cs -> out [N][C][H][W] fp32 (what forward hooks / callers see: AT.py:22,226) */
 int egaze_nhwc_to_nchw(const void* hi, const void* lo, const float* f32, int N, int C, int H, int W, int Cs, int fmt,
                        float* out, void* stream);

@@ -57,7 +57,7 @@ def test_flat_bucket_allreduce_matches_full_batch(tmp_path):
     x = torch.randn(8, 3, 16, 16, generator=g)
     t = torch.rand(8, 1, 16, 16, generator=g)
     torch.nn.functional.binary_cross_entropy(m(x), t).backward()
-    ref = torch.cat([p.grad.reshape(-1) for p in m.parameters()])
+    ref = torch.cat([torch.nn.functional.pad(p.grad.reshape(-1), (0, (-p.numel()) % 4)) for p in m.parameters()])
     assert torch.allclose(res["flat"], ref, rtol=1e-5, atol=1e-7)
     assert res["seeds"] == [1234, 1235]
 
@@ -87,7 +87,7 @@ def _reducer_worker(rank, world, port, out):
         ps[3].requires_grad_(False)                      # frozen: not part of the buffer at all
         # the segments deliberately do NOT follow the parameters' registration order; "rest" repeats them all
         r = OverlappedGradReducer([("late", [ps[2], ps[4]]), ("early", [ps[0], ps[1], ps[3]]), ("rest", ps)])
-        assert [n for n, _ in r.segments] == ["late", "early"] and r.numel == 8 + 3 + 12 + 5
+        assert [n for n, _ in r.segments] == ["late", "early"] and r.numel == 8 + 4 + 12 + 8
         results = []
         for step in range(2):
             bag = _Bag()
@@ -140,4 +140,4 @@ def test_sp_segments_cover_every_parameter_once():
     assert names == ["decoder", "fusion_bn", "trunk_deep", "trunk_shallow"]      # "rest" is empty: nothing was missed
     sizes = {n: sum(p.numel() for p in ps) for n, ps in r.segments}
     assert sizes["trunk_deep"] > 0.95 * (sizes["trunk_deep"] + sizes["trunk_shallow"]) and DEEP_FROM == 4
-    assert r.numel == sum(p.numel() for p in m.parameters())
+    assert r.numel == sum((p.numel() + 3) // 4 * 4 for p in m.parameters())
