@@ -61,7 +61,7 @@ def build(verbose=False):
             if did and log.strip():
                 print("== %s\n%s" % (src, log))
     if rebuilt or not os.path.exists(LIB):
-        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + [r[0] for r in results] + ["-lcudart"]
+        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + [r[0] for r in results] + ["-lcudart", "-ldl"]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (res.stdout, res.stderr))

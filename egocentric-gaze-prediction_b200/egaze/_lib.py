@@ -98,7 +98,7 @@ def _cur_device():
 _LAUNCHES = {"egaze_floss_fwd": 2, "egaze_conv3x3_tiles": 0, "egaze_check_device": 0, "egaze_sm_count": 0,
              "egaze_bn_bwd_blocks": 0, "egaze_conv3x3_stats_shape": 0, "egaze_bn_bwd_reduce": 2,
              "egaze_conv3x3_set_prof": 0, "egaze_lf_scratch": 0, "egaze_lf_fwd": 7, "egaze_lf_bwd": 12,
-             "egaze_adam_job_bytes": 0, "egaze_adam_multi": 2, "egaze_f16_weight_scale": 0}
+             "egaze_adam_job_bytes": 0, "egaze_jpeg_info": 0, "egaze_adam_multi": 2, "egaze_f16_weight_scale": 0}
 _launch_count = 0
 
 

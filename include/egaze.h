@@ -173,6 +173,25 @@ int egaze_crop_align_mean(const float* feat_nchw, const int* gaze, int B, int C,
 int egaze_weighted_map(const float* feat_nchw, const float* chn_weight, int B, int C, int HW, float* out, void* stream);
 int egaze_bilinear_up(const float* x, int B, int h, int w, int scale, int align_corners, float* out, void* stream);
 
+/* np.uint8(255 * x) / 255 element-wise (x in [0,1]): the quantisation of the maps the reference writes to image files between
+ * its stages (AT.py:228-230,249-250 ; read back by data/lateDataset.py:21-34) -- the "bit-compatible" option of the
+ * streaming pipeline */
+int egaze_quant_u8(const float* x, long long n, float* out, void* stream);
+
+/* ---- input pipeline on the device (replaces the per-sample CPU work of data/STdatas.py:50-73) ------------ */
+/* nvJPEG decode of one JPEG held in HOST memory into DEVICE uint8: [H][W][3] BGR interleaved like cv2.imread (gray == 0) or
+ * [H][W] (gray != 0, cv2.imread(.., 0)).  nvJPEG is dlopen'ed at first use; EGAZE_EUNSUPPORTED (-2) where it is missing. */
+int egaze_jpeg_info(const void* jpeg, long long nbytes, int* width, int* height, int* components);
+int egaze_jpeg_decode(const void* jpeg, long long nbytes, int gray, void* out, int H, int W, void* stream);
+/* bgr_u8 [N][H][W][3] -> out [N][3][H][W] fp32 = ((u/255) - mean) / std in the reference's (BGR) channel order (STdatas.py:51-55) */
+int egaze_image_norm(const void* bgr_u8, int N, int H, int W, float* out, void* stream);
+/* Sliding flow window: ring [V][T][2][H][W] uint8 holds the last T decoded (flow_x, flow_y) frames of V videos, so every flow
+ * frame is decoded / uploaded once instead of T times.  push: frames flow_x, flow_y [V][H][W] -> slot.  stack: out
+ * [V][2T][H][W] fp32, channel 2k / 2k+1 = ((u/255) - 0.5) / 0.5 of flow_x / flow_y of the k-th most recent frame (newest = slot of
+ * the latest push; count = frames pushed so far, capped at T: older positions repeat the oldest frame).  (STdatas.py:18-20,59-68) */
+int egaze_flow_push(void* ring, const void* flow_x, const void* flow_y, int V, int T, int H, int W, int slot, void* stream);
+int egaze_flow_stack(const void* ring, int V, int T, int H, int W, int newest, int count, float* out, void* stream);
+
 /* ---- lstmnet (models/LSTMnet.py:15-37) ------------------------------------------------------------------------ */
 int egaze_lstm_seq_fwd(const float* x, const float* h0, const float* c0, const float* const* w_ih,
                        const float* const* w_hh, const float* const* b_ih, const float* const* b_hh, const float* lin_w,
