@@ -37,6 +37,7 @@
 // bias / folded-BN affine / ReLU, 2x2 max or sum, ReLU-backward mask, nearest-2x replicate, packed bf16 split, coalesced
 // NHWC stores -- with BatchNorm batch statistics (shifted sums) and bias-gradient column sums accumulated in the same pass.
 #include "common.cuh"
+#include <new>
 
 namespace {
 
@@ -1033,12 +1034,25 @@ extern "C" int egaze_conv3x3_set_prof(void* buf) {
   return EGAZE_OK;
 }
 
-// See include/egaze.h for the contract.
-extern "C" int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, int N, int H, int W,
-                                int Cin_p, int Cout, const float* bias, const float* scale, const float* shift, int relu,
-                                int reduce, int ups, const void* mask, int mask_ups, float* out_f32, void* out_hi,
-                                void* out_lo, void* out_xb, float* stats, float* stats_cnt, float* colsum, int in_f16,
-                                int out_f16, float acc_scale, void* stream) {
+// A fully specified launch: tile / ring / accumulator configuration, the four TMA descriptors (cuTensorMapEncodeTiled) and the
+// kernel parameters.  Built once per distinct call (egaze_conv3x3_plan_create) or on the stack (egaze_conv3x3_tc).
+struct ConvPlan {
+  CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
+  ConvTcParams p;
+  int CS, ksteps, nsa, clusters, device;
+  size_t smem;
+};
+
+static int conv_build(ConvPlan* pl, const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, int N, int H, int W,
+                      int Cin_p, int Cout, const float* bias, const float* scale, const float* shift, int relu,
+                      int reduce, int ups, const void* mask, int mask_ups, float* out_f32, void* out_hi,
+                      void* out_lo, void* out_xb, float* stats, float* stats_cnt, float* colsum, int in_f16,
+                      int out_f16, float acc_scale) {
+  ConvTcParams& p = pl->p;
+  CUtensorMap& tmA_hi = pl->tmA_hi;
+  CUtensorMap& tmA_lo = pl->tmA_lo;
+  CUtensorMap& tmB_hi = pl->tmB_hi;
+  CUtensorMap& tmB_lo = pl->tmB_lo;
   EGAZE_CHECK_ARG(x_hi && w_hi, "conv3x3_tc: null operand");
   EGAZE_CHECK_ARG(!(x_lo && !w_lo), "conv3x3_tc: an activation lo plane needs a weight lo plane (operand modes: hi+lo x hi+lo, hi x hi+lo, hi x hi)");
   EGAZE_CHECK_ARG(acc_scale > 0.f, "conv3x3_tc: acc_scale must be positive");
@@ -1062,7 +1076,6 @@ extern "C" int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* 
     if (cluster_env != 1 && cluster_env != 2) cluster_env = 2;
   }
 
-  ConvTcParams p;
   memset(&p, 0, sizeof(p));
   p.N = N; p.H = H; p.W = W; p.Cin_p = Cin_p; p.Cout = Cout;
   p.KC = (Cin_p % 64 == 0) ? 64 : ((Cin_p % 32 == 0) ? 32 : 16);
@@ -1192,7 +1205,6 @@ extern "C" int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* 
   p.colsum = colsum;
   p.prof = g_conv_prof;
 
-  CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
   {
     uint64_t dims[4] = {(uint64_t)Cin_p, (uint64_t)W, (uint64_t)H, (uint64_t)N};
     uint64_t str[3] = {(uint64_t)Cin_p * 2, (uint64_t)W * Cin_p * 2, (uint64_t)H * W * Cin_p * 2};
@@ -1213,11 +1225,19 @@ extern "C" int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* 
   }
   int clusters = sm_count / CS;
   if (clusters > p.num_items) clusters = p.num_items;
+  pl->CS = CS; pl->ksteps = p.KC / 16; pl->nsa = nsa; pl->clusters = clusters; pl->smem = smem;
+  EGAZE_CUDA(cudaGetDevice(&pl->device));
+  return EGAZE_OK;
+}
+
+static int conv_run(const ConvPlan& pl, void* stream) {
+  const ConvTcParams& p = pl.p;
+  const int CS = pl.CS, nsa = pl.nsa;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((unsigned)(clusters * CS));
+  cfg.gridDim = dim3((unsigned)(pl.clusters * CS));
   cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = smem;
+  cfg.dynamicSmemBytes = pl.smem;
   cfg.stream = (cudaStream_t)stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1226,7 +1246,7 @@ extern "C" int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = CS > 1 ? 1 : 0;
-  const int ksteps = p.KC / 16;
+  const int ksteps = pl.ksteps;
 #define EGAZE_CONV_LAUNCH(NA, NS, KS, C)                                                                              \
   do {                                                                                                                \
     static unsigned long long attr_set = 0;                                                                           \
@@ -1234,7 +1254,7 @@ extern "C" int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* 
       EGAZE_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<NA, NS, KS, C>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                       224 * 1024));                                                                   \
     }                                                                                                                 \
-    EGAZE_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<NA, NS, KS, C>, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p));        \
+    EGAZE_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<NA, NS, KS, C>, pl.tmA_hi, pl.tmA_lo, pl.tmB_hi, pl.tmB_lo, p)); \
   } while (0)
 #define EGAZE_CONV_DISPATCH(NA, NS, C)                                                                                \
   do {                                                                                                                \
@@ -1255,5 +1275,53 @@ extern "C" int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* 
 #undef EGAZE_CONV_DISPATCH
 #undef EGAZE_CONV_LAUNCH
   EGAZE_LAUNCH_CHECK();
+  return EGAZE_OK;
+}
+
+// See include/egaze.h for the contract.
+extern "C" int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, int N, int H, int W,
+                                int Cin_p, int Cout, const float* bias, const float* scale, const float* shift, int relu,
+                                int reduce, int ups, const void* mask, int mask_ups, float* out_f32, void* out_hi,
+                                void* out_lo, void* out_xb, float* stats, float* stats_cnt, float* colsum, int in_f16,
+                                int out_f16, float acc_scale, void* stream) {
+  ConvPlan pl;
+  const int rc = conv_build(&pl, x_hi, x_lo, w_hi, w_lo, N, H, W, Cin_p, Cout, bias, scale, shift, relu, reduce, ups, mask, mask_ups,
+                            out_f32, out_hi, out_lo, out_xb, stats, stats_cnt, colsum, in_f16, out_f16, acc_scale);
+  return rc ? rc : conv_run(pl, stream);
+}
+
+// Plans (SURVEY 8b "egaze_plan_{create,destroy}: caches CUtensorMap descriptors per (ptr, shape)").  A plan freezes one
+// egaze_conv3x3_tc call -- every pointer, shape and flag -- with its four encoded TMA descriptors and its tile configuration;
+// egaze_conv3x3_plan_run launches it with two arguments.  The caller owns the handle and must not run it after any of the
+// buffers it names has been freed (the Python binding keys its plan cache on the full argument tuple, egaze/ops.py).
+extern "C" int egaze_conv3x3_plan_create(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, int N, int H,
+                                         int W, int Cin_p, int Cout, const float* bias, const float* scale, const float* shift,
+                                         int relu, int reduce, int ups, const void* mask, int mask_ups, float* out_f32,
+                                         void* out_hi, void* out_lo, void* out_xb, float* stats, float* stats_cnt,
+                                         float* colsum, int in_f16, int out_f16, float acc_scale, long long* plan) {
+  EGAZE_CHECK_ARG(plan, "conv3x3_plan_create: null handle pointer");
+  ConvPlan* pl = new (std::nothrow) ConvPlan;
+  EGAZE_CHECK_ARG(pl, "conv3x3_plan_create: out of host memory");
+  const int rc = conv_build(pl, x_hi, x_lo, w_hi, w_lo, N, H, W, Cin_p, Cout, bias, scale, shift, relu, reduce, ups, mask, mask_ups,
+                            out_f32, out_hi, out_lo, out_xb, stats, stats_cnt, colsum, in_f16, out_f16, acc_scale);
+  if (rc) {
+    delete pl;
+    return rc;
+  }
+  *plan = (long long)reinterpret_cast<intptr_t>(pl);
+  return EGAZE_OK;
+}
+
+extern "C" int egaze_conv3x3_plan_run(long long plan, void* stream) {
+  const ConvPlan* pl = reinterpret_cast<const ConvPlan*>((intptr_t)plan);
+  EGAZE_CHECK_ARG(pl, "conv3x3_plan_run: null plan");
+  int dev = -1;
+  EGAZE_CUDA(cudaGetDevice(&dev));
+  EGAZE_CHECK_ARG(dev == pl->device, "conv3x3_plan_run: plan was created on device %d, current device is %d", pl->device, dev);
+  return conv_run(*pl, stream);
+}
+
+extern "C" int egaze_plan_destroy(long long plan) {
+  delete reinterpret_cast<ConvPlan*>((intptr_t)plan);
   return EGAZE_OK;
 }

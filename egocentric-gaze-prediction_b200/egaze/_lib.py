@@ -98,7 +98,7 @@ def _cur_device():
 _LAUNCHES = {"egaze_floss_fwd": 2, "egaze_conv3x3_tiles": 0, "egaze_check_device": 0, "egaze_sm_count": 0,
              "egaze_bn_bwd_blocks": 0, "egaze_conv3x3_stats_shape": 0, "egaze_bn_bwd_reduce": 2,
              "egaze_conv3x3_set_prof": 0, "egaze_lf_scratch": 0, "egaze_lf_fwd": 7, "egaze_lf_bwd": 12,
-             "egaze_adam_job_bytes": 0, "egaze_jpeg_info": 0, "egaze_adam_multi": 2, "egaze_f16_weight_scale": 0}
+             "egaze_adam_job_bytes": 0, "egaze_jpeg_info": 0, "egaze_conv3x3_plan_create": 0, "egaze_plan_destroy": 0, "egaze_adam_multi": 2, "egaze_f16_weight_scale": 0}
 _launch_count = 0
 
 
@@ -148,6 +148,21 @@ def call(name, *args):
         _launch_count += 6 * int(args[6]) + 16  # per step: 2 x (gate grad + 2 small GEMMs); + Linear / weight-grad passes
     else:
         _launch_count += _LAUNCHES.get(name, 1)
+    if rc != 0:
+        raise RuntimeError("egaze: %s failed (rc=%d): %s" % (name, rc, last_error()))
+
+
+def call_on(dev, name, *args):
+    """call() for entry points whose arguments carry no tensor (plans, handles): runs on device index `dev`."""
+    global _launch_count
+    fn = getattr(lib(), name)
+    cargs = [(_raw_stream(dev) if a is STREAM else a) for a in args]
+    if dev != _cur_device():
+        with torch.cuda.device(dev):
+            rc = fn(*cargs)
+    else:
+        rc = fn(*cargs)
+    _launch_count += _LAUNCHES.get(name, 1)
     if rc != 0:
         raise RuntimeError("egaze: %s failed (rc=%d): %s" % (name, rc, last_error()))
 

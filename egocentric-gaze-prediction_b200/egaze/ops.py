@@ -300,7 +300,7 @@ pack_cache = _PackCache()
 
 
 # optional per-launch timing of the tensor-core conv (bench.py roofline): CUDA events on the launching stream
-_conv_timer = {"on": False, "events": []}
+_conv_timer = {"on": False, "events": [], "prof": False}
 
 
 def conv_timer_reset(enable):
@@ -341,6 +341,35 @@ def conv_stats_shape(Cout, precise):
     return _stats_shape_cache[key]
 
 
+# ---- conv plans: one frozen launch (TMA descriptors + tile configuration) per distinct argument tuple -----------------------
+# The caching allocator hands a training loop the same addresses step after step, so after the first step nearly every conv
+# call finds its plan: the host then passes 2 arguments through ctypes instead of 28 and skips four cuTensorMapEncodeTiled calls
+# and the tile search.  A plan is keyed on the FULL argument tuple (every pointer, shape and flag), so a hit is the same call by
+# construction, whatever tensor now lives at those addresses.  EGAZE_CONV_PLANS=0: always the plain entry point.
+_plans = {}
+_PLAN_CAP = 4096
+
+
+def _use_plans():
+    return os.environ.get("EGAZE_CONV_PLANS", "1") != "0" and not _conv_timer["prof"]
+
+
+def _conv_plan_run(dev, args):
+    key = (dev.index,) + tuple((a.data_ptr() if isinstance(a, torch.Tensor) else a) for a in args)
+    plan = _plans.get(key)
+    if plan is None:
+        for a in args:
+            if isinstance(a, torch.Tensor) and (not a.is_contiguous() or a.device != dev):
+                raise RuntimeError("egaze: conv3x3 needs contiguous tensors on one device")
+        h = ctypes.c_longlong(0)
+        call("egaze_conv3x3_plan_create", *(args + (ctypes.addressof(h),)))
+        if len(_plans) >= _PLAN_CAP:
+            for k in list(_plans)[:_PLAN_CAP // 4]:
+                call("egaze_plan_destroy", _plans.pop(k))
+        plan = _plans[key] = h.value
+    _lib.call_on(dev.index, "egaze_conv3x3_plan_run", plan, stream_ptr())
+
+
 def conv3x3(act, wpack, bias=None, scale=None, shift=None, relu=False, reduce=0, ups=False, mask=None,
             want_f32=False, want_split=True, stats=False, mask_ups=False, colsum=None, want_lo=True, xb=False):
     """3x3/pad-1 conv on the tcgen05 path.  wpack = (w_hi, w_lo, Cout_p, Cin_p, fmt) from pack_cache, in the activation's format.
@@ -372,11 +401,15 @@ def conv3x3(act, wpack, bias=None, scale=None, shift=None, relu=False, reduce=0,
     if _conv_timer["on"]:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-    call("egaze_conv3x3_tc", act.hi, x_lo, w_hi, w_lo if use_wlo else None, N, H, W, Cin_p, Cout,
-         bias, scale, shift, int(relu), int(reduce), int(ups), mask, int(mask_ups), out_f32,
-         out_act.hi if out_act is not None else None, out_act.lo if out_act is not None else None,
-         out_act.xb if out_act is not None else None,
-         st[0] if st else None, st[1] if st else None, colsum, fmt, fmt, (1.0 / f16_weight_scale()) if fmt else 1.0, stream_ptr())
+    args = (act.hi, x_lo, w_hi, w_lo if use_wlo else None, N, H, W, Cin_p, Cout,
+            bias, scale, shift, int(relu), int(reduce), int(ups), mask, int(mask_ups), out_f32,
+            out_act.hi if out_act is not None else None, out_act.lo if out_act is not None else None,
+            out_act.xb if out_act is not None else None,
+            st[0] if st else None, st[1] if st else None, colsum, fmt, fmt, (1.0 / f16_weight_scale()) if fmt else 1.0)
+    if _use_plans():
+        _conv_plan_run(dev, args)
+    else:
+        call("egaze_conv3x3_tc", *(args + (stream_ptr(),)))
     if _conv_timer["on"]:
         ev1.record()
         _conv_timer["events"].append((ev0, ev1, ("conv", N, H, W, Cin_p, Cout, int(reduce), int(ups), bool(stats))))

@@ -79,6 +79,16 @@ int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* w_hi, const
                      int reduce, int ups, const void* mask, int mask_ups, float* out_f32, void* out_hi, void* out_lo,
                      void* out_xb, float* stats, float* stats_cnt, float* colsum, int in_f16, int out_f16, float acc_scale,
                      void* stream);
+/* Plans: freeze one egaze_conv3x3_tc call (pointers, shapes, flags) with its encoded TMA descriptors (cuTensorMapEncodeTiled x4)
+ * and tile configuration; run it with (plan, stream).  Valid while the buffers it names are alive; destroy with
+ * egaze_plan_destroy.  ("egaze_plan_{create,destroy}: caches CUtensorMap descriptors per (ptr, shape)") */
+int egaze_conv3x3_plan_create(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, int N, int H, int W,
+                              int Cin_p, int Cout, const float* bias, const float* scale, const float* shift, int relu,
+                              int reduce, int ups, const void* mask, int mask_ups, float* out_f32, void* out_hi, void* out_lo,
+                              void* out_xb, float* stats, float* stats_cnt, float* colsum, int in_f16, int out_f16,
+                              float acc_scale, long long* plan);
+int egaze_conv3x3_plan_run(long long plan, void* stream);
+int egaze_plan_destroy(long long plan);
 /* Weight gradient: dwp[9][Cout][Cin_p] (fp32, ACCUMULATED: zero first) += sum_pixels dY (x) X-window; tcgen05 GEMM with the
  * pixel axis as K, MN-major operands straight from NHWC.  Cin_p % 64 == 0, Cout % 64 == 0.  (loss.backward(): SP.py:136) */
 int egaze_wgrad3x3_tc(const void* x_hi, const void* x_lo, const void* dy_hi, const void* dy_lo, int N, int H, int W,

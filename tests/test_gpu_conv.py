@@ -166,3 +166,24 @@ def test_conv3x3_bn_stats(cuda_dev, shape, numeric_mode):
             ref = F.max_pool2d(ref, 2, 2)
         assert (ops.nhwc_f32_to_nchw(f) - ref).abs().max().item() <= 2e-5 * max(1.0, ref.abs().max().item())
         assert (ops.from_split(a) - ref).abs().max().item() <= 5e-5 * max(1.0, ref.abs().max().item())
+
+
+def test_conv_plans_match_plain_entry(cuda_dev, monkeypatch):
+    """egaze_conv3x3_plan_create / _run (frozen TMA descriptors + tile configuration) == egaze_conv3x3_tc bit for bit,
+    and a repeated call with the same arguments reuses its plan."""
+    from egaze import ops
+    x, w, b = _mk(2, 28, 28, 128, 256, cuda_dev, seed=3)
+    act = ops.to_split(x)
+    wp = ops.pack_cache.get(w, 0, cols_p=act.Cp)
+    monkeypatch.setenv("EGAZE_CONV_PLANS", "0")
+    ref, _, _ = ops.conv3x3(act, wp, bias=b, relu=True)
+    monkeypatch.setenv("EGAZE_CONV_PLANS", "1")
+    n0 = len(ops._plans)
+    outs = []
+    for _ in range(3):
+        o, _, _ = ops.conv3x3(act, wp, bias=b, relu=True)
+        outs.append((o.hi.clone(), o.lo.clone()))
+        del o          # the allocator hands the next call the same output addresses: same argument tuple, same plan
+    assert len(ops._plans) - n0 <= 2
+    for hi, lo in outs:
+        assert torch.equal(hi, ref.hi) and torch.equal(lo, ref.lo)

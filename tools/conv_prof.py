@@ -3,6 +3,7 @@
 Prints, per layer, the average over CTAs of: cycles per work item, and the share of its time each role spent
 waiting on each barrier (producer: A/B slot free; MMA issuer: accumulator free, A landed, B landed; epilogue:
 accumulator ready)."""
+import os; os.environ["EGAZE_CONV_PLANS"] = "0"  # the cycle counters are a launch-time setting
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "egocentric-gaze-prediction_b200"))

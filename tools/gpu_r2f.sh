@@ -1,6 +1,6 @@
 #!/bin/bash
 TAG=${1:-r02f}; OUT=gpurun_out/$TAG; mkdir -p $OUT
-for f in test_gpu_conv test_gpu_optim test_gpu_backward test_gpu_models test_gpu_lf test_gpu_small test_gpu_golden test_gpu_graph; do
+for f in test_gpu_data test_gpu_conv test_gpu_optim test_gpu_backward test_gpu_models test_gpu_lf test_gpu_small test_gpu_golden test_gpu_graph; do
   timeout 900 python -m pytest tests/$f.py -m gpu -q -p no:cacheprovider > $OUT/$f.log 2>&1; echo "$f exit $?" | tee -a $OUT/summary.txt
   grep -E "passed|failed|error" $OUT/$f.log | tail -1; grep -E "^E  " $OUT/$f.log | head -6
 done
