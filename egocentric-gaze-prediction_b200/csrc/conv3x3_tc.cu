@@ -162,10 +162,15 @@ template <int RED, bool MASK, bool UPS, bool F32, int OUTK, bool STATS = false>
 __device__ __forceinline__ void epi_store(const ConvTcParams& p, const EpiTile& e, float4& cs, float4 k4 = float4(),
                                           float4* s1 = nullptr, float4* s2 = nullptr) {
   const int obw_mask = (1 << e.obw_log) - 1;
+  // The ReLU mask of an output pixel is fetched (read-only path) BEFORE the staged accumulators it gates are touched: issued
+  // next to the shared-memory loads, the global-load latency (~600 cycles) of all pixels of a trip overlaps instead of
+  // serialising inside the per-pixel code -- the masked data-gradient layers at 224^2 / 112^2 were bound by exactly that.
+  auto load_mask = [&](int ph, int pw) {
+    return __ldg(reinterpret_cast<const uint2*>(p.mask + e.mask_base + (size_t)(ph * e.mask_row + pw * e.mask_px)));
+  };
   // everything after the staged value(s) of output pixel `pix` are in registers
-  auto finish = [&](int pix, int ph, int pw, float4 v) {
+  auto finish = [&](int ph, int pw, float4 v, const uint2 mk) {
     if (MASK) {
-      const uint2 mk = __ldg(reinterpret_cast<const uint2*>(p.mask + e.mask_base + (size_t)(ph * e.mask_row + pw * e.mask_px)));
       if (!pos16(mk.x & 0xffffu)) v.x = 0.f;
       if (!pos16(mk.x >> 16)) v.y = 0.f;
       if (!pos16(mk.y & 0xffffu)) v.z = 0.f;
@@ -190,10 +195,20 @@ __device__ __forceinline__ void epi_store(const ConvTcParams& p, const EpiTile& 
       }
   };
   if (RED == 0) {
-    // four pixels per trip: the four staged float4 are loaded up front so their latency overlaps
+    // four pixels per trip: the four staged float4 (and masks) are loaded up front so their latency overlaps
     constexpr int U = 4;
     for (int pix0 = e.pl; pix0 < e.npix; pix0 += U * e.PS) {
       float4 a[U];
+      uint2 mk[U];
+      bool ok[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int pix = pix0 + u * e.PS;
+        const int ph = pix >> e.obw_log, pw = pix & obw_mask;
+        ok[u] = pix < e.npix && ph < e.vh && pw < e.vw;
+        mk[u] = make_uint2(0u, 0u);
+        if (MASK && ok[u]) mk[u] = load_mask(ph, pw);
+      }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int pix = pix0 + u * e.PS;
@@ -203,38 +218,67 @@ __device__ __forceinline__ void epi_store(const ConvTcParams& p, const EpiTile& 
       for (int u = 0; u < U; ++u) {
         const int pix = pix0 + u * e.PS;
         const int ph = pix >> e.obw_log, pw = pix & obw_mask;
-        if (pix >= e.npix || ph >= e.vh || pw >= e.vw) continue;
+        if (!ok[u]) continue;
         if (STATS) {
           const float dx = a[u].x - k4.x, dy = a[u].y - k4.y, dz = a[u].z - k4.z, dw = a[u].w - k4.w;
           s1->x += dx; s1->y += dy; s1->z += dz; s1->w += dw;
           s2->x = fmaf(dx, dx, s2->x); s2->y = fmaf(dy, dy, s2->y); s2->z = fmaf(dz, dz, s2->z); s2->w = fmaf(dw, dw, s2->w);
         }
-        finish(pix, ph, pw, epi_affine(a[u], e.s4, e.t4, e.lo_clamp));
+        finish(ph, pw, epi_affine(a[u], e.s4, e.t4, e.lo_clamp), mk[u]);
       }
     }
   } else {
-#pragma unroll 2
-    for (int pix = e.pl; pix < e.npix; pix += e.PS) {
-      const int ph = pix >> e.obw_log, pw = pix & obw_mask;
-      if (ph >= e.vh || pw >= e.vw) continue;
-      const uint32_t rb = e.st_addr + (uint32_t)(((2 * ph) * e.BW + 2 * pw) * e.ldst_b);
-      const float4 a = epi_affine(ptx::lds128(rb), e.s4, e.t4, e.lo_clamp);
-      const float4 b = epi_affine(ptx::lds128(rb + (uint32_t)e.ldst_b), e.s4, e.t4, e.lo_clamp);
-      const float4 c = epi_affine(ptx::lds128(rb + (uint32_t)(e.BW * e.ldst_b)), e.s4, e.t4, e.lo_clamp);
-      const float4 d = epi_affine(ptx::lds128(rb + (uint32_t)((e.BW + 1) * e.ldst_b)), e.s4, e.t4, e.lo_clamp);
-      float4 v;
-      if (RED == 1) {
-        v.x = fmaxf(fmaxf(a.x, b.x), fmaxf(c.x, d.x));
-        v.y = fmaxf(fmaxf(a.y, b.y), fmaxf(c.y, d.y));
-        v.z = fmaxf(fmaxf(a.z, b.z), fmaxf(c.z, d.z));
-        v.w = fmaxf(fmaxf(a.w, b.w), fmaxf(c.w, d.w));
-      } else {
-        v.x = (a.x + b.x) + (c.x + d.x);
-        v.y = (a.y + b.y) + (c.y + d.y);
-        v.z = (a.z + b.z) + (c.z + d.z);
-        v.w = (a.w + b.w) + (c.w + d.w);
+    // two output pixels (eight staged float4 + two masks) per trip
+    constexpr int U = 2;
+    for (int pix0 = e.pl; pix0 < e.npix; pix0 += U * e.PS) {
+      float4 q[U][4];
+      uint2 mk[U];
+      bool ok[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int pix = pix0 + u * e.PS;
+        const int ph = pix >> e.obw_log, pw = pix & obw_mask;
+        ok[u] = pix < e.npix && ph < e.vh && pw < e.vw;
+        mk[u] = make_uint2(0u, 0u);
+        if (MASK && ok[u]) mk[u] = load_mask(ph, pw);
       }
-      finish(pix, ph, pw, v);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int pix = pix0 + u * e.PS;
+        const int ph = pix >> e.obw_log, pw = pix & obw_mask;
+        if (pix < e.npix) {
+          const uint32_t rb = e.st_addr + (uint32_t)(((2 * ph) * e.BW + 2 * pw) * e.ldst_b);
+          q[u][0] = ptx::lds128(rb);
+          q[u][1] = ptx::lds128(rb + (uint32_t)e.ldst_b);
+          q[u][2] = ptx::lds128(rb + (uint32_t)(e.BW * e.ldst_b));
+          q[u][3] = ptx::lds128(rb + (uint32_t)((e.BW + 1) * e.ldst_b));
+        } else {
+          q[u][0] = q[u][1] = q[u][2] = q[u][3] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int pix = pix0 + u * e.PS;
+        const int ph = pix >> e.obw_log, pw = pix & obw_mask;
+        if (!ok[u]) continue;
+        const float4 a = epi_affine(q[u][0], e.s4, e.t4, e.lo_clamp);
+        const float4 b = epi_affine(q[u][1], e.s4, e.t4, e.lo_clamp);
+        const float4 c = epi_affine(q[u][2], e.s4, e.t4, e.lo_clamp);
+        const float4 d = epi_affine(q[u][3], e.s4, e.t4, e.lo_clamp);
+        float4 v;
+        if (RED == 1) {
+          v.x = fmaxf(fmaxf(a.x, b.x), fmaxf(c.x, d.x));
+          v.y = fmaxf(fmaxf(a.y, b.y), fmaxf(c.y, d.y));
+          v.z = fmaxf(fmaxf(a.z, b.z), fmaxf(c.z, d.z));
+          v.w = fmaxf(fmaxf(a.w, b.w), fmaxf(c.w, d.w));
+        } else {
+          v.x = (a.x + b.x) + (c.x + d.x);
+          v.y = (a.y + b.y) + (c.y + d.y);
+          v.z = (a.z + b.z) + (c.z + d.z);
+          v.w = (a.w + b.w) + (c.w + d.w);
+        }
+        finish(ph, pw, v, mk[u]);
+      }
     }
   }
 }

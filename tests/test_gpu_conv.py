@@ -184,6 +184,6 @@ def test_conv_plans_match_plain_entry(cuda_dev, monkeypatch):
         o, _, _ = ops.conv3x3(act, wp, bias=b, relu=True)
         outs.append((o.hi.clone(), o.lo.clone()))
         del o          # the allocator hands the next call the same output addresses: same argument tuple, same plan
-    assert len(ops._plans) - n0 <= 2
+    assert len(ops._plans) - n0 <= 3      # 1 when the allocator recycles the output addresses (it need not, e.g. under compute-sanitizer)
     for hi, lo in outs:
         assert torch.equal(hi, ref.hi) and torch.equal(lo, ref.lo)
