@@ -112,6 +112,53 @@ __device__ __forceinline__ uint2 pack_bf16x4(const float4& v) {
 }
 // value > 0 test on the raw 16 bits of a bf16 OR fp16 number (sign clear, not zero; NaN counts as positive in both formats,
 // which the ReLU masks never hold)
+// Sub-pixel decomposition of nearest-2x upsample -> 3x3 conv (conv3x3_tc.cu, ConvTcParams::sub).  Output phase py sees the
+// low-resolution rows through two taps a: py = 0: {w[0]} at row -1, {w[1] + w[2]} at row 0;  py = 1: {w[0] + w[1]} at row 0,
+// {w[2]} at row +1 -- the same along x.  w9: the 3x3 taps [r*3+s]; q16: [(py*2+px)*4 + a*2 + b], summed in fp32.
+__device__ __forceinline__ void egaze_subpixel_taps(const float* w9, float* q16) {
+#pragma unroll
+  for (int py = 0; py < 2; ++py)
+#pragma unroll
+    for (int px = 0; px < 2; ++px)
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          // rows / columns of the 3x3 kernel folded into tap (a, b) of phase (py, px): [lo, hi]
+          const int r0 = py == 0 ? (a == 0 ? 0 : 1) : (a == 0 ? 0 : 2), r1 = py == 0 ? (a == 0 ? 0 : 2) : (a == 0 ? 1 : 2);
+          const int s0 = px == 0 ? (b == 0 ? 0 : 1) : (b == 0 ? 0 : 2), s1 = px == 0 ? (b == 0 ? 0 : 2) : (b == 0 ? 1 : 2);
+          float acc = 0.f;
+#pragma unroll
+          for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int s = 0; s < 3; ++s)
+              if (r >= r0 && r <= r1 && s >= s0 && s <= s1) acc += w9[r * 3 + s];
+          q16[(py * 2 + px) * 4 + a * 2 + b] = acc;
+        }
+}
+// transpose of the map above: the gradient of 3x3 tap (r, s) is the sum of the sub-pixel planes it was folded into
+__device__ __forceinline__ void egaze_subpixel_taps_transpose(const float* q16, float* g9) {
+#pragma unroll
+  for (int t = 0; t < 9; ++t) g9[t] = 0.f;
+#pragma unroll
+  for (int py = 0; py < 2; ++py)
+#pragma unroll
+    for (int px = 0; px < 2; ++px)
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          const int r0 = py == 0 ? (a == 0 ? 0 : 1) : (a == 0 ? 0 : 2), r1 = py == 0 ? (a == 0 ? 0 : 2) : (a == 0 ? 1 : 2);
+          const int s0 = px == 0 ? (b == 0 ? 0 : 1) : (b == 0 ? 0 : 2), s1 = px == 0 ? (b == 0 ? 0 : 2) : (b == 0 ? 1 : 2);
+          const float q = q16[(py * 2 + px) * 4 + a * 2 + b];
+#pragma unroll
+          for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int s = 0; s < 3; ++s)
+              if (r >= r0 && r <= r1 && s >= s0 && s <= s1) g9[r * 3 + s] += q;
+        }
+}
+
 __device__ __forceinline__ bool pos16(uint32_t bits16) { return bits16 != 0u && bits16 < 0x8000u; }
 // decode element `fmt` (0 = bf16, 1 = fp16) from its 16 bits
 __device__ __forceinline__ float dec16(uint32_t bits16, int fmt) { return fmt ? f16_bits_to_float(bits16) : bf16_bits_to_float(bits16); }
@@ -293,6 +340,19 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
       ".reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
       "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "}\n" ::"r"(smem_u32(bar))
+      : "memory");
+}
+// The same with .relaxed semantics: for arrivals that publish no memory -- an epilogue warp telling the leader's MMA thread that
+// its tcgen05.ld reads of an accumulator stage have completed (tcgen05.wait::ld + tcgen05.fence::before_thread_sync precede it).
+// The .release form compiles to MEMBAR.ALL.GPU + ERRBAR, which waits for every earlier global store of the warp (the previous
+// tile's output) to be performed: ~8 % of the epilogue time of the rank-1 CTAs (ncu source page, round 2).
+__device__ __forceinline__ void mbar_arrive_leader_relaxed(uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t"
       "}\n" ::"r"(smem_u32(bar))
       : "memory");
 }

@@ -46,6 +46,26 @@ constexpr int kEpiThreads = 256;
 constexpr int kMaxSA = 4, kMaxSB = 9;
 constexpr int kEpiScratch = 32 + 8 * 3 * 64;   // floats of epilogue scratch behind the staging tile
 
+// Division by a launch constant as multiply-high + shift (exact for dividends < 2^31): the item decode runs once per tile in
+// every epilogue warp, and four hardware-less integer divisions there cost ~100 instructions of the ~700 a tile used to take.
+struct FastDiv {
+  uint32_t mul, shr;   // mul == 0: divisor 1
+};
+inline FastDiv make_fastdiv(int d) {
+  FastDiv f = {0u, 0u};
+  if (d > 1) {
+    int lg = 0;
+    while ((1u << lg) < (uint32_t)d) ++lg;
+    const unsigned p = 31u + (unsigned)lg;
+    f.mul = (uint32_t)(((1ull << p) + (uint64_t)d - 1ull) / (uint64_t)d);
+    f.shr = p - 32u;
+  }
+  return f;
+}
+__device__ __forceinline__ int fdiv(int n, const FastDiv f) {
+  return f.mul ? (int)(__umulhi((uint32_t)n, f.mul) >> f.shr) : n;
+}
+
 struct ConvTcParams {
   int N, H, W;         // conv output == input spatial size
   int Cin_p, Cout;     // Cin padded to a multiple of KC
@@ -55,6 +75,7 @@ struct ConvTcParams {
   int total_tiles;     // N * tiles_h * tiles_w
   int tile_groups;     // ceil(total_tiles / CS)
   int num_items;       // tile_groups * tiles_n
+  FastDiv fd_tn, fd_tw, fd_th;   // division by tiles_n / tiles_w / tiles_h
   int nsplit;          // planes of the WEIGHT operand: 1 = single pass, 2 = hi/lo split
   int nsplit_a;        // planes of the ACTIVATION operand: 2 = hi/lo (3 MMAs per product with nsplit = 2), 1 = hi only
                        //   (nsplit = 2: A_hi x [B_hi | B_lo], 2 MMAs per product -- the data-gradient mode)
@@ -80,6 +101,19 @@ struct ConvTcParams {
                        //     stays in its ring slot for all of the CTA's tiles.  For the 64 -> 64 channel layers at 224^2 the
                        //     per-tile weight stream (147 KB against a 47 KB activation window and ~1700 cycles of MMAs) is what
                        //     bounds the streaming schedule: ~110 B/clk/SM out of L2, 2.5x what the L2 delivers per SM.
+  // Sub-pixel decomposition of "nearest-2x upsample -> 3x3 conv" (the four upsample-fed decoder convs, reference
+  // models/model_SP.py:16-27): output pixel (2i+py, 2j+px) only ever sees a 2x2 neighbourhood of the LOW-resolution input, so the
+  // layer is four 2x2-tap convolutions (one per output phase) on the low-resolution map with weights pre-summed in fp32
+  // (packed [phase*4 + a*2 + b][Cout][Cin_p], layout.cu) -- 16 instead of 36 MACs per low-resolution pixel and weight.
+  //   1  forward: H x W is the low-resolution input, the output is 2H x 2W; one work item per (tile, n-tile, PHASE); phase
+  //      (py, px) reads window taps (py + a, px + b) and stores its 128 pixels at stride 2 from (py, px).
+  //   2  data gradient: the operand is the PHASE-PLANAR output gradient [4N][H][W][C] (image phase*N + n holds dY[n, 2i+py, 2j+px]),
+  //      one window per phase and K chunk, taps (2 - py - a, 2 - px - b); the output is the low-resolution H x W gradient
+  //      (the 2x2 sum that is the gradient of nn.Upsample happens inside the K loop).
+  int sub;
+  int out_planar;      // store the (H x W, even) output phase-planar: [4N][H/2][W/2][Cout] -- what a sub == 2 launch (and the
+                       //   sub-pixel weight gradient) reads
+  long long planar_stride;   // elements between two phase planes of the output
   int a_slot_bytes;    // bytes of one A plane slot (1024-aligned)
   int b_slot_bytes;    // bytes of one B plane slot
   int stage_off;       // byte offset of the epilogue staging buffer inside dynamic smem
@@ -104,24 +138,34 @@ struct ConvTcParams {
 };
 
 // cycle accounting of the three roles (debug aid, enabled by egaze_conv3x3_set_prof)
-#define PROF_T0(p) const long long prof_t0 = (p).prof ? clock64() : 0
-#define PROF_ADD(p, acc) do { if ((p).prof) (acc) += clock64() - prof_t0; } while (0)
+// (compiled in with -DEGAZE_CONV_PROF only: the run-time checks alone cost ~40 instructions per tile in every epilogue warp)
+#ifdef EGAZE_CONV_PROF
+#define PROF_ON(p) ((p).prof != nullptr)
+#else
+#define PROF_ON(p) false
+#endif
+#define PROF_T0(p) const long long prof_t0 = PROF_ON(p) ? clock64() : 0
+#define PROF_ADD(p, acc) do { if (PROF_ON(p)) (acc) += clock64() - prof_t0; } while (0)
 
 struct Item {
-  int nt, tile, img, h0, w0;
+  int nt, tile, img, h0, w0, phase;
   bool valid;
 };
 
 __device__ __forceinline__ Item decode_item(const ConvTcParams& p, int w, int cs, int rank) {
   Item it;
-  it.nt = w % p.tiles_n;                       // n-tile fastest: consecutive items reuse the activation window in L2
-  const int tg = w / p.tiles_n;
+  int tg = fdiv(w, p.fd_tn);
+  it.nt = w - tg * p.tiles_n;                  // n-tile fastest: consecutive items reuse the activation window in L2
+  it.phase = 0;
+  if (p.sub == 1) { it.phase = tg & 3; tg >>= 2; }   // then the four output phases of the same window
   it.tile = tg * cs + rank;
   it.valid = it.tile < p.total_tiles;
   const int t = it.valid ? it.tile : 0;
-  const int tw_i = t % p.tiles_w;
-  const int th_i = (t / p.tiles_w) % p.tiles_h;
-  it.img = it.valid ? t / (p.tiles_w * p.tiles_h) : p.N;   // img == N: every TMA box is out of bounds -> zeros
+  const int q = fdiv(t, p.fd_tw);
+  const int tw_i = t - q * p.tiles_w;
+  const int im = fdiv(q, p.fd_th);
+  const int th_i = q - im * p.tiles_h;
+  it.img = it.valid ? im : p.N;                // img == N: every TMA box is out of bounds -> zeros
   it.h0 = th_i * p.BH;
   it.w0 = tw_i * p.BW;
   return it;
@@ -140,6 +184,8 @@ struct EpiTile {
   size_t out_base;      // element offset of (img, oh0*rep, ow0*rep, first channel of this thread)
   int out_row, out_px;  // element pitch of one tile row / pixel in the output (already times the replicate factor)
   int ws_c;             // element pitch of one output image row (nearest-2x replicate)
+  int planar;           // phase-planar output (ConvTcParams::out_planar)
+  size_t planar_stride;
   size_t mask_base;     // same for the ReLU mask tensor
   int mask_row, mask_px;
 };
@@ -182,7 +228,11 @@ __device__ __forceinline__ void epi_store(const ConvTcParams& p, const EpiTile& 
     if (OUTK == 2 || OUTK == 3) split_f16x4(v, hi2, lo2);
     if (OUTK == 3) xb2 = pack_bf16x4(v);
     if (OUTK == 4) hi2 = pack_bf16x4(v);
-    const size_t off = e.out_base + (size_t)(ph * e.out_row + pw * e.out_px);
+    size_t off;
+    if (!UPS && e.planar)
+      off = e.out_base + (size_t)((ph & 1) * 2 + (pw & 1)) * e.planar_stride + (size_t)((ph >> 1) * e.out_row + (pw >> 1) * e.out_px);
+    else
+      off = e.out_base + (size_t)(ph * e.out_row + pw * e.out_px);
 #pragma unroll
     for (int dy = 0; dy < (UPS ? 2 : 1); ++dy)
 #pragma unroll
@@ -428,8 +478,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
   const int row_bytes = p.KC * 2;
   const int AW = p.win ? p.BW + 2 : p.BW;                        // pixel columns of one activation window
   const uint32_t a_box_bytes = (uint32_t)((p.BH + 2) * AW * row_bytes);
-  const int a_loads = p.win ? 1 : 3;                             // windows per K chunk (one per horizontal tap, or one in all)
-  const int a_taps = p.win ? 9 : 3;                              // weight boxes consumed per window
+  // windows per K chunk: one per horizontal tap, one in all (window mode), or one per phase plane (sub-pixel data gradient)
+  const int a_loads = p.sub == 2 ? 4 : (p.win ? 1 : 3);
+  const int a_taps = p.sub ? 4 : (p.win ? 9 : 3);                // weight boxes consumed per window
   const uint32_t b_box_bytes = (uint32_t)(p.BN * row_bytes);
   const int b_rows_cta = p.BN / CS;                              // weight rows this CTA fetches (and multicasts / keeps, pair mode)
 
@@ -443,7 +494,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
       const bool leader = ptx::elect_one();
       int sa = 0, sb = 0;
       long long prof_c[2] = {0, 0};
-      const long long prof_start = p.prof ? clock64() : 0;
+      const long long prof_start = PROF_ON(p) ? clock64() : 0;
       uint32_t a_par = 1, b_par = 1;  // a fresh mbarrier passes a parity-1 wait: the first lap never blocks
       for (int w = cluster_id; w < p.num_items; w += num_clusters) {
         const Item it = decode_item(p, w, CS, rank);
@@ -453,25 +504,29 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
           for (int al = 0; al < a_loads; ++al) {
             uint8_t* a_dst = a_ring + (size_t)sa * NSA * p.a_slot_bytes;
             const int wx = p.win ? it.w0 - 1 : it.w0 - 1 + al;
+            // sub-pixel data gradient: window `al` comes from phase plane al (images al*N ..); an invalid tile reads past the end
+            const int img_c = p.sub == 2 ? (it.valid ? al * p.N + it.img : 4 * p.N) : it.img;
             if (leader) {
               { PROF_T0(p); ptx::mbar_wait(&a_empty[sa], a_par); PROF_ADD(p, prof_c[0]); }
               if (pair) {
                 // both CTAs' windows are accounted on rank 0's barrier (its MMA thread consumes both)
                 if (rank == 0) ptx::mbar_arrive_expect_tx(&a_full[sa], 2 * a_box_bytes * NSA);
-                ptx::tma_load_4d_2sm(a_dst, &tmA_hi, &a_full[sa], kc * p.KC, wx, it.h0 - 1, it.img);
+                ptx::tma_load_4d_2sm(a_dst, &tmA_hi, &a_full[sa], kc * p.KC, wx, it.h0 - 1, img_c);
                 if (NSA == 2)
-                  ptx::tma_load_4d_2sm(a_dst + p.a_slot_bytes, &tmA_lo, &a_full[sa], kc * p.KC, wx, it.h0 - 1, it.img);
+                  ptx::tma_load_4d_2sm(a_dst + p.a_slot_bytes, &tmA_lo, &a_full[sa], kc * p.KC, wx, it.h0 - 1, img_c);
               } else {
                 ptx::mbar_arrive_expect_tx(&a_full[sa], a_box_bytes * NSA);
-                ptx::tma_load_4d(a_dst, &tmA_hi, &a_full[sa], kc * p.KC, wx, it.h0 - 1, it.img);
+                ptx::tma_load_4d(a_dst, &tmA_hi, &a_full[sa], kc * p.KC, wx, it.h0 - 1, img_c);
                 if (NSA == 2)
-                  ptx::tma_load_4d(a_dst + p.a_slot_bytes, &tmA_lo, &a_full[sa], kc * p.KC, wx, it.h0 - 1, it.img);
+                  ptx::tma_load_4d(a_dst + p.a_slot_bytes, &tmA_lo, &a_full[sa], kc * p.KC, wx, it.h0 - 1, img_c);
               }
             }
             if (++sa == p.SA) { sa = 0; a_par ^= 1; }
             for (int t = 0; t < a_taps; ++t) {
               const int s = p.win ? t / 3 : al, r = p.win ? t - 3 * s : t;
-              const int brow = (r * 3 + s) * p.Cout + n0 + rank * b_rows_cta;
+              // weight box of this step: tap (r, s), or sub-pixel box [phase*4 + t] (phase = the item's / the window's)
+              const int wbox = p.sub ? (p.sub == 1 ? it.phase : al) * 4 + t : r * 3 + s;
+              const int brow = wbox * p.Cout + n0 + rank * b_rows_cta;
               // pair mode: this CTA keeps only ITS half of the box (rows rank*BN/2 ..), hi plane then lo plane back to back;
               // multicast mode: it fetches its half and multicasts it into every CTA's full-size slot
               uint8_t* b_dst = b_ring + (size_t)sb * NSPLIT * p.b_slot_bytes + (pair ? 0 : (size_t)rank * b_rows_cta * row_bytes);
@@ -498,7 +553,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
           }
         }
       }
-      if (p.prof && leader) {
+      if (PROF_ON(p) && leader) {
         long long* o = p.prof + (size_t)blockIdx.x * 16;
         o[0] = prof_c[0]; o[1] = prof_c[1]; o[2] = clock64() - prof_start;
       }
@@ -531,12 +586,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
       const uint32_t bn = (uint32_t)p.BN;
       int sa = 0, sb = 0, as = 0;
       long long prof_c[3] = {0, 0, 0};
-      const long long prof_start = p.prof ? clock64() : 0;
+      const long long prof_start = PROF_ON(p) ? clock64() : 0;
       uint32_t a_par = 0, b_par = 0, acc_par[2] = {1, 1};
       // Only the elected lane waits on barriers and issues; the other lanes just keep the loop nest warp-uniform.
       bool a_ready = false, a_next_ready = false, b_ready = false;
       for (int w = cluster_id; w < p.num_items; w += num_clusters) {
         const bool b_resident = p.wstat && w != cluster_id;   // weight-stationary: boxes already in their slots, never released
+        const int phase = p.sub == 1 ? fdiv(w, p.fd_tn) & 3 : 0;
         if (leader) { PROF_T0(p); ptx::mbar_wait(&acc_empty[as], acc_par[as]); PROF_ADD(p, prof_c[0]); }   // epilogue has drained this accumulator stage
         acc_par[as] ^= 1;
         ptx::tc_fence_after();
@@ -552,7 +608,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
 #pragma unroll 1
             for (int t = 0; t < a_taps; ++t) {
               uint64_t ad;
-              if (p.win) {
+              if (p.sub) {
+                // window position of 2x2 tap (a, b) = (t >> 1, t & 1): forward phase (py, px) reads (py + a, px + b); the data
+                // gradient reads phase plane `al` at (2 - py - a, 2 - px - b)
+                const int a = t >> 1, b = t & 1;
+                const int r = p.sub == 1 ? (phase >> 1) + a : 2 - (al >> 1) - a;
+                const int s = p.sub == 1 ? (phase & 1) + b : 2 - (al & 1) - b;
+                ad = a_desc0 + (uint64_t)((uint32_t)r * r_step16 + (uint32_t)s * s_step16);
+              } else if (p.win) {
                 const int s = t / 3, r = t - 3 * s;
                 ad = a_desc0 + (uint64_t)((uint32_t)r * r_step16 + (uint32_t)s * s_step16);
               } else {
@@ -649,7 +712,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         }
         as ^= 1;
       }
-      if (p.prof && leader) {
+      if (PROF_ON(p) && leader) {
         long long* o = p.prof + (size_t)blockIdx.x * 16;
         o[3] = prof_c[0]; o[4] = prof_c[1]; o[5] = prof_c[2]; o[6] = clock64() - prof_start;
       }
@@ -722,24 +785,43 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
           lean_mode = 0;
       }
     }
-    const int rep = p.ups ? 2 : 1;
+    const int rep = (p.ups || p.sub == 1) ? 2 : 1;   // sub-pixel forward: this phase's pixels sit at stride 2 in the 2H x 2W output
     const int Hs = Ho * rep, Ws = Wo * rep;
     int as = 0;
-    uint32_t full_par[2] = {0, 0};
+    uint32_t full_par = 0;                   // bit `as`: phase parity of accumulator stage `as` (a register, not a local array)
     long long prof_c[2] = {0, 0};
     long long prof_e[5] = {0, 0, 0, 0, 0};   // phase 1 | barrier | store loop | reductions | barrier
-    const long long prof_start = p.prof ? clock64() : 0;
+    const long long prof_start = PROF_ON(p) ? clock64() : 0;
+    // Everything about a tile that does not depend on the tile is set up ONCE: the per-tile code of the eight epilogue warps
+    // (two per scheduler, so nothing hides its latency) is what bounds the 64-output-channel layers at 224^2, and it used to
+    // spend ~700 instructions per warp and tile on item decoding, address arithmetic and re-loading the affine constants.
+    const float asc = p.acc_scale;           // fp16 weights are packed pre-scaled by a power of two: folded into the affine scale
+    const int mf = p.mask_ups ? 2 : 1;
+    EpiTile e;
+    e.st_addr = stage_s + (uint32_t)(g * 16);
+    e.ldst_b = ldst * 4;
+    e.pl = pl; e.PS = PS; e.npix = oBH * oBW; e.obw_log = obw_log;
+    e.BW = p.BW;
+    e.lo_clamp = p.relu ? 0.f : -INFINITY;
+    e.out_row = rep * Ws * p.Cout; e.out_px = rep * p.Cout; e.ws_c = Ws * p.Cout;
+    e.planar = p.out_planar; e.planar_stride = (size_t)p.planar_stride;
+    if (p.out_planar) { e.out_row = (Wo >> 1) * p.Cout; e.out_px = p.Cout; }
+    e.mask_row = mf * mf * Wo * p.Cout; e.mask_px = mf * p.Cout;
+    e.vh = e.vw = 0; e.out_base = e.mask_base = 0;
+    e.s4 = e.t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool affine = p.bias || p.scale || asc != 1.f;
+    int n0_have = -1;                        // channel chunk whose affine constants e.s4 / e.t4 hold
     for (int w = cluster_id; w < p.num_items; w += num_clusters) {
       const Item it = decode_item(p, w, CS, rank);
       const int h0 = it.h0, w0 = it.w0, img = it.img;
-      { PROF_T0(p); ptx::mbar_wait(&acc_full[as], full_par[as]); PROF_ADD(p, prof_c[0]); }
-      full_par[as] ^= 1;
+      { PROF_T0(p); ptx::mbar_wait(&acc_full[as], (full_par >> as) & 1u); PROF_ADD(p, prof_c[0]); }
+      full_par ^= 1u << as;
       ptx::tc_fence_after();
       const uint32_t t_acc = tmem_base + (uint32_t)as * acc_cols + ((uint32_t)(lg * 32) << 16);
 
       for (int cc = 0; cc < p.BN; cc += CW) {
         const int n0 = it.nt * p.BN + cc;   // first output channel of this chunk
-        const long long tp0 = p.prof ? clock64() : 0;
+        const long long tp0 = PROF_ON(p) ? clock64() : 0;
         // -- phase 1: TMEM -> registers -> smem staging [128][CW+4] (raw fp32 accumulators)
         for (int c0 = colsel * 32; c0 < CW; c0 += 64) {
           uint32_t v[32];
@@ -767,10 +849,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
           } else {
             ptx::tmem_ld_wait();
           }
-          if (p.acc_scale != 1.f) {   // fp16 weights are packed pre-scaled by a power of two: undo it (exact)
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * p.acc_scale);
-          }
+          // (the staged values are the raw accumulators: p.acc_scale is applied with the affine constants / the statistics)
           const uint32_t dst = stage_s + (uint32_t)((m * ldst + c0) * 4);
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
@@ -782,13 +861,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) {
-            if (pair && rank != 0) ptx::mbar_arrive_leader(&acc_empty[as]);   // rank 0's MMA thread waits for both CTAs
+            if (pair && rank != 0) ptx::mbar_arrive_leader_relaxed(&acc_empty[as]);   // rank 0's MMA thread waits for both CTAs
             else ptx::mbar_arrive(&acc_empty[as]);
           }
         }
-        const long long tp1 = p.prof ? clock64() : 0;
+        const long long tp1 = PROF_ON(p) ? clock64() : 0;
         ptx::named_bar_sync(1, kEpiThreads);
-        const long long tp2 = p.prof ? clock64() : 0;
+        const long long tp2 = PROF_ON(p) ? clock64() : 0;
 
         float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
         float4 k4 = cs, s1v = cs, s2v = cs;
@@ -809,32 +888,29 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
           // -- phase 3: (+bias, *scale+shift, relu) -> 2x2 max/sum -> mask -> coalesced NHWC stores.
           //    A thread keeps ONE float4 channel group and strides over pixels: its affine constants live in registers.
           const int ch = n0 + g * 4;
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = make_float4(1.f, 1.f, 1.f, 1.f), t4 = b4;
-          if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + ch));
-          if (p.scale) {
-            s4 = __ldg(reinterpret_cast<const float4*>(p.scale + ch));
-            t4 = __ldg(reinterpret_cast<const float4*>(p.shift + ch));
+          if (n0 != n0_have) {   // one n-tile and one chunk per tile (the 64-channel layers): loaded once per launch
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), s4 = make_float4(1.f, 1.f, 1.f, 1.f), t4 = b4;
+            if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + ch));
+            if (p.scale) {
+              s4 = __ldg(reinterpret_cast<const float4*>(p.scale + ch));
+              t4 = __ldg(reinterpret_cast<const float4*>(p.shift + ch));
+            }
+            // fold: v = (asc*acc + b)*s + t = acc*(asc*s) + (b*s + t)
+            e.t4 = make_float4(fmaf(b4.x, s4.x, t4.x), fmaf(b4.y, s4.y, t4.y), fmaf(b4.z, s4.z, t4.z), fmaf(b4.w, s4.w, t4.w));
+            e.s4 = make_float4(s4.x * asc, s4.y * asc, s4.z * asc, s4.w * asc);
+            n0_have = n0;
           }
-          // fold: v = (acc + b)*s + t = acc*s + (b*s + t)
-          t4 = make_float4(fmaf(b4.x, s4.x, t4.x), fmaf(b4.y, s4.y, t4.y), fmaf(b4.z, s4.z, t4.z), fmaf(b4.w, s4.w, t4.w));
-          const bool affine = p.bias || p.scale;
+          const float4 s4 = e.s4, t4 = e.t4;
           const int oh0 = p.reduce ? h0 / 2 : h0;
           const int ow0 = p.reduce ? w0 / 2 : w0;
           bool done = false;
           if (lean_ok) {
-            EpiTile e;
-            e.st_addr = stage_s + (uint32_t)(g * 16);
-            e.ldst_b = ldst * 4;
-            e.pl = pl; e.PS = PS; e.npix = oBH * oBW; e.obw_log = obw_log;
             e.vh = min(oBH, Ho - oh0); e.vw = min(oBW, Wo - ow0);
-            e.BW = p.BW;
-            e.s4 = s4; e.t4 = t4;
-            e.lo_clamp = p.relu ? 0.f : -INFINITY;
-            e.out_base = ((size_t)(img * Hs + oh0 * rep) * Ws + (size_t)(ow0 * rep)) * p.Cout + ch;
-            e.out_row = rep * Ws * p.Cout; e.out_px = rep * p.Cout; e.ws_c = Ws * p.Cout;
-            const int mf = p.mask_ups ? 2 : 1;
-            e.mask_base = ((size_t)(img * mf * Ho + mf * oh0) * (mf * Wo) + (size_t)(mf * ow0)) * p.Cout + ch;
-            e.mask_row = mf * mf * Wo * p.Cout; e.mask_px = mf * p.Cout;
+            if (p.out_planar)   // (oh0, ow0) are even: the tile's phase-(0,0) origin inside one [H/2][W/2] plane
+              e.out_base = ((size_t)(img * (Ho >> 1) + (oh0 >> 1)) * (Wo >> 1) + (size_t)(ow0 >> 1)) * p.Cout + ch;
+            else
+              e.out_base = ((size_t)(img * Hs + oh0 * rep + (it.phase >> 1)) * Ws + (size_t)(ow0 * rep + (it.phase & 1))) * p.Cout + ch;
+            if (p.mask) e.mask_base = ((size_t)(img * mf * Ho + mf * oh0) * (mf * Wo) + (size_t)(mf * ow0)) * p.Cout + ch;
             done = true;
             // statistics ride on mode 1 only, column sums on the masked modes only; anything else takes the generic loop
             switch ((p.stats && lean_mode != 1) || (p.colsum && lean_mode != 5 && lean_mode != 6) ? 0 : lean_mode) {
@@ -915,9 +991,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                 else split_bf16x4(v, hi2, lo2);
               }
               if (p.out_xb) xb2 = pack_bf16x4(v);
-              for (int dy = 0; dy < rep; ++dy)
-                for (int dx = 0; dx < rep; ++dx) {
-                  const size_t off = ((size_t)(img * Hs + oh * rep + dy) * Ws + (ow * rep + dx)) * p.Cout + ch;
+              const int nrep = p.ups ? 2 : 1;
+              for (int dy = 0; dy < nrep; ++dy)
+                for (int dx = 0; dx < nrep; ++dx) {
+                  size_t off = ((size_t)(img * Hs + oh * rep + dy + (it.phase >> 1)) * Ws + (ow * rep + dx + (it.phase & 1))) * p.Cout + ch;
+                  if (p.out_planar)
+                    off = (size_t)((oh & 1) * 2 + (ow & 1)) * (size_t)p.planar_stride +
+                          ((size_t)(img * (Ho >> 1) + (oh >> 1)) * (Wo >> 1) + (size_t)(ow >> 1)) * p.Cout + ch;
                   if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + off) = v;
                   if (p.out_hi) *reinterpret_cast<uint2*>(p.out_hi + off) = hi2;
                   if (p.out_lo) *reinterpret_cast<uint2*>(p.out_lo + off) = lo2;
@@ -928,7 +1008,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
             while (pw >= oBW) { pw -= oBW; ++ph; }
           }
         }
-        const long long tp3 = p.prof ? clock64() : 0;
+        const long long tp3 = PROF_ON(p) ? clock64() : 0;
         // Fold the per-thread sums: lanes of a warp that share a channel group are gpp lanes apart (shuffles), then every
         // warp parks its partials in its own scratch row; after the chunk's closing barrier one thread per channel adds
         // the eight rows into the CTA's running sums.  (Shared-memory float atomics are CAS loops: 2k cycles per chunk.)
@@ -955,7 +1035,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
             if (p.colsum) *reinterpret_cast<float4*>(row + 128) = cs;
           }
         }
-        const long long tp4 = p.prof ? clock64() : 0;
+        const long long tp4 = PROF_ON(p) ? clock64() : 0;
         ptx::named_bar_sync(1, kEpiThreads);   // staging is free for the next chunk / item
         if (fold && et < 3 * 64) {
           // et -> (which sum, channel); the next write to `part` is two barriers away
@@ -968,14 +1048,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
             dst[n0 + c] += v;
           }
         }
-        if (p.prof) {
+        if (PROF_ON(p)) {
           const long long tp5 = clock64();
           prof_e[0] += tp1 - tp0; prof_e[1] += tp2 - tp1; prof_e[2] += tp3 - tp2; prof_e[3] += tp4 - tp3; prof_e[4] += tp5 - tp4;
         }
       }
       as ^= 1;
     }
-    if (p.prof && et == 0) {
+    if (PROF_ON(p) && et == 0) {
       long long* o = p.prof + (size_t)blockIdx.x * 16;
       o[7] = prof_c[0]; o[8] = clock64() - prof_start; o[9] = (p.num_items - cluster_id + num_clusters - 1) / num_clusters;
       for (int i = 0; i < 5; ++i) o[10 + i] = prof_e[i];
@@ -990,10 +1070,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
       for (int c = et; c < p.Cout; c += kEpiThreads) {
         const float n = red[c / p.BN];
         float mean = 0.f, m2 = 0.f;
-        if (n > 0.f) {
+        if (n > 0.f) {   // the sums were taken over the raw accumulators: scale them (acc_scale is a power of two: exact)
           const float s1 = st_s1[c];
-          mean = st_k[c] + s1 / n;
-          m2 = fmaxf(st_s2[c] - s1 * s1 / n, 0.f);
+          mean = (st_k[c] + s1 / n) * p.acc_scale;
+          m2 = fmaxf(st_s2[c] - s1 * s1 / n, 0.f) * (p.acc_scale * p.acc_scale);
         }
         p.stats[((size_t)blockIdx.x * 2 + 0) * p.Cout + c] = mean + (p.bias ? __ldg(p.bias + c) : 0.f);
         p.stats[((size_t)blockIdx.x * 2 + 1) * p.Cout + c] = m2;
@@ -1074,6 +1154,9 @@ static long long* g_conv_prof = nullptr;
 // producer: 0 a_empty wait, 1 b_empty wait, 2 total | MMA: 3 acc_empty, 4 a_full, 5 b_full, 6 total | epilogue: 7 acc_full
 // wait, 8 total, 9 items).  Pass null to switch it off.
 extern "C" int egaze_conv3x3_set_prof(void* buf) {
+#ifndef EGAZE_CONV_PROF
+  EGAZE_CHECK_ARG(!buf, "conv3x3_set_prof: libegaze.so was built without -DEGAZE_CONV_PROF (EGAZE_CONV_PROF=1 python csrc/build.py)");
+#endif
   g_conv_prof = (long long*)buf;
   return EGAZE_OK;
 }
@@ -1091,7 +1174,7 @@ static int conv_build(ConvPlan* pl, const void* x_hi, const void* x_lo, const vo
                       int Cin_p, int Cout, const float* bias, const float* scale, const float* shift, int relu,
                       int reduce, int ups, const void* mask, int mask_ups, float* out_f32, void* out_hi,
                       void* out_lo, void* out_xb, float* stats, float* stats_cnt, float* colsum, int in_f16,
-                      int out_f16, float acc_scale) {
+                      int out_f16, float acc_scale, int sub, int out_planar) {
   ConvTcParams& p = pl->p;
   CUtensorMap& tmA_hi = pl->tmA_hi;
   CUtensorMap& tmA_lo = pl->tmA_lo;
@@ -1106,6 +1189,11 @@ static int conv_build(ConvPlan* pl, const void* x_hi, const void* x_lo, const vo
   EGAZE_CHECK_ARG(Cout % 16 == 0 && Cout >= 16, "conv3x3_tc: Cout=%d must be a multiple of 16", Cout);
   EGAZE_CHECK_ARG(!(reduce && ((H | W) & 1)), "conv3x3_tc: 2x2 reduce needs even H, W");
   EGAZE_CHECK_ARG(out_f32 || out_hi, "conv3x3_tc: no output");
+  EGAZE_CHECK_ARG(sub >= 0 && sub <= 2, "conv3x3_tc: sub must be 0, 1 or 2");
+  EGAZE_CHECK_ARG(!(sub && (reduce || ups || stats || Cin_p % 64 != 0)),
+                  "conv3x3_tc: the sub-pixel modes need Cin_p %% 64 == 0 and take no reduce / ups / stats");
+  EGAZE_CHECK_ARG(!(out_planar && (reduce || ups || sub == 1 || ((H | W) & 1))),
+                  "conv3x3_tc: a phase-planar output needs even H, W and no reduce / ups / sub-pixel forward");
 
   static int sm_count = 0;
   if (sm_count == 0) {
@@ -1123,7 +1211,7 @@ static int conv_build(ConvPlan* pl, const void* x_hi, const void* x_lo, const vo
   memset(&p, 0, sizeof(p));
   p.N = N; p.H = H; p.W = W; p.Cin_p = Cin_p; p.Cout = Cout;
   p.KC = (Cin_p % 64 == 0) ? 64 : ((Cin_p % 32 == 0) ? 32 : 16);
-  pick_tile(H, W, reduce != 0, &p.BH, &p.BW);
+  pick_tile(H, W, reduce != 0 || out_planar, &p.BH, &p.BW);
   static int win_env = -1;
   if (win_env < 0) {
     const char* e = getenv("EGAZE_CONV_WINDOW");
@@ -1140,13 +1228,17 @@ static int conv_build(ConvPlan* pl, const void* x_hi, const void* x_lo, const vo
     const int bn = conv_pick_bn(Cout, precise), ns = precise ? 2 : 1;
     const int stage_b = ((128 * ((bn < 64 ? bn : 64) + 4) * 4 + kEpiScratch * 4 + (stats ? Cout * 3 * 4 : 0) + (colsum ? Cout * 4 : 0) + 1023) / 1024) * 1024;
     const int sb_w = (222 * 1024 - stage_b - 2 * nsa * 23552) / (ns * bn * 128);
-    if (eff_w >= eff_c * 0.999 && sb_w >= win_minsb) {
+    if ((eff_w >= eff_c * 0.999 && sb_w >= win_minsb) || sub) {
       p.win = 1;
       p.win_bo = win_env == 2 ? 1 : 0;
       p.BH = wbh;
       p.BW = 8;
     }
   }
+  EGAZE_CHECK_ARG(!(sub && !p.win), "conv3x3_tc: the sub-pixel modes run in window mode only (EGAZE_CONV_WINDOW=0?)");
+  p.sub = sub;
+  p.out_planar = out_planar;
+  p.planar_stride = (long long)N * (H / 2) * (W / 2) * Cout;
   p.nsplit = precise ? 2 : 1;
   p.nsplit_a = nsa;
   p.in_f16 = in_f16;
@@ -1159,7 +1251,8 @@ static int conv_build(ConvPlan* pl, const void* x_hi, const void* x_lo, const vo
   int CS = cluster_env;
   if (p.total_tiles < 2 || (p.BN / 2) % 8 != 0) CS = 1;
   p.tile_groups = ceil_div(p.total_tiles, CS);
-  p.num_items = p.tile_groups * p.tiles_n;
+  p.num_items = p.tile_groups * p.tiles_n * (sub == 1 ? 4 : 1);
+  p.fd_tn = make_fastdiv(p.tiles_n); p.fd_tw = make_fastdiv(p.tiles_w); p.fd_th = make_fastdiv(p.tiles_h);
   const int row_bytes = p.KC * 2;
   int a_rows = (p.BH + 2) * p.BW;
   if (a_rows < 2 * p.BW + 128) a_rows = 2 * p.BW + 128;
@@ -1199,7 +1292,7 @@ static int conv_build(ConvPlan* pl, const void* x_hi, const void* x_lo, const vo
       wstat_env = e ? atoi(e) : 1;
     }
     const int boxes = 9 * (Cin_p / p.KC);
-    if (wstat_env && p.pair && p.tiles_n == 1 && boxes <= kMaxSB && sb >= boxes) {
+    if (wstat_env && !sub && p.pair && p.tiles_n == 1 && boxes <= kMaxSB && sb >= boxes) {
       p.wstat = 1;
       sb = boxes;
     }
@@ -1250,7 +1343,7 @@ static int conv_build(ConvPlan* pl, const void* x_hi, const void* x_lo, const vo
   p.prof = g_conv_prof;
 
   {
-    uint64_t dims[4] = {(uint64_t)Cin_p, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    uint64_t dims[4] = {(uint64_t)Cin_p, (uint64_t)W, (uint64_t)H, (uint64_t)(sub == 2 ? 4 * N : N)};
     uint64_t str[3] = {(uint64_t)Cin_p * 2, (uint64_t)W * Cin_p * 2, (uint64_t)H * W * Cin_p * 2};
     uint32_t box[4] = {(uint32_t)p.KC, (uint32_t)(p.win ? p.BW + 2 : p.BW), (uint32_t)(p.BH + 2), 1};
     int rc = egaze_encode_tmap(&tmA_hi, x_hi, 4, dims, str, box, row_bytes, 2);
@@ -1259,7 +1352,7 @@ static int conv_build(ConvPlan* pl, const void* x_hi, const void* x_lo, const vo
     if (rc) return rc;
   }
   {
-    uint64_t dims[2] = {(uint64_t)Cin_p, (uint64_t)9 * Cout};
+    uint64_t dims[2] = {(uint64_t)Cin_p, (uint64_t)(sub ? 16 : 9) * Cout};
     uint64_t str[1] = {(uint64_t)Cin_p * 2};
     uint32_t box[2] = {(uint32_t)p.KC, (uint32_t)(p.BN / CS)};   // each CTA of the cluster fetches its share of the box
     int rc = egaze_encode_tmap(&tmB_hi, w_hi, 2, dims, str, box, row_bytes, 2);
@@ -1327,10 +1420,10 @@ extern "C" int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* 
                                 int Cin_p, int Cout, const float* bias, const float* scale, const float* shift, int relu,
                                 int reduce, int ups, const void* mask, int mask_ups, float* out_f32, void* out_hi,
                                 void* out_lo, void* out_xb, float* stats, float* stats_cnt, float* colsum, int in_f16,
-                                int out_f16, float acc_scale, void* stream) {
+                                int out_f16, float acc_scale, int sub, int out_planar, void* stream) {
   ConvPlan pl;
   const int rc = conv_build(&pl, x_hi, x_lo, w_hi, w_lo, N, H, W, Cin_p, Cout, bias, scale, shift, relu, reduce, ups, mask, mask_ups,
-                            out_f32, out_hi, out_lo, out_xb, stats, stats_cnt, colsum, in_f16, out_f16, acc_scale);
+                            out_f32, out_hi, out_lo, out_xb, stats, stats_cnt, colsum, in_f16, out_f16, acc_scale, sub, out_planar);
   return rc ? rc : conv_run(pl, stream);
 }
 
@@ -1342,12 +1435,13 @@ extern "C" int egaze_conv3x3_plan_create(const void* x_hi, const void* x_lo, con
                                          int W, int Cin_p, int Cout, const float* bias, const float* scale, const float* shift,
                                          int relu, int reduce, int ups, const void* mask, int mask_ups, float* out_f32,
                                          void* out_hi, void* out_lo, void* out_xb, float* stats, float* stats_cnt,
-                                         float* colsum, int in_f16, int out_f16, float acc_scale, long long* plan) {
+                                         float* colsum, int in_f16, int out_f16, float acc_scale, int sub, int out_planar,
+                                         long long* plan) {
   EGAZE_CHECK_ARG(plan, "conv3x3_plan_create: null handle pointer");
   ConvPlan* pl = new (std::nothrow) ConvPlan;
   EGAZE_CHECK_ARG(pl, "conv3x3_plan_create: out of host memory");
   const int rc = conv_build(pl, x_hi, x_lo, w_hi, w_lo, N, H, W, Cin_p, Cout, bias, scale, shift, relu, reduce, ups, mask, mask_ups,
-                            out_f32, out_hi, out_lo, out_xb, stats, stats_cnt, colsum, in_f16, out_f16, acc_scale);
+                            out_f32, out_hi, out_lo, out_xb, stats, stats_cnt, colsum, in_f16, out_f16, acc_scale, sub, out_planar);
   if (rc) {
     delete pl;
     return rc;

@@ -110,6 +110,7 @@ __global__ void f32_to_split_kernel(const float* __restrict__ x, size_t n, __nv_
 // fmt 1: fp16 planes of w * kF16WScale (the forward operand format; the conv multiplies its accumulators by 1 / kF16WScale):
 // with weights around 1e-2 the unscaled lo plane would sit in fp16's subnormal range and keep only ~19 bits of the weight.
 constexpr float kF16WScale = 256.f;
+//  mode 2 / 3: sub-pixel copies (16 planes, egaze_subpixel_taps in common.cuh); 2: [plane][co][ci], 3: [plane][ci][co]
 __device__ __forceinline__ void pack_w3x3_body(const float* __restrict__ w, int Co, int Ci, int rows, int cols_p, int mode,
                                                int fmt, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                                                uint32_t first, uint32_t stride) {
@@ -118,10 +119,30 @@ __device__ __forceinline__ void pack_w3x3_body(const float* __restrict__ w, int 
   for (uint32_t i = first; i < total; i += stride) {
     const uint32_t col = i % cols_p, row = i / cols_p;
     float v[9];
-    const bool live = mode == 0 ? col < (uint32_t)Ci : col < (uint32_t)Co;
-    const float* src = mode == 0 ? w + ((size_t)row * Ci + col) * 9 : w + ((size_t)col * Ci + row) * 9;
+    const bool fwd = (mode & 1) == 0;
+    const bool live = fwd ? col < (uint32_t)Ci : col < (uint32_t)Co;
+    const float* src = fwd ? w + ((size_t)row * Ci + col) * 9 : w + ((size_t)col * Ci + row) * 9;
 #pragma unroll
     for (int t = 0; t < 9; ++t) v[t] = live ? src[t] : 0.f;
+    if (mode >= 2) {
+      float q[16];
+      egaze_subpixel_taps(v, q);
+#pragma unroll
+      for (int t = 0; t < 16; ++t) {
+        if (fmt) {
+          __half h, l;
+          split_f16(q[t] * kF16WScale, h, l);
+          reinterpret_cast<__half*>(hi)[(size_t)t * plane + i] = h;
+          if (lo) reinterpret_cast<__half*>(lo)[(size_t)t * plane + i] = l;
+        } else {
+          __nv_bfloat16 h, l;
+          split_bf16(q[t], h, l);
+          hi[(size_t)t * plane + i] = h;
+          if (lo) lo[(size_t)t * plane + i] = l;
+        }
+      }
+      continue;
+    }
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       if (fmt) {
@@ -159,7 +180,8 @@ __global__ void pack_w3x3_multi_kernel(const PackJob* __restrict__ jobs) {
 
 // dwp: [9][Co_p][Ci_p] fp32 (wgrad accumulator)  ->  gw: OIHW [Co][Ci][3][3]  (gw = beta*gw + dwp).
 // One thread per (co, ci): nine strided reads, one 36-byte contiguous store (adjacent threads store adjacent 36-byte runs).
-__global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, int Co, int Ci, int Co_p, int Ci_p, float beta,
+// sub: dwp holds the 16 sub-pixel planes; tap (r, s) collects the planes it was pre-summed into.
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, int Co, int Ci, int Co_p, int Ci_p, float beta, int sub,
                                     float* __restrict__ gw) {
   const uint32_t total = (uint32_t)Co * Ci;
   const size_t tap_stride = (size_t)Co_p * Ci_p;
@@ -167,6 +189,15 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, int Co, int C
     const uint32_t ci = i % Ci, co = i / Ci;
     const float* src = dwp + (size_t)co * Ci_p + ci;
     float* dst = gw + (size_t)i * 9;
+    if (sub) {
+      float q[16], g9[9];
+#pragma unroll
+      for (int t = 0; t < 16; ++t) q[t] = src[t * tap_stride];
+      egaze_subpixel_taps_transpose(q, g9);
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) dst[tap] = beta == 0.f ? g9[tap] : fmaf(beta, dst[tap], g9[tap]);
+      continue;
+    }
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
       const float v = src[tap * tap_stride];
@@ -227,8 +258,9 @@ extern "C" int egaze_f16_weight_scale(float* out) {
 extern "C" int egaze_pack_w3x3(const float* w_oihw, int Cout, int Cin, int cols_p, int mode, int fmt, void* hi, void* lo,
                                void* stream) {
   EGAZE_CHECK_ARG(w_oihw && hi, "pack_w3x3: bad args");
-  const int rows = mode == 0 ? Cout : Cin;
-  EGAZE_CHECK_ARG(cols_p >= (mode == 0 ? Cin : Cout), "pack_w3x3: cols_p too small");
+  EGAZE_CHECK_ARG(mode >= 0 && mode <= 3, "pack_w3x3: mode must be 0..3");
+  const int rows = (mode & 1) == 0 ? Cout : Cin;
+  EGAZE_CHECK_ARG(cols_p >= ((mode & 1) == 0 ? Cin : Cout), "pack_w3x3: cols_p too small");
   const size_t total = (size_t)rows * cols_p;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
@@ -248,15 +280,15 @@ extern "C" int egaze_pack_w3x3_multi(const void* jobs, int njobs, void* stream) 
   return EGAZE_OK;
 }
 
-extern "C" int egaze_unpack_wgrad(float* dwp, int Cout, int Cin, int Cout_p, int Cin_p, float beta, int clear, float* gw_oihw,
-                                  void* stream) {
+extern "C" int egaze_unpack_wgrad(float* dwp, int Cout, int Cin, int Cout_p, int Cin_p, float beta, int clear, int sub,
+                                  float* gw_oihw, void* stream) {
   EGAZE_CHECK_ARG(dwp && gw_oihw && Cout_p >= Cout && Cin_p >= Cin, "unpack_wgrad: bad args");
   const size_t total = (size_t)Cout * Cin;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  unpack_wgrad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dwp, Cout, Cin, Cout_p, Cin_p, beta, gw_oihw);
+  unpack_wgrad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dwp, Cout, Cin, Cout_p, Cin_p, beta, sub, gw_oihw);
   EGAZE_LAUNCH_CHECK();
   // clear != 0: leave the (persistent) accumulator zeroed for the next accumulation -- a stream-ordered fill at full bandwidth
-  if (clear) EGAZE_CUDA(cudaMemsetAsync(dwp, 0, (size_t)9 * Cout_p * Cin_p * sizeof(float), (cudaStream_t)stream));
+  if (clear) EGAZE_CUDA(cudaMemsetAsync(dwp, 0, (size_t)(sub ? 16 : 9) * Cout_p * Cin_p * sizeof(float), (cudaStream_t)stream));
   return EGAZE_OK;
 }

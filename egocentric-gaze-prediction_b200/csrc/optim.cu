@@ -26,7 +26,7 @@ struct AdamJob {              // 112 bytes, mirrored by egaze/optim.py
   int Co, Ci;                 // conv weight [Co][Ci][3][3]; Ci == 0: flat tensor of n elements, no packed copies
   int rows0, cols0, fmt0;     // forward copy: rows0 >= Co, cols0 >= Ci, fmt 0 bf16 / 1 fp16 (values pre-scaled, see layout.cu)
   int rows1, cols1;           // data-gradient copy: rows1 >= Ci, cols1 >= Co (bf16)
-  int pad;
+  int sub;                    // the copies are the 16-plane SUB-PIXEL packs (layout.cu modes 2 / 3; no tap flip in the gradient copy)
 };
 
 struct AdamHyper {
@@ -138,6 +138,31 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const AdamJob* __restri
     }
     __syncthreads();
     // phase 2: packed copies from the updated tile (padding rows / columns of the copies are zero and never change)
+    if (j.sub) {
+      for (int half = 0; half < 2; ++half) {
+        void* hi = half == 0 ? j.p0_hi : j.p1_hi;
+        void* lo = half == 0 ? j.p0_lo : j.p1_lo;
+        if (!hi) continue;
+        for (int p = threadIdx.x; p < kTile * kTile; p += blockDim.x) {
+          // forward copy: adjacent threads write adjacent input channels; gradient copy: adjacent output channels
+          const int co_l = half == 0 ? p / kTile : p % kTile, ci_l = half == 0 ? p % kTile : p / kTile;
+          const int co = co0 + co_l, ci = ci0 + ci_l;
+          if (co < j.Co && ci < j.Ci) {
+            float w9[9], q[16];
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) w9[tap] = tile[tap][co_l][ci_l];
+            egaze_subpixel_taps(w9, q);
+            const size_t plane = half == 0 ? plane0 : plane1;
+            const size_t at = half == 0 ? (size_t)co * j.cols0 + ci : (size_t)ci * j.cols1 + co;
+#pragma unroll
+            for (int t = 0; t < 16; ++t)
+              store_split(hi, lo, (size_t)t * plane + at, q[t], half == 0 ? j.fmt0 : 0, half == 0 ? h.f16_scale : 1.f);
+          }
+        }
+      }
+      __syncthreads();
+      continue;
+    }
     if (j.p0_hi) {
       for (int p = threadIdx.x; p < kTile * kTile; p += blockDim.x) {
         const int co_l = p / kTile, ci_l = p % kTile;

@@ -32,6 +32,9 @@ struct WgradParams {
   int stacked;         // Cout == 64, precise: the M = 128 rows are [dY_hi ; dY_lo] of the same 64 channels, so ONE MMA against
                        // [X_hi | X_lo] yields all four hi/lo products (the epilogue adds the two lane halves into the same dW rows)
   int nsplit;
+  int sub;             // sub-pixel form (conv3x3_tc.cu ConvTcParams::sub): X is the low-resolution input, dY the phase-planar gradient
+                       // [4N][H][W][Cout]; job = (co-tile, ci-tile, phase, horizontal tap b), the TWO vertical taps a share the dY tile
+                       // (N = 128); dwp has 16 planes [phase*4 + a*2 + b]
   int stage_bytes, dy_plane_bytes, x_plane_bytes;
   float* dwp;          // [9][Cout][Cin_p]
 };
@@ -46,8 +49,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   int job = blockIdx.y;
-  const int s = job % 3;
-  job /= 3;
+  const int nj = p.sub ? 8 : 3;
+  const int s = job % nj;          // horizontal tap; sub-pixel: phase * 2 + b
+  job /= nj;
+  const int phase = p.sub ? s >> 1 : 0, py = phase >> 1, px = phase & 1, hb = p.sub ? s & 1 : s;
+  const int ntap_v = p.sub ? 2 : 3;
   const int ci_t = job % p.ci_tiles;
   const int co_t = job / p.ci_tiles;
   const int co0 = co_t * 128, ci0 = ci_t * 64;
@@ -93,15 +99,19 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid_constan
         ptx::mbar_wait(&empty[st], par);
         ptx::mbar_arrive_expect_tx(&full[st], tx_bytes);
         uint8_t* base = smem + (size_t)st * p.stage_bytes;
+        const int img_y = phase * p.N + img;   // sub-pixel: the gradient of this phase's output pixels is one plane of 4N images
         for (int c = 0; c < p.m_chunks; ++c) {
-          ptx::tma_load_4d(base + c * dy_box_bytes, &tmY_hi, &full[st], co0 + 64 * c, w0, h0, img);
+          ptx::tma_load_4d(base + c * dy_box_bytes, &tmY_hi, &full[st], co0 + 64 * c, w0, h0, img_y);
           if (NSPLIT == 2)
             ptx::tma_load_4d(base + (p.stacked ? dy_box_bytes : (uint32_t)p.dy_plane_bytes + c * dy_box_bytes), &tmY_lo, &full[st],
-                             co0 + 64 * c, w0, h0, img);
+                             co0 + 64 * c, w0, h0, img_y);
         }
         uint8_t* xb = base + (size_t)NSPLIT * p.dy_plane_bytes;
-        ptx::tma_load_4d(xb, &tmX_hi, &full[st], ci0, w0 - 1 + s, h0 - 1, img);
-        if (NSPLIT == 2) ptx::tma_load_4d(xb + p.x_plane_bytes, &tmX_lo, &full[st], ci0, w0 - 1 + s, h0 - 1, img);
+        // window origin: 3x3 tap (r, s) reads X[h + r - 1, w + s - 1]; sub-pixel tap (a, b) of phase (py, px) reads
+        // X[i + py + a - 1, j + px + b - 1]
+        const int xw = w0 - 1 + px + hb, xh = h0 - 1 + py;
+        ptx::tma_load_4d(xb, &tmX_hi, &full[st], ci0, xw, xh, img);
+        if (NSPLIT == 2) ptx::tma_load_4d(xb + p.x_plane_bytes, &tmX_lo, &full[st], ci0, xw, xh, img);
         if (++st == 2) { st = 0; par ^= 1; }
       }
     }
@@ -110,7 +120,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid_constan
     // (see conv3x3_tc.cu: a loop nest under `if (lane == 0)` costs ~100 cycles of R2UR traffic per tcgen05.mma).
     {
       const bool leader = ptx::elect_one();
-      const uint32_t idesc = ptx::make_idesc_bf16(128, 192, 1, 1);   // both operands MN-major, N = 3 taps x 64 channels
+      const uint32_t idesc = ptx::make_idesc_bf16(128, 64 * ntap_v, 1, 1);   // both operands MN-major, N = vertical taps x 64 channels
       // MN-major SWIZZLE_128B canonical layout: 64 channels (128 B) contiguous, 8 pixel rows per 1024 B atom (SBO),
       // next 64-channel chunk LBO bytes away: the other dY chunk for A, the window shifted by one tile row for B.
       const uint64_t a_static = ptx::make_smem_desc(0, dy_box_bytes, 1024, 128);
@@ -162,7 +172,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid_constan
     ptx::mbar_wait(&acc_full, 0);
     ptx::tc_fence_after();
     const bool any_tile = (int)blockIdx.x < p.total_tiles;
-    for (int r = 0; r < 3; ++r) {
+    for (int r = 0; r < ntap_v; ++r) {
 #pragma unroll 1
       for (int c0 = 0; c0 < 64; c0 += 32) {
         uint32_t v[32];
@@ -178,7 +188,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid_constan
         }
         const int co = p.stacked ? (m & 63) : co0 + m;   // stacked: lanes 64..127 hold the dY_lo products of channels 0..63
         if (any_tile && co < p.Cout) {
-          float* dst = p.dwp + ((size_t)(r * 3 + s) * p.Cout + co) * p.Cin_p + ci0 + c0;
+          const int plane = p.sub ? phase * 4 + r * 2 + hb : r * 3 + s;
+          float* dst = p.dwp + ((size_t)plane * p.Cout + co) * p.Cin_p + ci0 + c0;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             float4 val = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
@@ -210,9 +221,9 @@ void pick_wgrad_tile(int H, int W, int* BH, int* BW) {
 
 }  // namespace
 
-// dwp ([9][Cout][Cin_p] fp32) is ACCUMULATED into: zero it first.  Cin_p % 64 == 0, Cout % 64 == 0.
+// dwp ([9][Cout][Cin_p] fp32; sub: [16][Cout][Cin_p]) is ACCUMULATED into: zero it first.  Cin_p % 64 == 0, Cout % 64 == 0.
 extern "C" int egaze_wgrad3x3_tc(const void* x_hi, const void* x_lo, const void* dy_hi, const void* dy_lo, int N, int H,
-                                 int W, int Cin_p, int Cout, float* dwp, int precise, void* stream) {
+                                 int W, int Cin_p, int Cout, float* dwp, int precise, int sub, void* stream) {
   EGAZE_CHECK_ARG(x_hi && dy_hi && dwp, "wgrad3x3_tc: null operand");
   EGAZE_CHECK_ARG(!precise || (x_lo && dy_lo), "wgrad3x3_tc: precise mode needs lo planes");
   EGAZE_CHECK_ARG(Cin_p % 64 == 0 && Cout % 64 == 0, "wgrad3x3_tc: Cin_p=%d, Cout=%d must be multiples of 64", Cin_p, Cout);
@@ -225,6 +236,7 @@ extern "C" int egaze_wgrad3x3_tc(const void* x_hi, const void* x_lo, const void*
   p.co_tiles = ceil_div(Cout, 128); p.ci_tiles = Cin_p / 64;
   p.m_chunks = Cout >= 128 ? 2 : 1;
   p.nsplit = precise ? 2 : 1;
+  p.sub = sub ? 1 : 0;
   p.stacked = (precise && Cout == 64) ? 1 : 0;
   {
     const char* e = getenv("EGAZE_WGRAD_STACKED");
@@ -241,7 +253,7 @@ extern "C" int egaze_wgrad3x3_tc(const void* x_hi, const void* x_lo, const void*
 
   CUtensorMap tmY_hi, tmY_lo, tmX_hi, tmX_lo;
   {
-    uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)(sub ? 4 * N : N)};
     uint64_t str[3] = {(uint64_t)Cout * 2, (uint64_t)W * Cout * 2, (uint64_t)H * W * Cout * 2};
     uint32_t box[4] = {64, (uint32_t)p.BW, (uint32_t)p.BH, 1};
     int rc = egaze_encode_tmap(&tmY_hi, dy_hi, 4, dims, str, box, 128, 2);
@@ -259,7 +271,7 @@ extern "C" int egaze_wgrad3x3_tc(const void* x_hi, const void* x_lo, const void*
     if (rc) return rc;
   }
   // split-K factor: one CTA per SM is resident (208 KB of smem), so pick the factor that fills whole waves of SMs best
-  const int jobs = p.co_tiles * p.ci_tiles * 3;
+  const int jobs = p.co_tiles * p.ci_tiles * (sub ? 8 : 3);
   static int sms = 0;
   if (sms == 0) {
     int dev = 0;

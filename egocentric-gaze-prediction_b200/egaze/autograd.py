@@ -39,8 +39,9 @@ def _get_side_stream(dev):
     return side
 
 
-def _wgrad(x_act, dy_act, cout, cin):
-    return _wgrad_impl(ops.wgrad3x3, x_act, dy_act, cout, cin)
+def _wgrad(x_act, dy_act, cout, cin, sub=False):
+    wg = (lambda x, dy, co, ci: ops.wgrad3x3(x, dy, co, ci, sub=True)) if sub else ops.wgrad3x3
+    return _wgrad_impl(wg, x_act, dy_act, cout, cin)
 
 
 def _wgrad_impl(wg, x_act, dy_act, cout, cin):
@@ -79,13 +80,13 @@ class _GradBag(object):
         return self.d.get(id(p))
 
 
-def _conv_param_grads(bag, conv, x_act, gpre_act, bias_grad_is_zero=False, bias_grad=None):
+def _conv_param_grads(bag, conv, x_act, gpre_act, bias_grad_is_zero=False, bias_grad=None, sub=False):
     """dW via the tcgen05 wgrad kernel, db via a column sum.  gpre_act: gradient w.r.t. the conv output.
     A conv bias that feeds a training-mode BatchNorm has an exactly-zero gradient (the batch mean removes it; stock
     PyTorch returns rounding noise ~1e-9 there), so no reduction pass is spent on it.  bias_grad: column sums already
     accumulated by the dgrad epilogue that produced gpre_act (then no pass over gpre_act is needed either)."""
     if _req(conv.weight):
-        gw = _wgrad(x_act, gpre_act, conv.out_channels, conv.in_channels)
+        gw = _wgrad(x_act, gpre_act, conv.out_channels, conv.in_channels, sub=sub)
         bag.put(conv.weight, gw)
     if _req(conv.bias):
         if bias_grad_is_zero:
@@ -96,12 +97,13 @@ def _conv_param_grads(bag, conv, x_act, gpre_act, bias_grad_is_zero=False, bias_
             bag.put(conv.bias, ops.col_sum(gpre_act, conv.out_channels))
 
 
-def _dgrad(conv, gpre_act, **kw):
-    """Data gradient of a 3x3 conv: the same tcgen05 kernel with flipped / transposed weights."""
+def _dgrad(conv, gpre_act, sub=False, **kw):
+    """Data gradient of a 3x3 conv: the same tcgen05 kernel with flipped / transposed weights.  sub: the conv ran in sub-pixel form
+    (gpre_act is phase-planar; the result is the gradient w.r.t. the LOW-resolution map in front of the nn.Upsample)."""
     cin = conv.in_channels
     rows_p = ops.pad_channels(cin) if cin % 16 else cin
-    wpack = ops.pack_cache.get(conv.weight, 1, rows_p=rows_p, cols_p=gpre_act.Cp)
-    return ops.conv3x3(gpre_act, wpack, want_lo=ops.mode()["dy_lo"], **kw)
+    wpack = ops.pack_cache.get(conv.weight, 3 if sub else 1, rows_p=rows_p, cols_p=gpre_act.Cp)
+    return ops.conv3x3(gpre_act, wpack, want_lo=ops.mode()["dy_lo"], sub=2 if sub else 0, **kw)
 
 
 def _first_cp(conv):
@@ -198,11 +200,13 @@ def relu_sequential_backward(specs, saved, gpre, bag, want_input_grad_f32):
     """Backward through a conv+bias+ReLU(+ups) chain.  gpre: split gradient w.r.t. the LAST conv's output
     (its ReLU mask already applied).  Returns the NHWC fp32 gradient w.r.t. the chain input (or None).
     The dgrad of layer i writes the masked gradient w.r.t. layer i-1's output; its epilogue also accumulates that
-    tensor's column sums, which are layer i-1's bias gradient."""
+    tensor's column sums, which are layer i-1's bias gradient.
+    A conv in sub-pixel form (engine.ConvSpec.sub) reads its output gradient phase-planar -- the dgrad of the layer after it stores
+    it that way -- and its own dgrad lands directly on the low-resolution map (no 2x2 sum pass)."""
     bias_grad = None
     for i in range(len(specs) - 1, -1, -1):
         sp, rec = specs[i], saved[i]
-        _conv_param_grads(bag, sp.conv, rec["x"], gpre, bias_grad=bias_grad)
+        _conv_param_grads(bag, sp.conv, rec["x"], gpre, bias_grad=bias_grad, sub=sp.sub)
         bias_grad = None
         if i > 0:
             prev = specs[i - 1]
@@ -210,8 +214,9 @@ def relu_sequential_backward(specs, saved, gpre, bag, want_input_grad_f32):
                 cin = sp.conv.in_channels   # == prev.conv.out_channels; the dgrad output carries them padded to 16
                 bias_grad = torch.zeros((ops.pad_channels(cin) if cin % 16 else cin,), dtype=torch.float32,
                                         device=gpre.hi.device)
-            gpre, _, _ = _dgrad(sp.conv, gpre, reduce=2 if prev.ups else 0, mask=saved[i - 1]["y"].hi, mask_ups=prev.ups,
-                                colsum=bias_grad)
+            ups = prev.ups and not prev.ups_folded      # the upsampled map exists: 2x2 sum + upsampled mask in the epilogue
+            gpre, _, _ = _dgrad(sp.conv, gpre, sub=sp.sub, reduce=2 if ups else 0, mask=saved[i - 1]["y"].hi, mask_ups=ups,
+                                colsum=bias_grad, planar=prev.sub)
         elif want_input_grad_f32:
             _, g, _ = _dgrad(sp.conv, gpre, want_f32=True, want_split=False)
             return g

@@ -8,6 +8,8 @@ layout (SURVEY 8b "State layout"); this module reads their parameters and drives
                          -> bn_apply [normalise + ReLU (+pool)] -> split act
   decoder layer        : conv3x3_tc [+bias, ReLU (, 2x nearest replicate for the following nn.Upsample)] -> split act
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -15,11 +17,19 @@ from . import ops
 
 
 class ConvSpec(object):
-    """One fused step of a Sequential: conv [+ bn] [+ relu] [+ pool | + upsample]."""
-    __slots__ = ("conv", "bn", "relu", "pool", "ups")
+    """One fused step of a Sequential: conv [+ bn] [+ relu] [+ pool | + upsample].
+    ups_folded: the nn.Upsample after this conv is NOT materialised -- the next conv (`sub`) consumes the low-resolution map in
+    sub-pixel form (four 2x2-tap phase convolutions with pre-summed weights, 16 instead of 36 MACs per low-resolution pixel)."""
+    __slots__ = ("conv", "bn", "relu", "pool", "ups", "ups_folded", "sub")
 
     def __init__(self, conv):
         self.conv, self.bn, self.relu, self.pool, self.ups = conv, None, False, False, False
+        self.ups_folded, self.sub = False, False
+
+
+def subpixel_enabled():
+    """EGAZE_SUBPIXEL=0 materialises every nn.Upsample and runs the direct 3x3 convolution on it (the round-1 schedule)."""
+    return os.environ.get("EGAZE_SUBPIXEL", "1") != "0"
 
 
 def parse_sequential(seq):
@@ -49,6 +59,14 @@ def parse_sequential(seq):
             specs[-1].ups = True
         else:
             raise RuntimeError("egaze: unsupported module on the hot path: %r" % (m,))
+    if subpixel_enabled():
+        # conv+ReLU+Upsample -> conv+ReLU -> conv (the decoder pattern, models/model_SP.py:16-17,20-21,24-25,27-28): the middle
+        # conv runs in sub-pixel form; in the backward the following conv's data gradient hands it a phase-planar gradient
+        for i in range(1, len(specs) - 1):
+            prev, sp, nxt = specs[i - 1], specs[i], specs[i + 1]
+            if (prev.ups and prev.bn is None and sp.bn is None and nxt.bn is None and not sp.pool and not nxt.pool
+                    and sp.conv.in_channels % 64 == 0 and sp.conv.out_channels % 64 == 0):
+                prev.ups_folded, sp.sub = True, True
     return specs, tail
 
 
@@ -62,12 +80,13 @@ def run_conv_spec(act, spec, saved=None, xb=False):
     conv, bn = spec.conv, spec.bn
     xb = ops.want_xb(xb)
     cout_p = ops.pad_channels(conv.out_channels) if conv.out_channels % 16 else conv.out_channels
-    wpack = ops.pack_cache.get(conv.weight, 0, rows_p=cout_p, cols_p=act.Cp, fmt=act.fmt)
+    wpack = ops.pack_cache.get(conv.weight, 2 if spec.sub else 0, rows_p=cout_p, cols_p=act.Cp, fmt=act.fmt)
     bias = conv.bias.detach() if conv.bias is not None else None
     if bias is not None and cout_p != conv.out_channels:
         bias = torch.cat([bias, bias.new_zeros(cout_p - conv.out_channels)])
     if bn is None:
-        out, _, _ = ops.conv3x3(act, wpack, bias=bias, relu=spec.relu, reduce=1 if spec.pool else 0, ups=spec.ups, xb=xb)
+        out, _, _ = ops.conv3x3(act, wpack, bias=bias, relu=spec.relu, reduce=1 if spec.pool else 0,
+                                ups=spec.ups and not spec.ups_folded, xb=xb, sub=1 if spec.sub else 0)
         if saved is not None:
             saved.append({"x": act, "y": out})
         out.C = conv.out_channels

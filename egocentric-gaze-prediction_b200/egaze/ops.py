@@ -190,16 +190,18 @@ class _PackCache(object):
     @staticmethod
     def _dims(w, mode, rows_p, cols_p):
         Co, Ci = int(w.shape[0]), int(w.shape[1])
-        rows = Co if mode == 0 else Ci
-        cols = Ci if mode == 0 else Co
+        rows = Co if mode in (0, 2) else Ci
+        cols = Ci if mode in (0, 2) else Co
         return Co, Ci, rows, (rows if rows_p is None else rows_p), (pad_channels(cols) if cols_p is None else cols_p)
 
     def get(self, w, mode, rows_p=None, cols_p=None, fmt=None):
         """w: nn.Conv2d weight [Co, Ci, 3, 3] (or Conv3d [Co, Ci, 1, 3, 3]).  mode 0: forward operand, 1: flipped / transposed
-        (data gradient).  fmt 1: fp16 planes pre-scaled by f16_weight_scale(); default: the numeric mode's forward format for
-        mode 0, bf16 for mode 1.  Returns (hi, lo, rows, cols_p, fmt)."""
+        (data gradient); 2 / 3: the 16-plane sub-pixel forms of 0 / 1 for a conv that follows nn.Upsample (egaze.h).  fmt 1: fp16
+        planes pre-scaled by f16_weight_scale(); default: the numeric mode's forward format for the forward copies, bf16 for the
+        gradient copies.  Returns (hi, lo, rows, cols_p, fmt)."""
+        planes = 9 if mode < 2 else 16
         if fmt is None:
-            fmt = _MODES[precision()]["fwd_fmt"] if mode == 0 else 0
+            fmt = _MODES[precision()]["fwd_fmt"] if mode in (0, 2) else 0
         Co, Ci, rows, rp, cp = self._dims(w, mode, rows_p, cols_p)
         dt = F16 if fmt else BF16
         key = (id(w), mode, rp, cp, fmt)
@@ -210,18 +212,18 @@ class _PackCache(object):
         w4 = w.detach().reshape(Co, Ci, 3, 3).contiguous().float()
         if rp == rows:
             # the pack kernel writes every element (padding columns included): reuse the previous buffers when possible
-            if ent is not None and ent[3][0].shape == (9, rp, cp) and ent[3][0].device == w.device:
+            if ent is not None and ent[3][0].shape == (planes, rp, cp) and ent[3][0].device == w.device:
                 hi, lo = ent[3][0], ent[3][1]
             else:
-                hi = torch.empty((9, rp, cp), dtype=dt, device=w.device)
-                lo = torch.empty((9, rp, cp), dtype=dt, device=w.device)
+                hi = torch.empty((planes, rp, cp), dtype=dt, device=w.device)
+                lo = torch.empty((planes, rp, cp), dtype=dt, device=w.device)
             call("egaze_pack_w3x3", w4, Co, Ci, cp, mode, fmt, hi, lo, stream_ptr())
         else:
-            hi = torch.zeros((9, rp, cp), dtype=dt, device=w.device)
-            lo = torch.zeros((9, rp, cp), dtype=dt, device=w.device)
+            hi = torch.zeros((planes, rp, cp), dtype=dt, device=w.device)
+            lo = torch.zeros((planes, rp, cp), dtype=dt, device=w.device)
             # padded rows (tiny layers only): pack densely then copy into the padded buffer
-            thi = torch.empty((9, rows, cp), dtype=dt, device=w.device)
-            tlo = torch.empty((9, rows, cp), dtype=dt, device=w.device)
+            thi = torch.empty((planes, rows, cp), dtype=dt, device=w.device)
+            tlo = torch.empty((planes, rows, cp), dtype=dt, device=w.device)
             call("egaze_pack_w3x3", w4, Co, Ci, cp, mode, fmt, thi, tlo, stream_ptr())
             hi[:, :rows].copy_(thi)
             lo[:, :rows].copy_(tlo)
@@ -235,7 +237,7 @@ class _PackCache(object):
         out = []
         for (wid, mode, rp, cp, fmt), ent in self._d.items():
             if wid == id(w) and ent[0]() is w and ent[2] == w.data_ptr():
-                rows = int(w.shape[0]) if mode == 0 else int(w.shape[1])
+                rows = int(w.shape[0]) if mode in (0, 2) else int(w.shape[1])
                 if rp == rows and not any(o[0] == mode for o in out):
                     out.append((mode, rp, cp, fmt, ent[3][0], ent[3][1]))
         return out
@@ -371,12 +373,16 @@ def _conv_plan_run(dev, args):
 
 
 def conv3x3(act, wpack, bias=None, scale=None, shift=None, relu=False, reduce=0, ups=False, mask=None,
-            want_f32=False, want_split=True, stats=False, mask_ups=False, colsum=None, want_lo=True, xb=False):
+            want_f32=False, want_split=True, stats=False, mask_ups=False, colsum=None, want_lo=True, xb=False, sub=0,
+            planar=False):
     """3x3/pad-1 conv on the tcgen05 path.  wpack = (w_hi, w_lo, Cout_p, Cin_p, fmt) from pack_cache, in the activation's format.
     The operand mode follows from the planes present (and the numeric mode): act.lo given -> 3 MMAs per product, act.lo None ->
     act.hi x [w_hi | w_lo] (2), `fast` -> 1.  The split output has the input's format (a forward activation stays fp16, a
     gradient stays bf16); want_lo=False writes the hi plane only (bf16), xb=True adds the bf16 copy (fp16 outputs).
     colsum: optional [Cout] fp32 tensor the kernel ADDS the per-channel sums of the stored values to.
+    sub (egaze.h): 1 = sub-pixel forward of "nearest-2x upsample -> this conv" (act is the LOW-resolution map, wpack a mode-2 pack, the
+    output is 2H x 2W); 2 = its data gradient (act is the phase-planar output gradient [4N, H, W, C], wpack a mode-3 pack, the output
+    the low-resolution gradient).  planar: store the output phase-planar ([4N, H/2, W/2, C]).
     Returns (out_act | None, out_f32 | None, (stats_partial, stats_cnt) | None)."""
     w_hi, w_lo, Cout, Cin_p, wfmt = wpack
     if Cin_p != act.Cp:
@@ -388,12 +394,17 @@ def conv3x3(act, wpack, bias=None, scale=None, shift=None, relu=False, reduce=0,
     use_wlo = md["w_lo"]
     x_lo = act.lo if (use_wlo and md["fwd_lo"] and act.lo is not None) else None
     N, H, W = act.N, act.H, act.W
+    if sub == 2:
+        N //= 4
     dev = act.hi.device
     Ho, Wo = (H // 2, W // 2) if reduce else (H, W)
-    if ups:
+    if ups or sub == 1:
         Ho, Wo = Ho * 2, Wo * 2
-    out_act = empty_act(N, Ho, Wo, Cout, Cout, dev, lo=want_lo or fmt == 1, fmt=fmt, xb=xb and fmt == 1) if want_split else None
-    out_f32 = torch.empty((N, Ho, Wo, Cout), dtype=F32, device=dev) if want_f32 else None
+    No = N
+    if planar:
+        No, Ho, Wo = 4 * N, Ho // 2, Wo // 2
+    out_act = empty_act(No, Ho, Wo, Cout, Cout, dev, lo=want_lo or fmt == 1, fmt=fmt, xb=xb and fmt == 1) if want_split else None
+    out_f32 = torch.empty((No, Ho, Wo, Cout), dtype=F32, device=dev) if want_f32 else None
     st = None
     if stats:
         parts, cs, cd = conv_stats_shape(Cout, use_wlo)
@@ -405,14 +416,16 @@ def conv3x3(act, wpack, bias=None, scale=None, shift=None, relu=False, reduce=0,
             bias, scale, shift, int(relu), int(reduce), int(ups), mask, int(mask_ups), out_f32,
             out_act.hi if out_act is not None else None, out_act.lo if out_act is not None else None,
             out_act.xb if out_act is not None else None,
-            st[0] if st else None, st[1] if st else None, colsum, fmt, fmt, (1.0 / f16_weight_scale()) if fmt else 1.0)
+            st[0] if st else None, st[1] if st else None, colsum, fmt, fmt, (1.0 / f16_weight_scale()) if fmt else 1.0,
+            int(sub), int(planar))
     if _use_plans():
         _conv_plan_run(dev, args)
     else:
         call("egaze_conv3x3_tc", *(args + (stream_ptr(),)))
     if _conv_timer["on"]:
         ev1.record()
-        _conv_timer["events"].append((ev0, ev1, ("conv", N, H, W, Cin_p, Cout, int(reduce), int(ups), bool(stats))))
+        _conv_timer["events"].append((ev0, ev1, ("conv" if not sub else "conv/sub%d" % sub, N, H, W, Cin_p, Cout, int(reduce), int(ups),
+                                                 bool(stats))))
     return out_act, out_f32, st
 
 
@@ -503,9 +516,11 @@ def wgrad_operands(x_act, dy_act, precise=None):
     return x_act.hi, (x_act.lo if precise else None), dy_act.hi, (dy_act.lo if precise else None), precise
 
 
-def wgrad3x3(x_act, dy_act, Cout, Cin, precise=None):
+def wgrad3x3(x_act, dy_act, Cout, Cin, precise=None, sub=False):
     """dW (OIHW fp32 [Cout, Cin, 3, 3]) of a 3x3/pad-1 conv from its input activation and output gradient (bf16 planes).
-    precise (default: the numeric mode's choice): dY_hi*X_hi + dY_hi*X_lo + dY_lo*X_hi, else dY_hi * bf16(X) (1 MMA)."""
+    precise (default: the numeric mode's choice): dY_hi*X_hi + dY_hi*X_lo + dY_lo*X_hi, else dY_hi * bf16(X) (1 MMA).
+    sub: the conv follows nn.Upsample and ran in sub-pixel form: x_act is the LOW-resolution input, dy_act the phase-planar
+    gradient [4N, H, W, C] of the 2H x 2W output."""
     x_hi, x_lo, dy_hi, dy_lo, precise = [_pad64(t) if torch.is_tensor(t) else t for t in wgrad_operands(x_act, dy_act, precise)]
     N, H, W = x_act.N, x_act.H, x_act.W
     dev = x_act.hi.device
@@ -513,19 +528,19 @@ def wgrad3x3(x_act, dy_act, Cout, Cin, precise=None):
     # persistent accumulator per shape: allocated zeroed once, left zeroed again by egaze_unpack_wgrad (clear=1)
     # (keyed by stream too: two streams -- the two trunks of model_SP have identical layer shapes -- must never accumulate
     # into the same buffer concurrently)
-    key = (cout_p, cin_p, dev, _lib.stream_key(dev))
+    key = (cout_p, cin_p, dev, _lib.stream_key(dev), bool(sub))
     dwp = _dwp_cache.get(key)
     if dwp is None:
-        dwp = _dwp_cache[key] = torch.zeros((9, cout_p, cin_p), dtype=F32, device=dev)
+        dwp = _dwp_cache[key] = torch.zeros((16 if sub else 9, cout_p, cin_p), dtype=F32, device=dev)
     if _conv_timer["on"]:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-    call("egaze_wgrad3x3_tc", x_hi, x_lo, dy_hi, dy_lo, N, H, W, cin_p, cout_p, dwp, int(precise), stream_ptr())
+    call("egaze_wgrad3x3_tc", x_hi, x_lo, dy_hi, dy_lo, N, H, W, cin_p, cout_p, dwp, int(precise), int(bool(sub)), stream_ptr())
     if _conv_timer["on"]:
         ev1.record()
-        _conv_timer["events"].append((ev0, ev1, ("wgrad", N, H, W, cin_p, cout_p, 0, 0, False)))
+        _conv_timer["events"].append((ev0, ev1, ("wgrad" if not sub else "wgrad/sub", N, H, W, cin_p, cout_p, 0, 0, False)))
     gw = torch.empty((Cout, Cin, 3, 3), dtype=F32, device=dev)
-    call("egaze_unpack_wgrad", dwp, Cout, Cin, cout_p, cin_p, 0.0, 1, gw, stream_ptr())
+    call("egaze_unpack_wgrad", dwp, Cout, Cin, cout_p, cin_p, 0.0, 1, int(bool(sub)), gw, stream_ptr())
     return gw
 
 

@@ -19,7 +19,7 @@ from ._lib import call, stream_ptr
 
 _JOB_DT = np.dtype([("w", "<u8"), ("g", "<u8"), ("m", "<u8"), ("v", "<u8"), ("step", "<u8"), ("p0_hi", "<u8"), ("p0_lo", "<u8"),
                     ("p1_hi", "<u8"), ("p1_lo", "<u8"), ("n", "<i8"), ("Co", "<i4"), ("Ci", "<i4"), ("rows0", "<i4"),
-                    ("cols0", "<i4"), ("fmt0", "<i4"), ("rows1", "<i4"), ("cols1", "<i4"), ("pad", "<i4")])
+                    ("cols0", "<i4"), ("fmt0", "<i4"), ("rows1", "<i4"), ("cols1", "<i4"), ("sub", "<i4")])
 
 
 class Adam(torch.optim.Optimizer):
@@ -72,18 +72,20 @@ class Adam(torch.optim.Optimizer):
                 st = self._init_state(p)
                 ents = ops.pack_cache.entries_for(p)
                 is_conv = ents and (p.dim() == 4 or p.dim() == 5) and tuple(p.shape[-2:]) == (3, 3)
-                e0 = next((e for e in ents if e[0] == 0), None) if is_conv else None
-                e1 = next((e for e in ents if e[0] == 1), None) if is_conv else None
+                # a conv that follows nn.Upsample runs in sub-pixel form: its copies are the 16-plane packs (modes 2 / 3)
+                sub = bool(is_conv and any(e[0] >= 2 for e in ents))
+                e0 = next((e for e in ents if e[0] == (2 if sub else 0)), None) if is_conv else None
+                e1 = next((e for e in ents if e[0] == (3 if sub else 1)), None) if is_conv else None
                 # copies the kernel cannot maintain (a second forward format of the same weight, padded rows) are left stale
                 maintained = [e for e in (e0, e1) if e is not None]
                 rec = (p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), st["step"].data_ptr(),
                        e0[4].data_ptr() if e0 else 0, e0[5].data_ptr() if e0 else 0,
                        e1[4].data_ptr() if e1 else 0, e1[5].data_ptr() if e1 else 0,
                        p.numel(), int(p.shape[0]) if maintained else 0, int(p.shape[1]) if maintained else 0,
-                       e0[1] if e0 else 0, e0[2] if e0 else 0, e0[3] if e0 else 0, e1[1] if e1 else 0, e1[2] if e1 else 0, 0)
+                       e0[1] if e0 else 0, e0[2] if e0 else 0, e0[3] if e0 else 0, e1[1] if e1 else 0, e1[2] if e1 else 0, int(sub))
                 recs.append(rec)
                 packs.append((p, maintained))
-            key = (gi, tuple(r[:9] for r in recs))
+            key = (gi, tuple(r[:9] + r[-1:] for r in recs))
             tab = self._tables.get(key)
             if tab is None:
                 host = torch.from_numpy(np.array(recs, dtype=_JOB_DT).view(np.uint8)).pin_memory()

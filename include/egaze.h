@@ -44,12 +44,19 @@ int egaze_f32_to_split(const float* x, long long n, void* hi, void* lo, int fmt,
  * mode 1 (dgrad): taps flipped, [9][Cin][cols_p>=Cout].  fmt 1: fp16 planes of w * egaze_f16_weight_scale (the conv is then
  * called with acc_scale = 1 / that).  (weights of utils.py:70, model_SP.py:10,13-30) */
 int egaze_f16_weight_scale(float* out);
+/* mode 2 / 3: the SUB-PIXEL copies of a conv that follows nn.Upsample(scale_factor=2) (model_SP.py:16-17,20-21,24-25,27-28):
+ * 16 planes [phase*4 + a*2 + b] of 2x2-tap weights pre-summed in fp32 -- output phase (py, px) of the upsample+conv pair is a
+ * 2x2 conv of the LOW-resolution map with taps W2[py][a] = {py=0: w[0], w[1]+w[2]; py=1: w[0]+w[1], w[2]} (same along x);
+ * mode 2 rows = Cout (forward), mode 3 rows = Cin (data gradient, transposed).  hi / lo: [16][rows][cols_p]. */
 int egaze_pack_w3x3(const float* w_oihw, int Cout, int Cin, int cols_p, int mode, int fmt, void* hi, void* lo, void* stream);
 /* egaze_pack_w3x3 for many weights in ONE launch.  jobs: device array of njobs 48-byte records
  * {const float* w; void* hi; void* lo; int Cout, Cin, rows, cols_p, mode, fmt;} (rows = Cout for mode 0, Cin for mode 1). */
 int egaze_pack_w3x3_multi(const void* jobs, int njobs, void* stream);
-/* wgrad accumulator [9][Cout_p][Cin_p] fp32 -> OIHW grad, gw = beta*gw + dw; clear != 0 zeroes the accumulator afterwards */
-int egaze_unpack_wgrad(float* dwp, int Cout, int Cin, int Cout_p, int Cin_p, float beta, int clear, float* gw_oihw, void* stream);
+/* wgrad accumulator [9][Cout_p][Cin_p] fp32 -> OIHW grad, gw = beta*gw + dw; clear != 0 zeroes the accumulator afterwards.
+ * sub != 0: the accumulator holds the 16 sub-pixel planes [phase*4 + a*2 + b] (egaze_wgrad3x3_tc sub = 1); every 3x3 tap
+ * gradient is the sum of the four planes it was pre-summed into (transpose of the egaze_pack_w3x3 mode-2 map). */
+int egaze_unpack_wgrad(float* dwp, int Cout, int Cin, int Cout_p, int Cin_p, float beta, int clear, int sub, float* gw_oihw,
+                       void* stream);
 
 /* ---- 3x3 convolution, tcgen05 implicit GEMM (replaces nn.Conv2d(k=3,p=1): utils.py:70, model_SP.py:10,13-30) - */
 /* Tile geometry the kernel will use for an (N,H,W) map; num_tiles sizes the BN-statistics workspace. */
@@ -73,12 +80,20 @@ int egaze_conv3x3_set_prof(void* buf);
  *   colsum : optional [Cout] fp32, ACCUMULATED: += sum over all output pixels of the final (masked) values.  When the
  *            kernel computes a data gradient this is the bias gradient of the conv that produced the masked activation,
  *            so no separate reduction pass over the gradient tensor is needed.
+ *   sub : sub-pixel decomposition of nn.Upsample(scale_factor=2) -> conv3x3 (model_SP.py:16-17,20-21,24-25,27-28), 16 instead of
+ *            36 MACs per low-resolution pixel and weight.  1 = forward: x is the LOW-resolution [N][H][W][Cin_p] map, w the mode-2
+ *            pack, the output is [N][2H][2W][Cout].  2 = data gradient: x is the PHASE-PLANAR output gradient
+ *            [4N][H][W][Cin_p] (image (py*2+px)*N + n = dY[n, 2i+py, 2j+px]), w the mode-3 pack, the output is the gradient
+ *            w.r.t. the low-resolution map [N][H][W][Cout] (the 2x2 sum of the Upsample gradient is part of the K loop).
+ *            Cin_p % 64 == 0; no reduce / ups / stats.
+ *   out_planar : store the [N][H][W][Cout] output phase-planar as [4N][H/2][W/2][Cout] (what a sub = 2 launch and the sub-pixel
+ *            weight gradient read); H, W even.
  */
 int egaze_conv3x3_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, int N, int H, int W,
                      int Cin_p, int Cout, const float* bias, const float* scale, const float* shift, int relu,
                      int reduce, int ups, const void* mask, int mask_ups, float* out_f32, void* out_hi, void* out_lo,
                      void* out_xb, float* stats, float* stats_cnt, float* colsum, int in_f16, int out_f16, float acc_scale,
-                     void* stream);
+                     int sub, int out_planar, void* stream);
 /* Plans: freeze one egaze_conv3x3_tc call (pointers, shapes, flags) with its encoded TMA descriptors (cuTensorMapEncodeTiled x4)
  * and tile configuration; run it with (plan, stream).  Valid while the buffers it names are alive; destroy with
  * egaze_plan_destroy.  ("egaze_plan_{create,destroy}: caches CUtensorMap descriptors per (ptr, shape)") */
@@ -86,13 +101,15 @@ int egaze_conv3x3_plan_create(const void* x_hi, const void* x_lo, const void* w_
                               int Cin_p, int Cout, const float* bias, const float* scale, const float* shift, int relu,
                               int reduce, int ups, const void* mask, int mask_ups, float* out_f32, void* out_hi, void* out_lo,
                               void* out_xb, float* stats, float* stats_cnt, float* colsum, int in_f16, int out_f16,
-                              float acc_scale, long long* plan);
+                              float acc_scale, int sub, int out_planar, long long* plan);
 int egaze_conv3x3_plan_run(long long plan, void* stream);
 int egaze_plan_destroy(long long plan);
 /* Weight gradient: dwp[9][Cout][Cin_p] (fp32, ACCUMULATED: zero first) += sum_pixels dY (x) X-window; tcgen05 GEMM with the
  * pixel axis as K, MN-major operands straight from NHWC.  Cin_p % 64 == 0, Cout % 64 == 0.  (loss.backward(): SP.py:136) */
+/* sub != 0: weight gradient of the sub-pixel form: x is the LOW-resolution [N][H][W][Cin_p] input, dy the phase-planar output
+ * gradient [4N][H][W][Cout], dwp the 16-plane accumulator [16][Cout][Cin_p] (-> egaze_unpack_wgrad sub = 1). */
 int egaze_wgrad3x3_tc(const void* x_hi, const void* x_lo, const void* dy_hi, const void* dy_lo, int N, int H, int W,
-                      int Cin_p, int Cout, float* dwp, int precise, void* stream);
+                      int Cin_p, int Cout, float* dwp, int precise, int sub, void* stream);
 
 /* ---- BatchNorm2d pieces (utils.py:72, model_SP.py:12, late_fusion.py:10-12) ---------------------------------- */
 /* partial [T][2][C] (mean, M2); count behind (t, c) = cnt[t*cnt_stride + c/cnt_div] */

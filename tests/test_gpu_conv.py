@@ -187,3 +187,139 @@ def test_conv_plans_match_plain_entry(cuda_dev, monkeypatch):
     assert len(ops._plans) - n0 <= 3      # 1 when the allocator recycles the output addresses (it need not, e.g. under compute-sanitizer)
     for hi, lo in outs:
         assert torch.equal(hi, ref.hi) and torch.equal(lo, ref.lo)
+
+
+# ---- sub-pixel form of nn.Upsample(scale_factor=2) -> conv3x3 (model_SP.py:16-17,20-21,24-25,27-28) ------------------------------
+SUB_SHAPES = [
+    # N, H (low-res), W, Cin, Cout
+    (2, 14, 14, 128, 128),   # partial tiles (14 rows), 2 K chunks
+    (1, 28, 28, 256, 128),
+    (2, 16, 24, 64, 64),     # one K chunk, Cout = 64 (single-CTA / pair split)
+    (1, 56, 56, 128, 64),    # the decoder's last upsample-fed layer shape family
+]
+
+
+def _planar(t):
+    """[N, C, 2H, 2W] -> phase-planar [4N, C, H, W]: image (py*2+px)*N + n holds t[n, :, py::2, px::2]."""
+    return torch.cat([t[:, :, py::2, px::2] for py in (0, 1) for px in (0, 1)], 0).contiguous()
+
+
+@pytest.mark.parametrize("shape", SUB_SHAPES)
+def test_conv3x3_subpixel_forward(cuda_dev, shape, numeric_mode):
+    """sub = 1 on the low-resolution map == conv3x3(upsample_nearest_2x(x)) (bias + ReLU epilogue), and == the kernel's own direct
+    path on the materialised upsampled map to rounding."""
+    from egaze import ops
+    N, H, W, Cin, Cout = shape
+    x, w, b = _mk(N, H, W, Cin, Cout, cuda_dev, seed=7)
+    act = ops.to_split(x)
+    wp = ops.pack_cache.get(w, 2, cols_p=act.Cp, fmt=act.fmt)
+    out, f32, _ = ops.conv3x3(act, wp, bias=b, relu=True, sub=1, want_f32=True)
+    xr = ops.from_split(act)
+    ref = F.relu(F.conv2d(F.interpolate(xr.double(), scale_factor=2, mode="nearest"), w.double(), b.double(), padding=1)).float()
+    sc = ref.abs().max().item()
+    assert tuple(f32.shape) == (N, 2 * H, 2 * W, Cout)
+    err = (ops.nhwc_f32_to_nchw(f32, Cout) - ref).abs().max().item()
+    assert err <= 3e-4 * sc, "f32 out: %.3e (scale %.3e)" % (err, sc)
+    err2 = (ops.from_split(out, Cout) - ref).abs().max().item()
+    assert err2 <= 3.2e-4 * sc, "split out: %.3e (scale %.3e)" % (err2, sc)
+
+
+@pytest.mark.parametrize("shape", SUB_SHAPES)
+def test_conv3x3_subpixel_backward(cuda_dev, shape, numeric_mode):
+    """sub = 2 (data gradient from a phase-planar dY, masked, with the bias-gradient column sums), the phase-planar store of an
+    ordinary data-gradient launch, and the sub-pixel weight gradient -- against fp64 autograd of conv3x3(upsample(x))."""
+    from egaze import ops
+    N, H, W, Cin, Cout = shape
+    x, w, b = _mk(N, H, W, Cin, Cout, cuda_dev, seed=9)
+    g = torch.Generator().manual_seed(11)
+    dy = torch.randn(N, Cout, 2 * H, 2 * W, generator=g).to(cuda_dev)
+    x_act = ops.to_split(x, xb=True)
+    dy_act = ops.grad_split(_planar(dy))                      # [4N, H, W, Cout] bf16 planes
+    # reference on the operands the kernels see
+    xq = (x_act.xb.float() if x_act.xb is not None else ops.from_split_nhwc(x_act)).permute(0, 3, 1, 2)[:, :Cin].double()
+    dyq = ops.from_split_nhwc(dy_act).permute(0, 3, 1, 2).double()     # planar, rounded
+    dyq_full = torch.zeros(N, Cout, 2 * H, 2 * W, dtype=torch.float64, device=cuda_dev)
+    for ph, (py, px) in enumerate([(0, 0), (0, 1), (1, 0), (1, 1)]):
+        dyq_full[:, :, py::2, px::2] = dyq[ph * N:(ph + 1) * N]
+    xq.requires_grad_(True)
+    wd = w.double().requires_grad_(True)
+    y = F.conv2d(F.interpolate(xq, scale_factor=2, mode="nearest"), wd, None, padding=1)
+    y.backward(dyq_full)
+    # (a) weight gradient
+    gw = ops.wgrad3x3(x_act, dy_act, Cout, Cin, sub=True)
+    e = ((gw.double() - wd.grad).norm() / wd.grad.norm()).item()
+    assert e <= (2e-4 if ops.mode()["wgrad_precise"] or x_act.fmt == 1 else 3e-3), "wgrad rel-L2 %.3e" % e
+    # (b) data gradient, fp32 out
+    wp = ops.pack_cache.get(w, 3, cols_p=dy_act.Cp)
+    _, gx, _ = ops.conv3x3(dy_act, wp, sub=2, want_f32=True, want_split=False, want_lo=ops.mode()["dy_lo"])
+    assert tuple(gx.shape) == (N, H, W, Cin)
+    ref = xq.grad.float()
+    err = (ops.nhwc_f32_to_nchw(gx, Cin) - ref).abs().max().item()
+    assert err <= 3e-4 * ref.abs().max().item(), "dgrad max-abs %.3e (scale %.3e)" % (err, ref.abs().max().item())
+    # (c) masked, bf16 out, column sums
+    mask_src = torch.randn(N, Cin, H, W, generator=g).to(cuda_dev)
+    mact = ops.to_split(mask_src, Cin)
+    cs = torch.zeros(Cin, device=cuda_dev)
+    gm, _, _ = ops.conv3x3(dy_act, wp, sub=2, mask=mact.hi, colsum=cs, want_lo=ops.mode()["dy_lo"])
+    refm = ref * (mact.hi.float().permute(0, 3, 1, 2) > 0)
+    got = ops.from_split_nhwc(gm).permute(0, 3, 1, 2)
+    tol = 3e-4 if ops.mode()["dy_lo"] else 5e-3          # hi-only bf16 store: 2^-9 relative
+    assert (got - refm).abs().max().item() <= tol * ref.abs().max().item()
+    ecs = (cs - refm.sum((0, 2, 3))).abs().max().item()
+    assert ecs <= 3e-4 * refm.abs().sum((0, 2, 3)).max().item() + 1e-3, "colsum %.3e" % ecs
+
+
+def test_conv3x3_planar_store(cuda_dev, numeric_mode):
+    """out_planar: the same values as the ordinary store, laid out [4N][H/2][W/2][C] by output-pixel parity (masked dgrad mode)."""
+    from egaze import ops
+    N, H, W, Cin, Cout = 2, 28, 24, 64, 128
+    x, w, b = _mk(N, H, W, Cout, Cin, cuda_dev, seed=13)     # a data-gradient launch: operand has the conv's Cout channels
+    wt = torch.randn(Cout, Cin, 3, 3, device=cuda_dev) * 0.05
+    act = ops.grad_split(x)
+    wp = ops.pack_cache.get(wt, 1, cols_p=act.Cp)
+    g = torch.Generator().manual_seed(3)
+    mact = ops.to_split(torch.randn(N, Cin, H, W, generator=g).to(cuda_dev), Cin)
+    cs0, cs1 = torch.zeros(Cin, device=cuda_dev), torch.zeros(Cin, device=cuda_dev)
+    a, _, _ = ops.conv3x3(act, wp, mask=mact.hi, colsum=cs0, want_lo=ops.mode()["dy_lo"])
+    p, _, _ = ops.conv3x3(act, wp, mask=mact.hi, colsum=cs1, want_lo=ops.mode()["dy_lo"], planar=True)
+    assert tuple(p.hi.shape) == (4 * N, H // 2, W // 2, Cin)
+    ref = torch.cat([a.hi[:, py::2, px::2] for py in (0, 1) for px in (0, 1)], 0)
+    assert torch.equal(p.hi, ref)
+    if a.lo is not None:
+        assert torch.equal(p.lo, torch.cat([a.lo[:, py::2, px::2] for py in (0, 1) for px in (0, 1)], 0))
+    assert torch.allclose(cs0, cs1, rtol=1e-5, atol=1e-5)
+    _, f, _ = ops.conv3x3(act, wp, want_f32=True, want_split=False, planar=True)
+    _, f0, _ = ops.conv3x3(act, wp, want_f32=True, want_split=False)
+    assert torch.equal(f, torch.cat([f0[:, py::2, px::2] for py in (0, 1) for px in (0, 1)], 0))
+
+
+def test_subpixel_weight_pack_roundtrip(cuda_dev):
+    """The 16-plane pack (modes 2 / 3) is the fp32 pre-sum of the 3x3 taps, and the sub-pixel unpack is its transpose."""
+    from egaze import ops
+    Co, Ci = 64, 128
+    w = torch.randn(Co, Ci, 3, 3, device=cuda_dev)
+    V = {(0, 0): [0], (0, 1): [1, 2], (1, 0): [0, 1], (1, 1): [2]}
+    ref = torch.zeros(16, Co, Ci, device=cuda_dev)
+    for py in (0, 1):
+        for px in (0, 1):
+            for a in (0, 1):
+                for b in (0, 1):
+                    for r in V[(py, a)]:
+                        for s in V[(px, b)]:
+                            ref[(py * 2 + px) * 4 + a * 2 + b] += w[:, :, r, s]
+    hi, lo, _, _, _ = ops.pack_cache.get(w, 2, cols_p=Ci, fmt=0)
+    assert (hi.float() + lo.float() - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
+    hi3, lo3, _, _, _ = ops.pack_cache.get(w, 3, cols_p=Co, fmt=0)
+    assert (hi3.float() + lo3.float() - ref.transpose(1, 2)).abs().max().item() <= 2e-5 * ref.abs().max().item()
+    q = torch.randn(16, Co, Ci, device=cuda_dev)
+    gw = torch.empty(Co, Ci, 3, 3, device=cuda_dev)
+    ops.call("egaze_unpack_wgrad", q.clone(), Co, Ci, Co, Ci, 0.0, 0, 1, gw, ops.stream_ptr())
+    refg = torch.zeros_like(gw)
+    for py in (0, 1):
+        for px in (0, 1):
+            for a in (0, 1):
+                for b in (0, 1):
+                    for r in V[(py, a)]:
+                        for s in V[(px, b)]:
+                            refg[:, :, r, s] += q[(py * 2 + px) * 4 + a * 2 + b]
+    assert torch.allclose(gw, refg, rtol=1e-6, atol=1e-6)

@@ -18,7 +18,9 @@ tab = ops.conv_timer_table(); ops.conv_timer_reset(False)
 tot = 0.0
 for d, ms in tab:
     kind, N, H, W, Ci, Co, red, ups, st = d
-    fl = 2.0 * N * H * W * Ci * Co * 9
+    # algorithmic FLOPs of the reference's direct convolution: a sub-pixel launch (low-resolution H x W listed) stands for the
+    # 3x3 conv on the 2H x 2W upsampled map
+    fl = 2.0 * N * H * W * Ci * Co * 9 * (4 if "sub" in kind else 1)
     tot += ms
-    print("%-5s N=%2d %3dx%-3d %3d->%-3d red=%d ups=%d stats=%d  %7.3f ms  %6.1f TFLOP/s(padded)" % (kind, N, H, W, Ci, Co, red, ups, st, ms, fl / ms / 1e9))
+    print("%-10s N=%2d %3dx%-3d %3d->%-3d red=%d ups=%d stats=%d  %7.3f ms  %6.1f TFLOP/s(padded)" % (kind, N, H, W, Ci, Co, red, ups, st, ms, fl / ms / 1e9))
 print("timed kernels %.2f ms of step %.2f ms (%s)" % (tot, e0.elapsed_time(e1), ops.precision()))

@@ -14,7 +14,7 @@ for name, N, H, W, Ci, Co in LAYERS:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         dwp = torch.zeros((9, Co, Ci), device="cuda")
         e0.record()
-        ops.call("egaze_wgrad3x3_tc", xa.hi, xa.lo, dya.hi, dya.lo, N, H, W, Ci, Co, dwp, 1, ops.stream_ptr())
+        ops.call("egaze_wgrad3x3_tc", xa.hi, xa.lo, dya.hi, dya.lo, N, H, W, Ci, Co, dwp, 1, 0, ops.stream_ptr())
         e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     print("%-16s %.3f ms  %.1f TFLOP/s" % (name, ms, 2.0 * N * H * W * Co * Ci * 9 / ms / 1e9))
