@@ -18,6 +18,10 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
          "-Xptxas", "-v" if os.environ.get("EGAZE_PTXAS_V") else "-O3"]
+if os.environ.get("EGAZE_MBAR_SPIN"):   # experiment: mbarrier waits poll test_wait instead of try_wait + suspend hint
+    FLAGS.append("-DEGAZE_MBAR_SPIN")
+if os.environ.get("EGAZE_CONV_PROF"):   # per-role cycle counters in the conv kernel (tools/conv_prof.py); never the shipped build
+    FLAGS.append("-DEGAZE_CONV_PROF")
 
 
 def _sources():

@@ -266,18 +266,33 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must surface as a trapped launch (cudaErrorLaunchFailure),
-// never as a hung GPU.  ~2 s of try_wait retries at most.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
+// Bounded wait: a protocol bug must surface as a trapped launch (cudaErrorLaunchFailure), never as a hung GPU (~2 s of
+// try_wait retries at most).  The retry loop with its clock reads and the diagnostic printf is kept OUT of line: inlined at
+// every wait site it put ~25 instructions of cold code into loops whose instruction-cache footprint is what bounds them
+// (conv3x3_tc.cu, MMA warp).
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, 0x989680;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
     if (clock64() - t0 > 4000000000LL) {
-      printf("egaze: mbarrier wait timeout (block %d,%d thread %d bar@%u parity %u)\n", blockIdx.x, blockIdx.y,
-             threadIdx.x, smem_u32(bar), parity);
+      printf("egaze: mbarrier wait timeout (block %d,%d thread %d bar@%u parity %u)\n", blockIdx.x, blockIdx.y, threadIdx.x, bar,
+             parity);
       __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(smem_u32(bar), parity);
 }
 
 // ---- TMA (cp.async.bulk.tensor, tiled mode) --------------------------------------------------

@@ -76,6 +76,7 @@ int main() {
       {128, 64, 0, 0, 0, 256}, {256, 128, 0, 0, 0, 256}, {128, 128, 0, 0, 0, 256}, {64, 64, 0, 0, 0, 256},
       {128, 128, 0, 0, 0, 128}, {64, 64, 0, 0, 0, 128}, {64, 64, 0, 0, 0, 64}, {128, 64, 0, 0, 0, 128},
       {128, 128, 0, 0, 0, 0}, {64, 64, 0, 0, 0, 0}, {256, 128, 0, 0, 0, 0},
+      {128, 64, 0, 0, 0, 32}, {128, 64, 0, 0, 0, 64}, {256, 128, 0, 0, 0, 64}, {128, 0, 0, 0, 1, 0},
       {192, 192, 1, 1, 0, 256}, {192, 192, 1, 1, 0, 0}, {192, 0, 1, 1, 1, 0},
   };
   const int iters = 512;
