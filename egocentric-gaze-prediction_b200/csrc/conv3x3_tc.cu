@@ -97,7 +97,6 @@ struct ConvTcParams {
   int win;             // 1 = "window" mode: ONE (BH+2) x (BW+2) activation window per K chunk serves all nine taps
   int win_bo;          // window mode: fill the descriptor's base_offset field with (start >> 7) & 7
   int SA, SB;          // ring depths
-  int direct;          // 1 = the warp-private "direct" epilogue (epilogue_direct), 0 = the staged one
   int probe;           // 1 = the round-1 MMA loop everywhere (barrier probes fused into a per-tap asm block); 0 = the lean unrolled
                        //     tap loop for window-mode CTA pairs (see the MMA warp)
   int wstat;           // 1 = weight-stationary: every weight box of the layer (9 taps x chunks <= SB) is loaded ONCE per CTA and
@@ -488,252 +487,6 @@ __device__ __forceinline__ void lean_tap_2sm(uint32_t d1, uint32_t d2, uint32_t 
 #undef EGAZE_LT_HEAD2
 #undef EGAZE_LT_OPERANDS
 
-// ---------------------------------------------------------------------------------------------------------------------------
-// "Direct" epilogue: every epilogue warp drains its own 32-pixel x 32-channel accumulator blocks on its own.
-//
-// The staged epilogue further down moves a whole 128 x 64 chunk through ONE shared staging tile: eight warps in lockstep, two
-// named barriers per chunk, and a store loop whose unrolled body (several KB of code per tile, executed twice) is bound by
-// instruction fetch and exposed latency -- 2,300-4,700 cycles per tile of the 64-channel 224^2 layers against 2,304-3,456
-// cycles of MMAs (-DEGAZE_CONV_PROF accounting, tools/conv_prof.py).  Here a warp
-//   1. loads its block from TMEM (lane = pixel), adds the hi/lo accumulator blocks and writes the 32 x 32 floats to a
-//      warp-PRIVATE staging tile [32][36] (conflict-free 16-byte stores), then hands the accumulator stage back;
-//   2. reads the tile back transposed -- lane = (pixel-row group of 4, channel quad of 8), four pixel rows per step -- so the
-//      per-channel constants (folded bias / BatchNorm affine, statistics reference) are per-lane registers, eight lanes of a
-//      store cover a pixel's 64- or 128-byte run, and the BatchNorm statistics / bias-gradient column sums are per-lane
-//      running sums folded with two shuffles per value at the end of the block;
-//   3. adds its sums into the row of its TMEM lane group in shared memory (only that warp and its column twin, on disjoint
-//      channels, ever touch the row).
-// No barrier between the warps except the one-off agreement on the statistics reference value of a channel block; the loops are
-// a few dozen instructions long.  Serves every launch with reduce == 0, no replicate, BN % 64 == 0 and a power-of-two tile width.
-// ---------------------------------------------------------------------------------------------------------------------------
-constexpr int kDirPitch = 36;                       // floats per staged pixel row (32 + 4: conflict-free float4 stores)
-constexpr int kDirStage = 8 * 32 * kDirPitch;       // floats of the eight warp-private staging tiles
-
-template <int NSPLIT, int CS>
-__device__ __forceinline__ void epilogue_direct(const ConvTcParams& p, float* stage, uint64_t* acc_full, uint64_t* acc_empty,
-                                                uint32_t tmem_base, int warp, int lane, int rank, int cluster_id, int num_clusters,
-                                                bool pair) {
-  const int ew = warp - 2;                 // 0..7
-  const int lg = warp & 3;                 // TMEM lane group this warp may access
-  const int colsel = ew >> 2;              // which 32-column half of a 64-column chunk this warp drains
-  const int et = threadIdx.x - 64;         // 0..255
-  float* wst = stage + ew * (32 * kDirPitch);
-  const uint32_t wst_s = ptx::smem_u32(wst);
-  float* st_k = stage + kDirStage;                               // [Cout] statistics reference (first pixel the CTA saw)
-  const int nq = p.stats ? 2 : (p.colsum ? 1 : 0);
-  float* rows = st_k + (p.stats ? p.Cout : 0);                   // [4 lane groups][nq][Cout] running sums
-  float* cnt = rows + 4 * nq * p.Cout;                           // [4][tiles_n] pixels behind the statistics
-  if (nq) {
-    for (int i = et; i < 4 * nq * p.Cout + 4 * p.tiles_n; i += kEpiThreads) rows[i] = 0.f;
-    ptx::named_bar_sync(1, kEpiThreads);
-  }
-  float* my_rows = rows + lg * nq * p.Cout;
-  const int bw_log = 31 - __clz(p.BW);
-  const int bw_mask = p.BW - 1;
-  const bool f32 = p.out_f32 != nullptr;
-  const int outk = f32 ? 0 : (p.out_f16 ? (p.out_xb ? 3 : 2) : (p.out_lo ? 1 : 4));
-  const int rep = p.sub == 1 ? 2 : 1;      // sub-pixel forward: this phase's pixels sit at stride 2 in the 2H x 2W output
-  const int Hs = p.H * rep, Ws = p.W * rep;
-  const int out_row = p.out_planar ? (p.W >> 1) * p.Cout : rep * Ws * p.Cout;
-  const int out_px = p.out_planar ? p.Cout : rep * p.Cout;
-  const int mf = p.mask_ups ? 2 : 1;
-  const int mask_row = mf * mf * p.W * p.Cout, mask_px = mf * p.Cout;
-  const float asc = p.acc_scale;
-  const float lo_clamp = p.relu ? 0.f : -INFINITY;
-  const uint32_t acc_cols = (uint32_t)p.acc_cols;
-  const int nchunk = p.BN >> 6;            // 64-channel chunks per n-tile
-  unsigned long long st_seen = 0;          // bit per 64-channel chunk of the layer: reference value chosen
-  int as = 0;
-  uint32_t full_par = 0;
-  int c_have = -1;                         // first channel the per-lane constants below belong to
-  float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f), t4 = make_float4(0.f, 0.f, 0.f, 0.f), k4 = t4;   // this lane's channel quad
-  long long prof_wait = 0;
-  const long long prof_start = PROF_ON(p) ? clock64() : 0;
-  for (int w = cluster_id; w < p.num_items; w += num_clusters) {
-    const Item it = decode_item(p, w, CS, rank);
-    { PROF_T0(p); ptx::mbar_wait(&acc_full[as], (full_par >> as) & 1u); PROF_ADD(p, prof_wait); }
-    full_par ^= 1u << as;
-    ptx::tc_fence_after();
-    const uint32_t t_acc = tmem_base + (uint32_t)as * acc_cols + ((uint32_t)(lg * 32) << 16);
-    size_t obase, mbase = 0;
-    if (p.out_planar) obase = ((size_t)(it.img * (p.H >> 1) + (it.h0 >> 1)) * (p.W >> 1) + (size_t)(it.w0 >> 1)) * p.Cout;
-    else obase = ((size_t)(it.img * Hs + it.h0 * rep + (it.phase >> 1)) * Ws + (size_t)(it.w0 * rep + (it.phase & 1))) * p.Cout;
-    if (p.mask) mbase = ((size_t)(it.img * mf * p.H + mf * it.h0) * (mf * p.W) + (size_t)(mf * it.w0)) * p.Cout;
-    for (int b = 0; b < nchunk; ++b) {
-      const int cb = b * 64 + colsel * 32;            // this warp's 32 channels inside the n-tile
-      // ---- 1. TMEM -> registers (lane = pixel) -> warp-private staging
-      {
-        uint32_t v[32];
-        uint32_t col0 = (uint32_t)cb, col1 = (uint32_t)(p.BN + cb);
-        if (pair && NSPLIT == 2) {
-          const uint32_t hb = (uint32_t)p.BN >> 1, half = (uint32_t)cb >= hb ? 1u : 0u;
-          col0 = half * (uint32_t)p.BN + ((uint32_t)cb - half * hb);
-          col1 = col0 + hb;
-        }
-        ptx::tmem_ld_32x32(t_acc + col0, v);
-        if (p.nsum >= 2) {
-          uint32_t v2[32];
-          ptx::tmem_ld_32x32(t_acc + col1, v2);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
-          if (p.nsum == 3) {
-            ptx::tmem_ld_32x32(t_acc + (uint32_t)(2 * p.BN + cb), v2);
-            ptx::tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
-          }
-        } else {
-          ptx::tmem_ld_wait();
-        }
-        const uint32_t dst = wst_s + (uint32_t)(lane * kDirPitch * 4);
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) ptx::sts128(dst + j * 4, v[j], v[j + 1], v[j + 2], v[j + 3]);
-      }
-      if (b == nchunk - 1) {
-        // last block read: hand the accumulator stage back to the MMA warp (one arrive per epilogue warp)
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if (pair && rank != 0) ptx::mbar_arrive_leader_relaxed(&acc_empty[as]);
-          else ptx::mbar_arrive(&acc_empty[as]);
-        }
-      } else {
-        __syncwarp();
-      }
-      if (it.valid) {
-        const int n0 = it.nt * p.BN + cb;
-        const int chunk_id = it.nt * nchunk + b;
-        if (p.stats && !((st_seen >> chunk_id) & 1ull)) {
-          // reference value of a channel = its raw accumulator at the tile's first pixel (always a valid one), taken from
-          // the lane-group-0 warp of this column half; every warp waits for it once per chunk of the layer
-          if (lg == 0) st_k[n0 + lane] = wst[lane];
-          ptx::named_bar_sync(2, kEpiThreads);
-          st_seen |= 1ull << chunk_id;
-        }
-        // ---- 2. staging -> global, transposed: lane = (pixel-row group rg of 4, channel quad q of 8).  Rows 4i .. 4i+3 of a warp
-        //         are four horizontally adjacent pixels (BW is a multiple of 8), so a lane's offset inside a step is constant.
-        const int m0 = lg * 32;              // first pixel (GEMM row) of this warp inside the tile
-        const int rg = lane >> 3, q = lane & 7;
-        const int c = n0 + 4 * q;
-        if (c != c_have) {
-          const float4 bb = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          const float4 ss = p.scale ? __ldg(reinterpret_cast<const float4*>(p.scale + c)) : make_float4(1.f, 1.f, 1.f, 1.f);
-          const float4 tt = p.scale ? __ldg(reinterpret_cast<const float4*>(p.shift + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          t4 = make_float4(fmaf(bb.x, ss.x, tt.x), fmaf(bb.y, ss.y, tt.y), fmaf(bb.z, ss.z, tt.z), fmaf(bb.w, ss.w, tt.w));
-          s4 = make_float4(ss.x * asc, ss.y * asc, ss.z * asc, ss.w * asc);
-          if (p.stats) k4 = *reinterpret_cast<const float4*>(st_k + c);
-          c_have = c;
-        }
-        // offset of pixel (ph, pw0 + rg): [plane] + row + column, branch-free for both output layouts
-        const int ps = p.out_planar ? 1 : 0;
-        const size_t lane_off = (p.out_planar ? (size_t)(rg & 1) * (size_t)p.planar_stride + (size_t)((rg >> 1) * out_px)
-                                              : (size_t)(rg * out_px)) + obase + c;
-        const size_t plane2 = p.out_planar ? 2 * (size_t)p.planar_stride : 0;
-        const size_t mlane_off = mbase + (size_t)(rg * mask_px) + c;
-        const uint32_t src = wst_s + (uint32_t)((rg * kDirPitch + 4 * q) * 4);
-        float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), a2 = a1;   // statistics (s1, s2) or column sums (a1)
-        int npx = 0;
-#pragma unroll 2
-        for (int i = 0; i < 8; ++i) {
-          const int m = m0 + 4 * i, ph = m >> bw_log, pw0 = m & bw_mask;
-          const bool ok = it.h0 + ph < p.H && it.w0 + pw0 + rg < p.W;
-          uint2 mk = make_uint2(0x3f803f80u, 0x3f803f80u);      // no mask: all "positive"
-          if (p.mask && ok) mk = __ldg(reinterpret_cast<const uint2*>(p.mask + mlane_off + (size_t)(ph * mask_row + pw0 * mask_px)));
-          const float4 x = ptx::lds128(src + (uint32_t)(i * 4 * kDirPitch * 4));
-          if (ok) {
-            const size_t off = lane_off + (size_t)(ph & ps) * plane2 + (size_t)((ph >> ps) * out_row + (pw0 >> ps) * out_px);
-            if (f32) {
-              if (p.stats) {
-                const float dx = x.x - k4.x, dy = x.y - k4.y, dz = x.z - k4.z, dw = x.w - k4.w;
-                a1.x += dx; a1.y += dy; a1.z += dz; a1.w += dw;
-                a2.x = fmaf(dx, dx, a2.x); a2.y = fmaf(dy, dy, a2.y); a2.z = fmaf(dz, dz, a2.z); a2.w = fmaf(dw, dw, a2.w);
-                ++npx;
-              }
-              *reinterpret_cast<float4*>(p.out_f32 + off) = epi_affine(x, s4, t4, lo_clamp);
-            } else {
-              float4 v = epi_affine(x, s4, t4, lo_clamp);
-              if (!pos16(mk.x & 0xffffu)) v.x = 0.f;
-              if (!pos16(mk.x >> 16)) v.y = 0.f;
-              if (!pos16(mk.y & 0xffffu)) v.z = 0.f;
-              if (!pos16(mk.y >> 16)) v.w = 0.f;
-              a1.x += v.x; a1.y += v.y; a1.z += v.z; a1.w += v.w;
-              uint2 hi2, lo2;
-              if (outk == 1) {
-                split_bf16x4(v, hi2, lo2);
-                *reinterpret_cast<uint2*>(p.out_hi + off) = hi2;
-                *reinterpret_cast<uint2*>(p.out_lo + off) = lo2;
-              } else if (outk == 4) {
-                *reinterpret_cast<uint2*>(p.out_hi + off) = pack_bf16x4(v);
-              } else {
-                split_f16x4(v, hi2, lo2);
-                *reinterpret_cast<uint2*>(p.out_hi + off) = hi2;
-                *reinterpret_cast<uint2*>(p.out_lo + off) = lo2;
-                if (outk == 3) *reinterpret_cast<uint2*>(p.out_xb + off) = pack_bf16x4(v);
-              }
-            }
-          }
-        }
-        if (nq) {
-          // fold the four row groups (lanes 8 apart), then lanes 0..7 add the quad's sums into this lane group's row
-#pragma unroll
-          for (int o = 8; o <= 16; o <<= 1) {
-            a1.x += __shfl_xor_sync(0xffffffffu, a1.x, o); a1.y += __shfl_xor_sync(0xffffffffu, a1.y, o);
-            a1.z += __shfl_xor_sync(0xffffffffu, a1.z, o); a1.w += __shfl_xor_sync(0xffffffffu, a1.w, o);
-            if (p.stats) {
-              a2.x += __shfl_xor_sync(0xffffffffu, a2.x, o); a2.y += __shfl_xor_sync(0xffffffffu, a2.y, o);
-              a2.z += __shfl_xor_sync(0xffffffffu, a2.z, o); a2.w += __shfl_xor_sync(0xffffffffu, a2.w, o);
-              npx += __shfl_xor_sync(0xffffffffu, npx, o);
-            }
-          }
-          if (rg == 0) {
-            float4* r1 = reinterpret_cast<float4*>(my_rows + c);
-            float4 t = *r1;
-            t.x += a1.x; t.y += a1.y; t.z += a1.z; t.w += a1.w;
-            *r1 = t;
-            if (p.stats) {
-              float4* r2 = reinterpret_cast<float4*>(my_rows + p.Cout + c);
-              t = *r2;
-              t.x += a2.x; t.y += a2.y; t.z += a2.z; t.w += a2.w;
-              *r2 = t;
-              if (colsel == 0 && b == 0 && lane == 0) cnt[lg * p.tiles_n + it.nt] += (float)npx;
-            }
-          }
-        }
-      }
-      __syncwarp();   // the staging tile is free for the next block
-    }
-    as ^= 1;
-  }
-  if (PROF_ON(p) && et == 0) {
-    long long* o = p.prof + (size_t)blockIdx.x * 16;
-    o[7] = prof_wait; o[8] = clock64() - prof_start; o[9] = (p.num_items - cluster_id + num_clusters - 1) / num_clusters;
-  }
-  if (nq) ptx::named_bar_sync(1, kEpiThreads);
-  if (p.colsum) {
-    for (int c = et; c < p.Cout; c += kEpiThreads)
-      atomicAdd(p.colsum + c, (rows[c] + rows[p.Cout + c]) + (rows[2 * p.Cout + c] + rows[3 * p.Cout + c]));
-  }
-  if (p.stats) {
-    // one (mean, M2, n) partial per CTA and channel; bias shifts the mean only
-    for (int c = et; c < p.Cout; c += kEpiThreads) {
-      const int nt = c / p.BN;
-      const float n = (cnt[nt] + cnt[p.tiles_n + nt]) + (cnt[2 * p.tiles_n + nt] + cnt[3 * p.tiles_n + nt]);
-      float mean = 0.f, m2 = 0.f;
-      if (n > 0.f) {   // the sums were taken over the raw accumulators: scale them (acc_scale is a power of two: exact)
-        float s1 = 0.f, sq = 0.f;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) { s1 += rows[(g * 2 + 0) * p.Cout + c]; sq += rows[(g * 2 + 1) * p.Cout + c]; }
-        mean = (st_k[c] + s1 / n) * asc;
-        m2 = fmaxf(sq - s1 * s1 / n, 0.f) * (asc * asc);
-      }
-      p.stats[((size_t)blockIdx.x * 2 + 0) * p.Cout + c] = mean + (p.bias ? __ldg(p.bias + c) : 0.f);
-      p.stats[((size_t)blockIdx.x * 2 + 1) * p.Cout + c] = m2;
-      if (c % p.BN == 0) p.stats_cnt[(size_t)blockIdx.x * p.tiles_n + nt] = n;
-    }
-  }
-}
-
 // NSA / NSPLIT: planes of the activation / weight operand: (2, 2) 3 MMAs per product, (1, 2) 2 MMAs, (1, 1) one.
 template <int NSA, int NSPLIT, int KSTEPS, int CS>
 __global__ void __maxnreg__(128)
@@ -1120,9 +873,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     }
   } else {
     // ================================ epilogue warps (8) ================================
-    if (p.direct) {
-      epilogue_direct<NSPLIT, CS>(p, stage, acc_full, acc_empty, tmem_base, warp, lane, rank, cluster_id, num_clusters, pair);
-    } else {
     // Two warps per TMEM lane group: warps 2..5 take the even 32-column blocks, warps 6..9 the odd ones.
     const int ew = warp - 2;                 // 0..7
     const int lg = warp & 3;                 // TMEM lane group this warp may access
@@ -1484,7 +1234,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         if (c % p.BN == 0) p.stats_cnt[(size_t)blockIdx.x * p.tiles_n + c / p.BN] = n;
       }
     }
-    }   // staged epilogue
   }
 
   __syncthreads();
@@ -1533,16 +1282,10 @@ extern "C" int egaze_conv3x3_tiles(int N, int H, int W, int need_even, int* num_
   return EGAZE_OK;
 }
 
-// Bytes of the epilogue's shared memory behind the operand rings (1 KB granules): the staged epilogue's [128][CW+4] tile, its
-// scratch and per-CTA sums, or the direct epilogue's eight warp-private tiles, reference values and per-lane-group sums.
-static int conv_stage_bytes(int bn, int Cout, bool stats, bool colsum, bool direct) {
-  int bytes;
-  if (direct) {
-    const int nq = stats ? 2 : (colsum ? 1 : 0);
-    bytes = (kDirStage + (stats ? Cout : 0) + 4 * nq * Cout + 4 * (Cout / bn)) * 4;
-  } else {
-    bytes = 128 * ((bn < 64 ? bn : 64) + 4) * 4 + kEpiScratch * 4 + (stats ? Cout * 3 * 4 : 0) + (colsum ? Cout * 4 : 0);
-  }
+// Bytes of the epilogue's shared memory behind the operand rings (1 KB granules): the [128][CW+4] staging tile, its scratch and
+// the per-CTA running sums.
+static int conv_stage_bytes(int bn, int Cout, bool stats, bool colsum) {
+  const int bytes = 128 * ((bn < 64 ? bn : 64) + 4) * 4 + kEpiScratch * 4 + (stats ? Cout * 3 * 4 : 0) + (colsum ? Cout * 4 : 0);
   return (bytes + 1023) / 1024 * 1024;
 }
 
@@ -1628,14 +1371,6 @@ static int conv_build(ConvPlan* pl, const void* x_hi, const void* x_lo, const vo
 
   memset(&p, 0, sizeof(p));
   p.N = N; p.H = H; p.W = W; p.Cin_p = Cin_p; p.Cout = Cout;
-  // the warp-private epilogue serves: no 2x2 reduce, no replicate, ONE kind of output (fp32, or 16-bit planes in a supported set)
-  static int direct_env = -1;
-  if (direct_env < 0) {
-    const char* e = getenv("EGAZE_CONV_DIRECT");
-    direct_env = e ? atoi(e) : 1;
-  }
-  const bool can_direct = direct_env && reduce == 0 && !ups && !(out_f32 && out_hi) && !(out_hi && !out_f16 && out_xb) &&
-                          !(stats && !out_f32) && !(colsum && out_f32);
   p.KC = (Cin_p % 64 == 0) ? 64 : ((Cin_p % 32 == 0) ? 32 : 16);
   pick_tile(H, W, reduce != 0 || out_planar, &p.BH, &p.BW);
   static int win_env = -1;
@@ -1652,7 +1387,7 @@ static int conv_build(ConvPlan* pl, const void* x_hi, const void* x_lo, const vo
     const double eff_c = (double)H * W / ((double)ceil_div(H, p.BH) * ceil_div(W, p.BW) * 128.0);
     // ring depth the weight boxes would get next to two 180-row windows (see the smem budget below)
     const int bn = conv_pick_bn(Cout, precise), ns = precise ? 2 : 1;
-    const int stage_b = conv_stage_bytes(bn, Cout, stats != nullptr, colsum != nullptr, can_direct && bn % 64 == 0);
+    const int stage_b = conv_stage_bytes(bn, Cout, stats != nullptr, colsum != nullptr);
     const int sb_w = (222 * 1024 - stage_b - 2 * nsa * 23552) / (ns * bn * 128);
     if ((eff_w >= eff_c * 0.999 && sb_w >= win_minsb) || sub) {
       p.win = 1;
@@ -1698,8 +1433,7 @@ static int conv_build(ConvPlan* pl, const void* x_hi, const void* x_lo, const vo
   const int b_plane_rows = p.pair ? p.BN / 2 : p.BN;   // weight rows of one plane kept in THIS CTA's slot
   p.b_slot_bytes = ((b_plane_rows * row_bytes + 1023) / 1024) * 1024;
   const int CW = p.BN < 64 ? p.BN : 64;
-  p.direct = (can_direct && p.BN % 64 == 0 && (p.BW & (p.BW - 1)) == 0) ? 1 : 0;
-  const int stage_bytes = conv_stage_bytes(p.BN, Cout, stats != nullptr, colsum != nullptr, p.direct != 0);
+  const int stage_bytes = conv_stage_bytes(p.BN, Cout, stats != nullptr, colsum != nullptr);
   (void)CW;
   static int sa_env = -1;
   if (sa_env < 0) {
