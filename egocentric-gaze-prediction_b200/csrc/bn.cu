@@ -17,7 +17,10 @@ bn_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ 
                    int T, int C, float eps,
                    float momentum, const float* __restrict__ gamma, const float* __restrict__ beta,
                    float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ mean_out,
-                   float* __restrict__ invstd_out, float* __restrict__ scale_out, float* __restrict__ shift_out) {
+                   float* __restrict__ invstd_out, float* __restrict__ scale_out, float* __restrict__ shift_out,
+                   long long* __restrict__ num_batches_tracked) {
+  // nn.BatchNorm2d.num_batches_tracked += 1 rides along (one thread of the launch) instead of costing an add_ kernel per layer
+  if (num_batches_tracked && blockIdx.x == 0 && threadIdx.x == 0 && threadIdx.y == 0) *num_batches_tracked += 1;
   __shared__ double s_n[32][33], s_a[32][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   const int sl = threadIdx.y;
@@ -386,12 +389,13 @@ __global__ void col_sum_split_kernel(const __nv_bfloat16* __restrict__ hi, const
 extern "C" int egaze_bn_finalize(const float* partial, const float* cnt, int cnt_stride, int cnt_div, int T, int C,
                                  float eps, float momentum,
                                  const float* gamma, const float* beta, float* running_mean, float* running_var,
-                                 float* mean_out, float* invstd_out, float* scale_out, float* shift_out, void* stream) {
+                                 float* mean_out, float* invstd_out, float* scale_out, float* shift_out,
+                                 long long* num_batches_tracked, void* stream) {
   EGAZE_CHECK_ARG(partial && cnt && T > 0 && C > 0 && cnt_stride > 0 && cnt_div > 0, "bn_finalize: bad args");
   dim3 block(32, 32), grid(ceil_div(C, 32));
   bn_finalize_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(partial, cnt, cnt_stride, cnt_div, T, C, eps, momentum, gamma, beta,
                                                                running_mean, running_var, mean_out, invstd_out,
-                                                               scale_out, shift_out);
+                                                               scale_out, shift_out, num_batches_tracked);
   EGAZE_LAUNCH_CHECK();
   return EGAZE_OK;
 }

@@ -42,6 +42,50 @@ __global__ void nchw_to_nhwc_split_kernel(const float* __restrict__ x, int C, in
   }
 }
 
+// The same for C <= 32 input channels (the module-boundary case: RGB 3 -> 16, flow 20 -> 32, with a 64-channel bf16 copy for the
+// first layer's weight gradient): one block converts 128 pixels x all channels, reads are 512-byte runs along the pixel axis,
+// every store is a 16-byte vector (8 channels) and consecutive lanes cover consecutive 16-byte pieces -- the padded planes
+// are mostly zeros (xb: 61 of 64 channels for RGB), so the kernel is bound by its writes (868 MB per B = 32 step at 224^2).
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_split_small_kernel(const float* __restrict__ x, int C, int HW, int Cp, __nv_bfloat16* __restrict__ hi,
+                                __nv_bfloat16* __restrict__ lo, __nv_bfloat16* __restrict__ xb, int Cp_xb, int fmt) {
+  __shared__ float tile[32][129];
+  const int n = blockIdx.y, p0 = blockIdx.x * 128;
+  const float* xn = x + (size_t)n * C * HW;
+  for (int i = threadIdx.x; i < 32 * 128; i += 256) {
+    const int c = i >> 7, pp = i & 127;
+    tile[c][pp] = (c < C && p0 + pp < HW) ? __ldg(xn + (size_t)c * HW + p0 + pp) : 0.f;
+  }
+  __syncthreads();
+  const int G = Cp >> 3;                 // 16-byte groups per pixel in the hi / lo planes
+  for (int i = threadIdx.x; i < 128 * G; i += 256) {
+    const int pp = i / G, g = i - pp * G;
+    if (p0 + pp >= HW) continue;
+    const float4 a = make_float4(tile[g * 8 + 0][pp], tile[g * 8 + 1][pp], tile[g * 8 + 2][pp], tile[g * 8 + 3][pp]);
+    const float4 b = make_float4(tile[g * 8 + 4][pp], tile[g * 8 + 5][pp], tile[g * 8 + 6][pp], tile[g * 8 + 7][pp]);
+    uint2 ha, la, hb, lb;
+    if (fmt) { split_f16x4(a, ha, la); split_f16x4(b, hb, lb); }
+    else { split_bf16x4(a, ha, la); split_bf16x4(b, hb, lb); }
+    const size_t o = ((size_t)n * HW + p0 + pp) * Cp + g * 8;
+    *reinterpret_cast<uint4*>(hi + o) = make_uint4(ha.x, ha.y, hb.x, hb.y);
+    if (lo) *reinterpret_cast<uint4*>(lo + o) = make_uint4(la.x, la.y, lb.x, lb.y);
+  }
+  if (xb) {
+    const int Gx = Cp_xb >> 3;
+    for (int i = threadIdx.x; i < 128 * Gx; i += 256) {
+      const int pp = i / Gx, g = i - pp * Gx;
+      if (p0 + pp >= HW) continue;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (g * 8 < C) {
+        const uint2 u0 = pack_bf16x4(make_float4(tile[g * 8 + 0][pp], tile[g * 8 + 1][pp], tile[g * 8 + 2][pp], tile[g * 8 + 3][pp]));
+        const uint2 u1 = pack_bf16x4(make_float4(tile[g * 8 + 4][pp], tile[g * 8 + 5][pp], tile[g * 8 + 6][pp], tile[g * 8 + 7][pp]));
+        v = make_uint4(u0.x, u0.y, u1.x, u1.y);
+      }
+      *reinterpret_cast<uint4*>(xb + ((size_t)n * HW + p0 + pp) * Cp_xb + g * 8) = v;
+    }
+  }
+}
+
 // hi/lo (or f32): [N][HW][Cs] (channel stride Cs >= C)  ->  out: [N][C][HW] fp32
 __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
                                     const float* __restrict__ f32, int C, int HW, int Cs, int fmt, float* __restrict__ out) {
@@ -212,6 +256,13 @@ extern "C" int egaze_nchw_to_nhwc_split(const float* x, int N, int C, int H, int
                                         int Cp_xb, int fmt, void* stream) {
   EGAZE_CHECK_ARG(x && hi && Cp >= C && (!xb || Cp_xb >= C), "nchw_to_nhwc_split: bad args");
   const int HW = H * W;
+  if (C <= 32 && Cp <= 32 && Cp % 8 == 0 && (!xb || Cp_xb % 8 == 0) && N <= 65535) {
+    dim3 grid(ceil_div(HW, 128), N);
+    nchw_to_nhwc_split_small_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, C, HW, Cp, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo,
+                                                                           (__nv_bfloat16*)xb, Cp_xb, fmt);
+    EGAZE_LAUNCH_CHECK();
+    return EGAZE_OK;
+  }
   const int cmax = (xb && Cp_xb > Cp) ? Cp_xb : Cp;
   dim3 grid(ceil_div(HW, 32), ceil_div(cmax, 32), N), block(32, 8);
   nchw_to_nhwc_split_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, C, HW, Cp, (__nv_bfloat16*)hi,

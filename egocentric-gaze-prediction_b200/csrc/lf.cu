@@ -27,7 +27,7 @@
 extern "C" int egaze_bn_finalize(const float* partial, const float* cnt, int cnt_stride, int cnt_div, int T, int C, float eps,
                                  float momentum, const float* gamma, const float* beta, float* running_mean,
                                  float* running_var, float* mean_out, float* invstd_out, float* scale_out, float* shift_out,
-                                 void* stream);
+                                 long long* num_batches_tracked, void* stream);
 extern "C" int egaze_bn_fold(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                              const float* conv_bias, float eps, int C, float* scale, float* shift, void* stream);
 
@@ -704,7 +704,7 @@ extern "C" int egaze_lf_fwd(const float* f, const float* g, int B, int H, int W,
     if (training)
       return egaze_bn_finalize(partial, cnt, 1, C, grid, C, eps, momentum, gamma[layer], beta[layer],
                                run_mean ? run_mean[layer] : nullptr, run_var ? run_var[layer] : nullptr, ws(layer, 0),
-                               ws(layer, 1), ws(layer, 2), ws(layer, 3), stream);
+                               ws(layer, 1), ws(layer, 2), ws(layer, 3), nullptr, stream);
     lf_eval_stats_kernel<<<1, 32, 0, st>>>(run_mean[layer], run_var[layer], eps, C, ws(layer, 0), ws(layer, 1));
     return egaze_bn_fold(gamma[layer], beta[layer], run_mean[layer], run_var[layer], nullptr, eps, C, ws(layer, 2), ws(layer, 3),
                          stream);

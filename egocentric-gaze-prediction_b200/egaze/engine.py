@@ -70,6 +70,12 @@ def parse_sequential(seq):
     return specs, tail
 
 
+def _nbt(bn):
+    """nn.BatchNorm2d.num_batches_tracked (int64 device scalar) when the layer tracks it: bn_finalize bumps it in its own launch."""
+    t = bn.num_batches_tracked if bn.track_running_stats else None
+    return t if (t is not None and t.is_cuda and t.dtype == torch.int64) else None
+
+
 def _bn_uses_batch_stats(bn):
     return bn.training or (bn.running_mean is None and bn.running_var is None)
 
@@ -132,13 +138,11 @@ def run_conv_spec(act, spec, saved=None, xb=False):
     if cout_p != C and rm is not None:
         rm_p = torch.cat([rm, rm.new_zeros(cout_p - C)])
         rv_p = torch.cat([rv, rv.new_ones(cout_p - C)])
-        mean, invstd, scale, shift = ops.bn_finalize(st, cout_p, bn.eps, bn.momentum, gamma, beta, rm_p, rv_p)
+        mean, invstd, scale, shift = ops.bn_finalize(st, cout_p, bn.eps, bn.momentum, gamma, beta, rm_p, rv_p, _nbt(bn))
         rm.copy_(rm_p[:C])
         rv.copy_(rv_p[:C])
     else:
-        mean, invstd, scale, shift = ops.bn_finalize(st, cout_p, bn.eps, bn.momentum, gamma, beta, rm, rv)
-    if bn.track_running_stats and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked.add_(1)
+        mean, invstd, scale, shift = ops.bn_finalize(st, cout_p, bn.eps, bn.momentum, gamma, beta, rm, rv, _nbt(bn))
     out, _ = ops.bn_apply(raw, scale, shift, relu=spec.relu, pool=spec.pool, xb=xb)
     if saved is not None:
         saved.append({"x": act, "raw": raw, "mean": mean, "invstd": invstd, "scale": scale, "shift": shift, "y": out})
@@ -193,9 +197,7 @@ def run_sp_tail(model, a_s, a_t, saved=None):
         st = ops.col_stats(mx.view(-1, C))
         rm = bn.running_mean if bn.track_running_stats else None
         rv = bn.running_var if bn.track_running_stats else None
-        mean, invstd, scale, shift = ops.bn_finalize(st, C, bn.eps, bn.momentum, gamma, beta, rm, rv)
-        if bn.track_running_stats and bn.num_batches_tracked is not None:
-            bn.num_batches_tracked.add_(1)
+        mean, invstd, scale, shift = ops.bn_finalize(st, C, bn.eps, bn.momentum, gamma, beta, rm, rv, _nbt(bn))
         rec.update(mean=mean, invstd=invstd)
     else:
         scale, shift = ops.bn_fold(gamma, beta, bn.running_mean, bn.running_var, None, bn.eps)

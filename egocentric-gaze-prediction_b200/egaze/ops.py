@@ -332,6 +332,7 @@ def conv_tiles(N, H, W, need_even=False):
 
 
 _stats_shape_cache = {}
+_stats_ws = {}
 
 
 def conv_stats_shape(Cout, precise):
@@ -407,8 +408,15 @@ def conv3x3(act, wpack, bias=None, scale=None, shift=None, relu=False, reduce=0,
     out_f32 = torch.empty((No, Ho, Wo, Cout), dtype=F32, device=dev) if want_f32 else None
     st = None
     if stats:
+        # Statistics workspace: persistent per (call shape, stream).  bn_finalize consumes it right after the conv on the same
+        # stream, and the kernel rewrites the count of every CTA it launches -- the same CTAs for the same shape -- so the slots
+        # of CTAs that never run stay at the zero they were allocated with: no fill launch per layer and step.
         parts, cs, cd = conv_stats_shape(Cout, use_wlo)
-        st = (torch.empty((parts, 2, Cout), dtype=F32, device=dev), torch.zeros((parts, cs), dtype=F32, device=dev), cs, cd)
+        key = (N, H, W, Cin_p, Cout, bool(use_wlo), x_lo is not None, dev, _lib.stream_key(dev))
+        ws = _stats_ws.get(key)
+        if ws is None:
+            ws = _stats_ws[key] = (torch.empty((parts, 2, Cout), dtype=F32, device=dev), torch.zeros((parts, cs), dtype=F32, device=dev))
+        st = (ws[0], ws[1], cs, cd)
     if _conv_timer["on"]:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
@@ -429,8 +437,8 @@ def conv3x3(act, wpack, bias=None, scale=None, shift=None, relu=False, reduce=0,
     return out_act, out_f32, st
 
 
-def bn_finalize(st, C, eps, momentum, gamma, beta, running_mean, running_var):
-    """-> (mean, invstd, scale, shift); updates running stats in place when given."""
+def bn_finalize(st, C, eps, momentum, gamma, beta, running_mean, running_var, num_batches_tracked=None):
+    """-> (mean, invstd, scale, shift); updates running stats (and the int64 num_batches_tracked counter) in place when given."""
     partial, cnt, cnt_stride, cnt_div = st
     dev = partial.device
     mean = torch.empty((C,), dtype=F32, device=dev)
@@ -438,7 +446,7 @@ def bn_finalize(st, C, eps, momentum, gamma, beta, running_mean, running_var):
     scale = torch.empty((C,), dtype=F32, device=dev)
     shift = torch.empty((C,), dtype=F32, device=dev)
     call("egaze_bn_finalize", partial, cnt, cnt_stride, cnt_div, partial.shape[0], C, float(eps), float(momentum), gamma, beta, running_mean,
-         running_var, mean, invstd, scale, shift, stream_ptr())
+         running_var, mean, invstd, scale, shift, num_batches_tracked, stream_ptr())
     return mean, invstd, scale, shift
 
 
@@ -586,13 +594,14 @@ def col_sum(act, C=None):
     return out if C is None or C == act.Cp else out[:C].contiguous()
 
 
-def head_bwd(act, w, y, gy, relu_mask=True):
-    """Backward of sigmoid(conv1x1(act)).  -> (dx Act, dw [C], db [1])"""
+def head_bwd(act, w, y, gy, relu_mask=True, zeros=None):
+    """Backward of sigmoid(conv1x1(act)).  -> (dx Act, dw [C], db [1]).  zeros(n, device): optional source of zero-initialised
+    fp32 vectors (the backward's pool, egaze.autograd._GradBag)."""
     dev = act.hi.device
     dx = empty_act(act.N, act.H, act.W, act.Cp, act.C, dev, lo=mode()["dy_lo"])
     wf = w.detach().reshape(-1).contiguous().float()
-    dw = torch.zeros((wf.numel(),), dtype=F32, device=dev)
-    db = torch.zeros((1,), dtype=F32, device=dev)
+    dw = zeros(wf.numel(), dev) if zeros is not None else torch.zeros((wf.numel(),), dtype=F32, device=dev)
+    db = zeros(1, dev) if zeros is not None else torch.zeros((1,), dtype=F32, device=dev)
     call("egaze_head_bwd", act.hi, act.lo, act.fmt, wf, wf.numel(), act.Cp, act.N * act.H * act.W, y.contiguous(),
          gy.contiguous().float(), int(relu_mask), dx.hi, dx.lo, dw, db, stream_ptr())
     return dx, dw, db

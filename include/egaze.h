@@ -112,10 +112,11 @@ int egaze_wgrad3x3_tc(const void* x_hi, const void* x_lo, const void* dy_hi, con
                       int Cin_p, int Cout, float* dwp, int precise, int sub, void* stream);
 
 /* ---- BatchNorm2d pieces (utils.py:72, model_SP.py:12, late_fusion.py:10-12) ---------------------------------- */
-/* partial [T][2][C] (mean, M2); count behind (t, c) = cnt[t*cnt_stride + c/cnt_div] */
+/* partial [T][2][C] (mean, M2); count behind (t, c) = cnt[t*cnt_stride + c/cnt_div].  num_batches_tracked (optional, device
+ * int64 scalar): incremented by one, like nn.BatchNorm2d's forward in training mode. */
 int egaze_bn_finalize(const float* partial, const float* cnt, int cnt_stride, int cnt_div, int T, int C, float eps,
                       float momentum, const float* gamma, const float* beta, float* running_mean, float* running_var, float* mean_out,
-                      float* invstd_out, float* scale_out, float* shift_out, void* stream);
+                      float* invstd_out, float* scale_out, float* shift_out, long long* num_batches_tracked, void* stream);
 int egaze_bn_fold(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                   const float* conv_bias, float eps, int C, float* scale, float* shift, void* stream);
 /* x [rows][C] fp32 -> partial [ceil(rows/128)][2][C], cnt [ceil(rows/128)] */

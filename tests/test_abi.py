@@ -31,7 +31,7 @@ def test_error_convention(built):
     from egaze import _lib
     h = _lib.lib()
     # invalid argument -> negative rc + message; no exception crosses the ABI, nothing launched
-    rc = h.egaze_bn_finalize(None, None, 1, 1, 0, 0, 1e-5, 0.1, None, None, None, None, None, None, None, None, None)
+    rc = h.egaze_bn_finalize(None, None, 1, 1, 0, 0, 1e-5, 0.1, None, None, None, None, None, None, None, None, None, None)
     assert rc < 0
     assert "bn_finalize" in _lib.last_error()
 
