@@ -12,6 +12,10 @@
 namespace {
 
 // partial: [T][2][C] (mean, M2), cnt: [T].  One thread column per channel, 32 slices of tiles per block.
+// The kernel sits on the critical path of every train-mode layer (conv -> finalize -> apply) and is pure latency: a thread
+// first loads ALL of its partials (its first kFinPer -- all of them for one partial per SM -- independent loads, one round trip to L2) and only then
+// runs the two Chan passes on registers; the num_batches_tracked bump rides along.
+constexpr int kFinPer = 5;   // partials a thread keeps in registers (32 slices x 5 = 160 >= one partial per SM)
 __global__ void __launch_bounds__(1024)
 bn_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ cnt, int cnt_stride, int cnt_div,
                    int T, int C, float eps,
@@ -24,12 +28,28 @@ bn_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ 
   __shared__ double s_n[32][33], s_a[32][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   const int sl = threadIdx.y;
+  const bool single = T <= 32 * kFinPer;   // every partial of this thread fits its registers: one load round
+  float fn[kFinPer], fm[kFinPer], fq[kFinPer];
+#pragma unroll
+  for (int i = 0; i < kFinPer; ++i) {
+    const int t = sl + 32 * i;
+    const bool ok = c < C && t < T;
+    fn[i] = ok ? cnt[(size_t)t * cnt_stride + c / cnt_div] : 0.f;
+    fm[i] = ok ? partial[((size_t)t * 2 + 0) * C + c] : 0.f;
+    fq[i] = ok ? partial[((size_t)t * 2 + 1) * C + c] : 0.f;
+  }
   // pass 1: N = sum n_t, S = sum n_t * mean_t  (no divisions in the loop)
   double n = 0.0, sm = 0.0;
-  if (c < C)
-    for (int t = sl; t < T; t += 32) {
+#pragma unroll
+  for (int i = 0; i < kFinPer; ++i)
+    if (fn[i] > 0.f) {   // unused partial slot: its (mean, M2) are uninitialised
+      n += (double)fn[i];
+      sm = fma((double)fn[i], (double)fm[i], sm);
+    }
+  if (!single && c < C)
+    for (int t = sl + 32 * kFinPer; t < T; t += 32) {
       const double nb = (double)cnt[(size_t)t * cnt_stride + c / cnt_div];
-      if (nb <= 0.0) continue;   // unused partial slot: its (mean, M2) are uninitialised
+      if (nb <= 0.0) continue;
       n += nb;
       sm = fma(nb, (double)partial[((size_t)t * 2 + 0) * C + c], sm);
     }
@@ -42,8 +62,14 @@ bn_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ 
   __syncthreads();
   // pass 2: M2 = sum ( M2_t + n_t * (mean_t - mean)^2 )
   double m2 = 0.0;
-  if (c < C)
-    for (int t = sl; t < T; t += 32) {
+#pragma unroll
+  for (int i = 0; i < kFinPer; ++i)
+    if (fn[i] > 0.f) {
+      const double d = (double)fm[i] - mean;
+      m2 += (double)fq[i] + (double)fn[i] * d * d;
+    }
+  if (!single && c < C)
+    for (int t = sl + 32 * kFinPer; t < T; t += 32) {
       const double nb = (double)cnt[(size_t)t * cnt_stride + c / cnt_div];
       if (nb <= 0.0) continue;
       const double d = (double)partial[((size_t)t * 2 + 0) * C + c] - mean;
@@ -212,11 +238,12 @@ __device__ __forceinline__ void bn_route(const float* __restrict__ src, size_t r
   }
 }
 
-// partial[blk][0][c] = sum gz ; partial[blk][1][c] = sum gz*xhat     blockDim = (C/4, rows)
+// acc[slot][0][c] += sum gz ; acc[slot][1][c] += sum gz*xhat (slot = block % kBwdSlots)     blockDim = (C/4, rows)
+constexpr int kBwdSlots = 8;
 __global__ void bn_bwd_reduce_kernel(const float* __restrict__ raw, const float* __restrict__ g, int N, int H, int W,
                                      int C, const float* __restrict__ scale, const float* __restrict__ shift,
                                      const float* __restrict__ mean, const float* __restrict__ invstd, int pool, int relu,
-                                     float* __restrict__ partial) {
+                                     double* __restrict__ acc) {
   extern __shared__ float red[];  // [rows][2][C]
   const int Ho = pool ? H / 2 : H, Wo = pool ? W / 2 : W;
   const int c4 = threadIdx.x;
@@ -251,34 +278,33 @@ __global__ void bn_bwd_reduce_kernel(const float* __restrict__ raw, const float*
 #pragma unroll
   for (int l = 0; l < 4; ++l) { my[c4 * 4 + l] = s1[l]; my[C + c4 * 4 + l] = s2[l]; }
   __syncthreads();
+  // block sums -> one of kBwdSlots fp64 accumulators per channel (native double atomics; ~150 adds per address and launch)
+  double* slot = acc + (size_t)(blockIdx.x % kBwdSlots) * 2 * C;
   for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < 2 * C; i += blockDim.x * blockDim.y) {
     float v = 0.f;
     for (int r = 0; r < (int)blockDim.y; ++r) v += red[(size_t)r * 2 * C + i];
-    partial[(size_t)blockIdx.x * 2 * C + i] = v;
+    atomicAdd(slot + i, (double)v);
   }
 }
 
-// dgamma[c] = sum_blk partial[blk][1][c]; dbeta[c] = sum_blk partial[blk][0][c]   (fp64 accumulation)
-__global__ void __launch_bounds__(1024)
-bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, float* __restrict__ dgamma,
-                       float* __restrict__ dbeta) {
-  __shared__ double s_a[32][33], s_b[32][33];
-  const int c = blockIdx.x * 32 + threadIdx.x;
-  double a = 0.0, b = 0.0;
-  if (c < C)
-    for (int i = threadIdx.y; i < nblk; i += 32) {
-      b += (double)partial[(size_t)i * 2 * C + c];
-      a += (double)partial[(size_t)i * 2 * C + C + c];
-    }
-  s_a[threadIdx.y][threadIdx.x] = a;
-  s_b[threadIdx.y][threadIdx.x] = b;
-  __syncthreads();
-  if (threadIdx.y == 0 && c < C) {
-    a = 0.0; b = 0.0;
-    for (int i = 0; i < 32; ++i) { a += s_a[i][threadIdx.x]; b += s_b[i][threadIdx.x]; }
-    dgamma[c] = (float)a;
-    dbeta[c] = (float)b;
+// dgamma[c] = sum_slot acc[slot][1][c]; dbeta[c] = sum_slot acc[slot][0][c]; the accumulators are left ZEROED for the next launch
+// (the workspace is persistent: no fill kernel per layer).  A few microseconds on the critical path of every layer's backward:
+// 8 loads per thread instead of the 1,184 per-block partials of the first version.
+__global__ void __launch_bounds__(256)
+bn_bwd_finalize_kernel(double* __restrict__ acc, int C, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // over [2][C]
+  if (i >= 2 * C) return;
+  double v[kBwdSlots];
+#pragma unroll
+  for (int sl = 0; sl < kBwdSlots; ++sl) v[sl] = acc[(size_t)sl * 2 * C + i];
+  double t = 0.0;
+#pragma unroll
+  for (int sl = 0; sl < kBwdSlots; ++sl) {
+    t += v[sl];
+    acc[(size_t)sl * 2 * C + i] = 0.0;
   }
+  if (i < C) dbeta[i] = (float)t;
+  else dgamma[i - C] = (float)t;
 }
 
 // draw = gamma*invstd * (gz - dbeta/n - xhat*dgamma/n)  -> NHWC split-bf16 (and/or fp32) at the conv-output resolution.
@@ -452,9 +478,10 @@ static void bn_bwd_block(int C, dim3* block) {
   *block = dim3(C / 4, rows);
 }
 
-// partial: [nblk][2][C] with nblk = egaze_bn_bwd_blocks(); dgamma/dbeta: [C]
+// partial: persistent workspace of egaze_bn_bwd_blocks() * 2 * C floats (8-byte aligned), ZERO before the first call that uses
+// it; every call leaves it zeroed again.  dgamma/dbeta: [C]
 extern "C" int egaze_bn_bwd_blocks(int* nblk) {
-  *nblk = 148 * 8;
+  *nblk = 2 * kBwdSlots;   // kBwdSlots fp64 accumulators per channel and sum
   return EGAZE_OK;
 }
 
@@ -463,14 +490,16 @@ extern "C" int egaze_bn_bwd_reduce(const float* raw, const float* g, int N, int 
                                    float* partial, float* dgamma, float* dbeta, void* stream) {
   EGAZE_CHECK_ARG(raw && g && scale && shift && mean && invstd && partial && dgamma && dbeta, "bn_bwd_reduce: null");
   EGAZE_CHECK_ARG(C % 4 == 0 && C <= 4096, "bn_bwd_reduce: unsupported C=%d", C);
+  EGAZE_CHECK_ARG((reinterpret_cast<uintptr_t>(partial) & 7) == 0, "bn_bwd_reduce: workspace must be 8-byte aligned");
   dim3 block;
   bn_bwd_block(C, &block);
   const int nblk = 148 * 8;
   const size_t smem = (size_t)block.y * 2 * C * sizeof(float);
+  double* acc = reinterpret_cast<double*>(partial);
   bn_bwd_reduce_kernel<<<nblk, block, smem, (cudaStream_t)stream>>>(raw, g, N, H, W, C, scale, shift, mean, invstd, pool,
-                                                                    relu, partial);
+                                                                    relu, acc);
   EGAZE_LAUNCH_CHECK();
-  bn_bwd_finalize_kernel<<<ceil_div(C, 32), dim3(32, 32), 0, (cudaStream_t)stream>>>(partial, nblk, C, dgamma, dbeta);
+  bn_bwd_finalize_kernel<<<ceil_div(2 * C, 256), 256, 0, (cudaStream_t)stream>>>(acc, C, dgamma, dbeta);
   EGAZE_LAUNCH_CHECK();
   return EGAZE_OK;
 }

@@ -554,6 +554,7 @@ def wgrad3x3(x_act, dy_act, Cout, Cin, precise=None, sub=False):
 
 _dwp_cache = {}
 _bn_bwd_nblk = [None]
+_bn_bwd_ws = {}
 
 
 def bn_bwd(raw, g, scale, shift, mean, invstd, pool, relu, want_f32=False, want_split=True, batch_stats=True):
@@ -566,7 +567,11 @@ def bn_bwd(raw, g, scale, shift, mean, invstd, pool, relu, want_f32=False, want_
         nb = ctypes.c_int(0)
         call("egaze_bn_bwd_blocks", ctypes.addressof(nb))
         _bn_bwd_nblk[0] = nb.value
-    partial = torch.empty((_bn_bwd_nblk[0], 2, C), dtype=F32, device=dev)
+    # persistent, self-cleaning accumulators (zero at allocation, re-zeroed by every call): one per (C, device, stream)
+    key = (C, dev, _lib.stream_key(dev))
+    partial = _bn_bwd_ws.get(key)
+    if partial is None:
+        partial = _bn_bwd_ws[key] = torch.zeros((_bn_bwd_nblk[0], 2, C), dtype=F32, device=dev)
     dgamma = torch.empty((C,), dtype=F32, device=dev)
     dbeta = torch.empty((C,), dtype=F32, device=dev)
     g = g.contiguous()

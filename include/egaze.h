@@ -127,6 +127,8 @@ int egaze_bn_apply(const float* x, int N, int H, int W, int C, const float* scal
 /* out[b] = max(x[b], x[b+B]) : Conv3d(1,3,3)+MaxPool3d((2,1,1)) second half (model_SP.py:11,43) */
 int egaze_pairmax(const float* x, long long per_stream, float* out, void* stream);
 /* backward pieces (autograd of the modules above; loss.backward() in SP.py:136, LF.py:98, spatialstream.py:140) */
+/* partial: a PERSISTENT workspace of egaze_bn_bwd_blocks() * 2 * C floats, 8-byte aligned and zero before its first use; every
+ * call leaves it zeroed again (fp64 accumulators, cleared by the call's own finalize kernel) */
 int egaze_bn_bwd_blocks(int* nblk);
 int egaze_bn_bwd_reduce(const float* raw, const float* g, int N, int H, int W, int C, const float* scale,
                         const float* shift, const float* mean, const float* invstd, int pool, int relu, float* partial,
