@@ -203,10 +203,12 @@ struct BnSrc {
 };
 
 // src: the (top-left) source pixel's channel group; row_pitch: floats between image rows of raw.
-__device__ __forceinline__ void bn_route(const float* __restrict__ src, size_t row_pitch, int C, int pool, int relu,
+template <int POOL>
+__device__ __forceinline__ void bn_route(const float* __restrict__ src, size_t row_pitch, int C, int relu,
                                          const float4& g, const float4& sc, const float4& sh, const float4& mean,
                                          const float4& invstd, BnSrc& o) {
-  const int np = pool ? 4 : 1;
+  constexpr int pool = POOL;
+  constexpr int np = POOL ? 4 : 1;
   float z[4][4];
   const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
   const float mv[4] = {mean.x, mean.y, mean.z, mean.w}, iv[4] = {invstd.x, invstd.y, invstd.z, invstd.w};
@@ -240,10 +242,15 @@ __device__ __forceinline__ void bn_route(const float* __restrict__ src, size_t r
 
 // acc[slot][0][c] += sum gz ; acc[slot][1][c] += sum gz*xhat (slot = block % kBwdSlots)     blockDim = (C/4, rows)
 constexpr int kBwdSlots = 8;
-__global__ void bn_bwd_reduce_kernel(const float* __restrict__ raw, const float* __restrict__ g, int N, int H, int W,
+// (POOL is a template parameter: the generic form kept 4 source pixels' worth of state live -- 79 registers, three blocks per SM --
+//  also for the eight un-pooled layers of a trunk, which need a quarter of it: 46-48 registers, five blocks per SM)
+template <int POOL>
+__global__ void __launch_bounds__(256, POOL ? 3 : 5)
+bn_bwd_reduce_kernel(const float* __restrict__ raw, const float* __restrict__ g, int N, int H, int W,
                                      int C, const float* __restrict__ scale, const float* __restrict__ shift,
-                                     const float* __restrict__ mean, const float* __restrict__ invstd, int pool, int relu,
+                                     const float* __restrict__ mean, const float* __restrict__ invstd, int relu,
                                      double* __restrict__ acc) {
+  constexpr int pool = POOL;
   extern __shared__ float red[];  // [rows][2][C]
   const int Ho = pool ? H / 2 : H, Wo = pool ? W / 2 : W;
   const int c4 = threadIdx.x;
@@ -262,8 +269,8 @@ __global__ void bn_bwd_reduce_kernel(const float* __restrict__ raw, const float*
     }
     const float4 gg = *reinterpret_cast<const float4*>(g + (size_t)pix * C + c4 * 4);
     BnSrc o;
-    bn_route(src, row_pitch, C, pool, relu, gg, sc, sh, mn, iv, o);
-    const int np = pool ? 4 : 1;
+    bn_route<POOL>(src, row_pitch, C, relu, gg, sc, sh, mn, iv, o);
+    constexpr int np = POOL ? 4 : 1;
 #pragma unroll
     for (int q = 0; q < 4; ++q)
       if (q < np) {
@@ -309,13 +316,15 @@ bn_bwd_finalize_kernel(double* __restrict__ acc, int C, float* __restrict__ dgam
 
 // draw = gamma*invstd * (gz - dbeta/n - xhat*dgamma/n)  -> NHWC split-bf16 (and/or fp32) at the conv-output resolution.
 // Same thread mapping as bn_apply_kernel: one float4 channel group per thread, its six per-channel constants in registers.
-__global__ void __launch_bounds__(256)
+template <int POOL>
+__global__ void __launch_bounds__(256, POOL ? 3 : 5)
 bn_bwd_apply_kernel(const float* __restrict__ raw, const float* __restrict__ g, int N, int H, int W, int C,
                     const float* __restrict__ scale, const float* __restrict__ shift,
                     const float* __restrict__ mean, const float* __restrict__ invstd,
-                    const float* __restrict__ dgamma, const float* __restrict__ dbeta, int pool, int relu, int batch_stats,
+                    const float* __restrict__ dgamma, const float* __restrict__ dbeta, int relu, int batch_stats,
                     float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_hi,
                     __nv_bfloat16* __restrict__ out_lo) {
+  constexpr int pool = POOL;
   const int Ho = pool ? H / 2 : H, Wo = pool ? W / 2 : W;
   const int C4 = C / 4;
   const int tpp = C4 < 256 ? C4 : 256;
@@ -326,7 +335,7 @@ bn_bwd_apply_kernel(const float* __restrict__ raw, const float* __restrict__ g, 
   const float inv_n = batch_stats ? 1.f / (float)((size_t)N * H * W) : 0.f;
   const uint32_t npix = (uint32_t)N * Ho * Wo;
   const size_t row_pitch = (size_t)W * C;
-  const int np = pool ? 4 : 1;
+  constexpr int np = POOL ? 4 : 1;
   for (int c4 = lane_c; c4 < C4; c4 += tpp) {
     const float4 sc = *reinterpret_cast<const float4*>(scale + c4 * 4), sh = *reinterpret_cast<const float4*>(shift + c4 * 4);
     const float4 mn = *reinterpret_cast<const float4*>(mean + c4 * 4), iv = *reinterpret_cast<const float4*>(invstd + c4 * 4);
@@ -345,7 +354,7 @@ bn_bwd_apply_kernel(const float* __restrict__ raw, const float* __restrict__ g, 
       }
       const float4 gg = *reinterpret_cast<const float4*>(g + (size_t)pix * C + c4 * 4);
       BnSrc o;
-      bn_route(raw + off0, row_pitch, C, pool, relu, gg, sc, sh, mn, iv, o);
+      bn_route<POOL>(raw + off0, row_pitch, C, relu, gg, sc, sh, mn, iv, o);
 #pragma unroll
       for (int q = 0; q < 4; ++q)
         if (q < np) {
@@ -496,8 +505,8 @@ extern "C" int egaze_bn_bwd_reduce(const float* raw, const float* g, int N, int 
   const int nblk = 148 * 8;
   const size_t smem = (size_t)block.y * 2 * C * sizeof(float);
   double* acc = reinterpret_cast<double*>(partial);
-  bn_bwd_reduce_kernel<<<nblk, block, smem, (cudaStream_t)stream>>>(raw, g, N, H, W, C, scale, shift, mean, invstd, pool,
-                                                                    relu, acc);
+  if (pool) bn_bwd_reduce_kernel<1><<<nblk, block, smem, (cudaStream_t)stream>>>(raw, g, N, H, W, C, scale, shift, mean, invstd, relu, acc);
+  else bn_bwd_reduce_kernel<0><<<nblk, block, smem, (cudaStream_t)stream>>>(raw, g, N, H, W, C, scale, shift, mean, invstd, relu, acc);
   EGAZE_LAUNCH_CHECK();
   bn_bwd_finalize_kernel<<<ceil_div(2 * C, 256), 256, 0, (cudaStream_t)stream>>>(acc, C, dgamma, dbeta);
   EGAZE_LAUNCH_CHECK();
@@ -513,9 +522,12 @@ extern "C" int egaze_bn_bwd_apply(const float* raw, const float* g, int N, int H
   const size_t total = (size_t)N * Ho * Wo * (C / 4);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  bn_bwd_apply_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(raw, g, N, H, W, C, scale, shift, mean, invstd, dgamma,
-                                                               dbeta, pool, relu, batch_stats, out_f32, (__nv_bfloat16*)out_hi,
-                                                               (__nv_bfloat16*)out_lo);
+  if (pool)
+    bn_bwd_apply_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(raw, g, N, H, W, C, scale, shift, mean, invstd, dgamma, dbeta, relu,
+                                                                    batch_stats, out_f32, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo);
+  else
+    bn_bwd_apply_kernel<0><<<blocks, 256, 0, (cudaStream_t)stream>>>(raw, g, N, H, W, C, scale, shift, mean, invstd, dgamma, dbeta, relu,
+                                                                    batch_stats, out_f32, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo);
   EGAZE_LAUNCH_CHECK();
   return EGAZE_OK;
 }

@@ -12,7 +12,8 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(os.path.dirname(_HERE))
-LIB_PATH = os.path.join(_HERE, "libegaze.so")
+# EGAZE_LIB: another build of the same ABI (A/B measurements of kernel variants inside one GPU session, tools/gpu_ab_lib.sh)
+LIB_PATH = os.environ.get("EGAZE_LIB") or os.path.join(_HERE, "libegaze.so")
 HEADER_PATH = os.path.join(_ROOT, "include", "egaze.h")
 
 _SCALARS = {"int": ctypes.c_int, "long long": ctypes.c_longlong, "float": ctypes.c_float, "double": ctypes.c_double}
