@@ -652,10 +652,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
       const uint32_t r_step16 = (uint32_t)(AW * row_bytes) >> 4;   // one tile row down inside the window
       const uint32_t s_step16 = (uint32_t)row_bytes >> 4;          // one pixel to the right (window mode)
       const int acc_mode = NSPLIT == 2 ? p.acc_mode : 0;
-      const bool lean = pair && NSPLIT == 2 && p.win && !p.probe;
+      const bool lean = pair && NSPLIT == 2 && !p.probe;
       const uint32_t bn = (uint32_t)p.BN;
       if (lean) {
-        // Lean issuer (window mode on a CTA pair): ONE lane runs the whole pipeline.  What bounds this warp is the latency of
+        // Lean issuer (CTA pairs): ONE lane runs the whole pipeline.  What bounds this warp is the latency of
         // its own scalar instruction stream (and fetching it: the SMSP's ~6 KB L0 instruction cache is shared with two epilogue
         // warps; ncu shows `no_instruction` as the top stall): with all work ablated the generic loop below still needed
         // ~560 cycles per tap (-DEGAZE_CONV_PROF, EGAZE_CONV_ABLATE=15) against 256-384 cycles of MMAs per tap in the 64-channel
@@ -670,7 +670,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
           const uint32_t a_ring_lo = (uint32_t)a_ring_desc, a_hi = (uint32_t)(a_ring_desc >> 32);
           const uint32_t b_ring_lo = (uint32_t)b_ring_desc, b_hi = (uint32_t)(b_ring_desc >> 32);
           const int SA = p.SA, SB = p.SB, sub = p.sub, wstat = p.wstat, n_items = p.num_items;
-          const int no = sub ? 2 : 3, ni = no;
+          // classic mode (one window per horizontal tap): its three vertical taps are one row of the walk
+          const int no = !p.win ? 1 : (sub ? 2 : 3), ni = sub ? 2 : 3;
           // strides in 16-byte units; "negative" steps as two's complement (only the low 14 bits of the field matter)
           const uint32_t so = sub == 0 ? s_step16 : (sub == 1 ? r_step16 : 0u - r_step16);
           const uint32_t si = sub == 0 ? r_step16 : (sub == 1 ? s_step16 : 0u - s_step16);
