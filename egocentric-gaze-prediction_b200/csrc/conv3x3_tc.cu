@@ -30,9 +30,12 @@
 //   multicast mode: every CTA keeps the full weight box; each loads 1/CS of it and TMA-multicasts it to its peers.
 // Two TMEM accumulator stages let the epilogue of item i overlap the MMAs of item i+1.
 //
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..9 = epilogue.  Producer
-// and issuer walk their loop nests with the WHOLE warp (uniform control flow keeps descriptors in uniform registers) and
-// one elected lane issues; the next slot's barrier query is fused into the MMA asm block.  The epilogue stages the
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..9 = epilogue.  The producer
+// walks its loop nest with the WHOLE warp (uniform control flow keeps box coordinates in uniform registers) and one elected
+// lane issues.  The issuer of a CTA pair is ONE lane running a lean loop (barriers by shared-window address, the taps of a
+// window as two descriptor strides, one asm block of MMAs per tap): what bounds that warp is the latency -- and the fetching
+// -- of its own scalar instruction stream, see the MMA warp below; the generic issuer (single CTAs, fast mode) keeps the
+// warp-uniform loop with the next slot's barrier query fused into the MMA asm block.  The epilogue stages the
 // accumulator tile through shared memory (64-column chunks) and drains it with compile-time-specialised store loops:
 // bias / folded-BN affine / ReLU, 2x2 max or sum, ReLU-backward mask, nearest-2x replicate, packed bf16 split, coalesced
 // NHWC stores -- with BatchNorm batch statistics (shifted sums) and bias-gradient column sums accumulated in the same pass.
