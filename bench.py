@@ -579,19 +579,31 @@ def run_reference(args):
     claim_stdout()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     threads = os.cpu_count() or 1
+    # The reference arm runs the workload's OWN batch (same config as the GPU arm) when the host has the memory for it (a batch-32
+    # two-stream train step keeps ~20 GB of activations in PyTorch-CPU), else the bounded batch (--ref-batch).  A batch-32 step
+    # takes ~7 s on the GPU box's 16 host threads: --steps / --warmup are honoured up to 5 / 1 there (10 / 2 for the small batch),
+    # so the whole arm stays within about a minute.
     B = args.ref_batch
-    # --steps / --warmup are honoured up to 10 / 2: each step is the bounded sample (batch 4 of the workload's 32 per GPU,
-    # under a second on the GPU box's host cores), so the whole arm stays within a minute
-    steps = max(1, min(args.steps, 10))
-    warmup = max(1, min(args.warmup, 2))
+    try:
+        import psutil
+        if args.ref_batch_auto and psutil.virtual_memory().available > 96 * 2 ** 30:
+            B = args.batch
+    except Exception:  # noqa: BLE001
+        pass
+    full = B == args.batch
+    steps = max(1, min(args.steps, 5 if full else 10))
+    warmup = max(1, min(args.warmup, 1 if full else 2))
     fps, dt, sample = cpu_reference_fps(args.workload, B, args.size, steps, warmup, threads)
     line = {"impl": "reference", "metric": metric_name(args.workload, args.batch, args.size), "value": fps, "unit": UNIT,
             "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": common_config(args, max(world, args.gpus)),
-            "detail": {"note": "reference CPU path (stock torch.nn modules, oneDNN) timed on ONE process on a bounded sample "
-                               "(%s) of the same workload" % sample},
+            "detail": {"note": ("reference CPU path (stock torch.nn modules, oneDNN) timed on ONE process on the same workload and "
+                                "batch (%s)" if full else
+                                "reference CPU path (stock torch.nn modules, oneDNN) timed on ONE process on a bounded sample "
+                                "(%s) of the same workload") % sample,
+                       "same_batch_as_gpu_arm": full},
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": "%s, %d step(s), torch %s CPU (oneDNN), %d threads" % (
                                  sample, steps, torch.__version__, threads)},
@@ -609,6 +621,8 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--size", type=int, default=224)
     ap.add_argument("--ref-batch", type=int, default=4)
+    ap.add_argument("--ref-batch-auto", type=int, default=1,
+                    help="--impl reference: 1 = time the workload's own batch when the host has > 96 GB of free memory")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dropin", action="store_true")
     args = ap.parse_args()

@@ -26,7 +26,7 @@ for S in [int(v) for v in args.sizes.split(",")]:
         row = {"size": S, "batch": B}
         for name in ("sp_fwd", "sp_train"):
             wl = bench.Workload(name, B, S, 0, 1, dev)
-            for _ in range(3):
+            for _ in range(8):      # new shapes: launch plans, allocator growth and the pack cache settle within a few steps
                 wl.step(*wl.dev)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
