@@ -32,6 +32,10 @@ struct WgradParams {
   int stacked;         // Cout == 64, precise: the M = 128 rows are [dY_hi ; dY_lo] of the same 64 channels, so ONE MMA against
                        // [X_hi | X_lo] yields all four hi/lo products (the epilogue adds the two lane halves into the same dW rows)
   int nsplit;
+  int pairs;           // Cout == 64, one plane: the M = 128 rows are [dY ; dY shifted by one pixel column], so ONE job yields two horizontal
+                       // taps (s and s + 1) against the same X window -- two jobs per (co, ci) tile instead of three (sub-pixel: one per phase
+                       // instead of two), dY and X are streamed a third (half) less often.  The paired job walks one extra tile column:
+                       // the shifted rows of tile column t cover pixels [w0 - 1, w0 + BW - 1), so pixel W - 1 needs the column at w0 = W.
   int sub;             // sub-pixel form (conv3x3_tc.cu ConvTcParams::sub): X is the low-resolution input, dY the phase-planar gradient
                        // [4N][H][W][Cout]; job = (co-tile, ci-tile, phase, horizontal tap b), the TWO vertical taps a share the dY tile
                        // (N = 128); dwp has 16 planes [phase*4 + a*2 + b]
@@ -49,9 +53,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   int job = blockIdx.y;
-  const int nj = p.sub ? 8 : 3;
-  const int s = job % nj;          // horizontal tap; sub-pixel: phase * 2 + b
+  const int nj = p.pairs ? (p.sub ? 4 : 2) : (p.sub ? 8 : 3);
+  int s = job % nj;                // horizontal tap; sub-pixel: phase * 2 + b
   job /= nj;
+  bool paired = false;             // this job's rows 64..127 hold dY shifted by one pixel column: tap s + 1 as well
+  if (p.pairs) {
+    if (p.sub) { s = s * 2; paired = true; }        // one job per phase: b = 0 and 1
+    else { paired = s == 0; s = s == 0 ? 0 : 2; }   // taps {0, 1} and {2}
+  }
+  const int tiles_w = paired ? (p.W + 1 + p.BW - 1) / p.BW : p.tiles_w;
+  const int total_tiles = p.N * p.tiles_h * tiles_w;
   const int phase = p.sub ? s >> 1 : 0, py = phase >> 1, px = phase & 1, hb = p.sub ? s & 1 : s;
   const int ntap_v = p.sub ? 2 : 3;
   const int ci_t = job % p.ci_tiles;
@@ -85,16 +96,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid_constan
   const int KP = p.BH * p.BW;                       // pixels (K) per tile, multiple of 16
   const uint32_t dy_box_bytes = (uint32_t)KP * 128u;
   const uint32_t x_box_bytes = (uint32_t)(p.BH + 2) * p.BW * 128u;
-  const uint32_t tx_bytes = NSPLIT * (p.m_chunks * dy_box_bytes + x_box_bytes);
+  const uint32_t tx_bytes = NSPLIT * ((p.m_chunks + (paired ? 1 : 0)) * dy_box_bytes + x_box_bytes);
 
   if (warp == 0) {
     if (lane == 0) {
       int st = 0;
       uint32_t par = 1;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const int tw_i = t % p.tiles_w;
-        const int th_i = (t / p.tiles_w) % p.tiles_h;
-        const int img = t / (p.tiles_w * p.tiles_h);
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int tw_i = t % tiles_w;
+        const int th_i = (t / tiles_w) % p.tiles_h;
+        const int img = t / (tiles_w * p.tiles_h);
         const int h0 = th_i * p.BH, w0 = tw_i * p.BW;
         ptx::mbar_wait(&empty[st], par);
         ptx::mbar_arrive_expect_tx(&full[st], tx_bytes);
@@ -106,6 +117,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid_constan
             ptx::tma_load_4d(base + (p.stacked ? dy_box_bytes : (uint32_t)p.dy_plane_bytes + c * dy_box_bytes), &tmY_lo, &full[st],
                              co0 + 64 * c, w0, h0, img_y);
         }
+        // paired job: the second 64-row chunk of A is the same dY tile one pixel column to the left (out-of-image columns are zeros)
+        if (paired) ptx::tma_load_4d(base + dy_box_bytes, &tmY_hi, &full[st], co0, w0 - 1, h0, img_y);
         uint8_t* xb = base + (size_t)NSPLIT * p.dy_plane_bytes;
         // window origin: 3x3 tap (r, s) reads X[h + r - 1, w + s - 1]; sub-pixel tap (a, b) of phase (py, px) reads
         // X[i + py + a - 1, j + px + b - 1]
@@ -129,7 +142,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid_constan
       int st = 0;
       uint32_t par = 0;
       uint32_t acc = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         ptx::mbar_wait(&full[st], par);
         ptx::tc_fence_after();
         const uint32_t base = ptx::smem_u32(smem + (size_t)st * p.stage_bytes);
@@ -171,7 +184,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid_constan
     const int m = ew * 32 + lane;
     ptx::mbar_wait(&acc_full, 0);
     ptx::tc_fence_after();
-    const bool any_tile = (int)blockIdx.x < p.total_tiles;
+    const bool any_tile = (int)blockIdx.x < total_tiles;
     for (int r = 0; r < ntap_v; ++r) {
 #pragma unroll 1
       for (int c0 = 0; c0 < 64; c0 += 32) {
@@ -186,9 +199,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid_constan
         } else {
           ptx::tmem_ld_wait();
         }
-        const int co = p.stacked ? (m & 63) : co0 + m;   // stacked: lanes 64..127 hold the dY_lo products of channels 0..63
-        if (any_tile && co < p.Cout) {
-          const int plane = p.sub ? phase * 4 + r * 2 + hb : r * 3 + s;
+        // stacked: lanes 64..127 hold the dY_lo products of channels 0..63; pairs: those of the next horizontal tap
+        const int co = (p.stacked || p.pairs) ? (m & 63) : co0 + m;
+        const int hshift = (p.pairs && m >= 64) ? 1 : 0;
+        if (any_tile && co < p.Cout && !(p.pairs && m >= 64 && !paired)) {
+          const int plane = p.sub ? phase * 4 + r * 2 + hb + hshift : r * 3 + s + hshift;
           float* dst = p.dwp + ((size_t)plane * p.Cout + co) * p.Cin_p + ci0 + c0;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -239,6 +254,14 @@ extern "C" int egaze_wgrad3x3_tc(const void* x_hi, const void* x_lo, const void*
   p.sub = sub ? 1 : 0;
   p.stacked = (precise && Cout == 64) ? 1 : 0;
   {
+    static int pairs_env = -1;
+    if (pairs_env < 0) {
+      const char* e = getenv("EGAZE_WGRAD_PAIRS");
+      pairs_env = e ? atoi(e) : 1;
+    }
+    p.pairs = (pairs_env && !precise && Cout == 64) ? 1 : 0;
+  }
+  {
     const char* e = getenv("EGAZE_WGRAD_STACKED");
     if (e && atoi(e) == 0) p.stacked = 0;
   }
@@ -271,7 +294,7 @@ extern "C" int egaze_wgrad3x3_tc(const void* x_hi, const void* x_lo, const void*
     if (rc) return rc;
   }
   // split-K factor: one CTA per SM is resident (208 KB of smem), so pick the factor that fills whole waves of SMs best
-  const int jobs = p.co_tiles * p.ci_tiles * (sub ? 8 : 3);
+  const int jobs = p.co_tiles * p.ci_tiles * (p.pairs ? (sub ? 4 : 2) : (sub ? 8 : 3));
   static int sms = 0;
   if (sms == 0) {
     int dev = 0;
