@@ -36,6 +36,9 @@ struct WgradParams {
                        // taps (s and s + 1) against the same X window -- two jobs per (co, ci) tile instead of three (sub-pixel: one per phase
                        // instead of two), dY and X are streamed a third (half) less often.  The paired job walks one extra tile column:
                        // the shifted rows of tile column t cover pixels [w0 - 1, w0 + BW - 1), so pixel W - 1 needs the column at w0 = W.
+  int ci2;             // one plane, Cin_p >= 128: a job covers TWO 64-channel input tiles (two X windows per stage, two N = 192 MMAs per
+                       // K step into accumulator blocks 0 / 256): the dY tile is streamed half as often, the kernel's L2 -> SM traffic per
+                       // FLOP drops by a third
   int sub;             // sub-pixel form (conv3x3_tc.cu ConvTcParams::sub): X is the low-resolution input, dY the phase-planar gradient
                        // [4N][H][W][Cout]; job = (co-tile, ci-tile, phase, horizontal tap b), the TWO vertical taps a share the dY tile
                        // (N = 128); dwp has 16 planes [phase*4 + a*2 + b]
@@ -65,9 +68,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid_constan
   const int total_tiles = p.N * p.tiles_h * tiles_w;
   const int phase = p.sub ? s >> 1 : 0, py = phase >> 1, px = phase & 1, hb = p.sub ? s & 1 : s;
   const int ntap_v = p.sub ? 2 : 3;
-  const int ci_t = job % p.ci_tiles;
-  const int co_t = job / p.ci_tiles;
-  const int co0 = co_t * 128, ci0 = ci_t * 64;
+  const int ci_jobs = p.ci2 ? p.ci_tiles / 2 : p.ci_tiles;
+  const int ci_t = job % ci_jobs;
+  const int co_t = job / ci_jobs;
+  const int co0 = co_t * 128, ci0 = ci_t * (p.ci2 ? 128 : 64);
 
   __shared__ uint64_t full[2], empty[2], acc_full;
   __shared__ uint32_t tmem_base_smem;
@@ -83,7 +87,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid_constan
   // precise: A_hi x [X_hi | X_lo] is ONE MMA of N = 128 (the X planes are 64-channel chunks LBO = plane stride apart),
   // so each tap owns 128 accumulator columns whose halves are added in the epilogue; fast: 64 columns per tap.
   constexpr uint32_t kD2 = 256;                       // column offset of the second accumulator block (precise)
-  constexpr uint32_t kTmemCols = NSPLIT == 2 ? 512 : 256;
+  constexpr uint32_t kTmemCols = 512;   // (one plane: the second block holds the second input-channel tile, ci2)
   if (warp == 1) {
     ptx::tmem_alloc(&tmem_base_smem, kTmemCols);
     ptx::tmem_relinquish();
@@ -96,7 +100,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid_constan
   const int KP = p.BH * p.BW;                       // pixels (K) per tile, multiple of 16
   const uint32_t dy_box_bytes = (uint32_t)KP * 128u;
   const uint32_t x_box_bytes = (uint32_t)(p.BH + 2) * p.BW * 128u;
-  const uint32_t tx_bytes = NSPLIT * ((p.m_chunks + (paired ? 1 : 0)) * dy_box_bytes + x_box_bytes);
+  const uint32_t tx_bytes = NSPLIT * ((p.m_chunks + (paired ? 1 : 0)) * dy_box_bytes + (p.ci2 ? 2 : 1) * x_box_bytes);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -125,6 +129,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid_constan
         const int xw = w0 - 1 + px + hb, xh = h0 - 1 + py;
         ptx::tma_load_4d(xb, &tmX_hi, &full[st], ci0, xw, xh, img);
         if (NSPLIT == 2) ptx::tma_load_4d(xb + p.x_plane_bytes, &tmX_lo, &full[st], ci0, xw, xh, img);
+        if (NSPLIT == 1 && p.ci2) ptx::tma_load_4d(xb + p.x_plane_bytes, &tmX_hi, &full[st], ci0 + 64, xw, xh, img);
         if (++st == 2) { st = 0; par ^= 1; }
       }
     }
@@ -157,6 +162,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid_constan
             const uint32_t first = acc | (uint32_t)k;   // 0 only for the very first K step of this CTA
             if (NSPLIT == 1) {
               ptx::umma_bf16(tmem_base, a_hi + ko, b_hi + ko, idesc, first);
+              if (p.ci2) ptx::umma_bf16(tmem_base + kD2, a_hi + ko, b_lo + ko, idesc, first);   // second input-channel tile -> block 2
             } else if (p.stacked) {
               ptx::umma_bf16(tmem_base, a_hi + ko, b_hi + ko, idesc, first);         // [dY_hi ; dY_lo] x X_hi -> D1
               ptx::umma_bf16(tmem_base + kD2, a_hi + ko, b_lo + ko, idesc, first);   // [dY_hi ; dY_lo] x X_lo -> D2
@@ -185,11 +191,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid_constan
     ptx::mbar_wait(&acc_full, 0);
     ptx::tc_fence_after();
     const bool any_tile = (int)blockIdx.x < total_tiles;
+    for (int hh = 0; hh < ((NSPLIT == 1 && p.ci2) ? 2 : 1); ++hh)
     for (int r = 0; r < ntap_v; ++r) {
 #pragma unroll 1
       for (int c0 = 0; c0 < 64; c0 += 32) {
         uint32_t v[32];
-        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(r * 64 + c0), v);
+        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(hh * kD2) + (uint32_t)(r * 64 + c0), v);
         if (NSPLIT == 2) {
           uint32_t v2[32];
           ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(ew * 32) << 16) + kD2 + (uint32_t)(r * 64 + c0), v2);
@@ -204,7 +211,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY_hi, const __grid_constan
         const int hshift = (p.pairs && m >= 64) ? 1 : 0;
         if (any_tile && co < p.Cout && !(p.pairs && m >= 64 && !paired)) {
           const int plane = p.sub ? phase * 4 + r * 2 + hb + hshift : r * 3 + s + hshift;
-          float* dst = p.dwp + ((size_t)plane * p.Cout + co) * p.Cin_p + ci0 + c0;
+          float* dst = p.dwp + ((size_t)plane * p.Cout + co) * p.Cin_p + ci0 + hh * 64 + c0;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             float4 val = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
@@ -265,11 +272,19 @@ extern "C" int egaze_wgrad3x3_tc(const void* x_hi, const void* x_lo, const void*
     const char* e = getenv("EGAZE_WGRAD_STACKED");
     if (e && atoi(e) == 0) p.stacked = 0;
   }
+  {
+    static int ci2_env = -1;
+    if (ci2_env < 0) {
+      const char* e = getenv("EGAZE_WGRAD_CI2");
+      ci2_env = e ? atoi(e) : 1;
+    }
+    p.ci2 = (ci2_env && !precise && p.ci_tiles % 2 == 0) ? 1 : 0;
+  }
   const int KP = p.BH * p.BW;
   p.dy_plane_bytes = 2 * KP * 128;                                  // room for both 64-channel chunks
   p.x_plane_bytes = ((p.BH + 2) * p.BW * 128 + 1023) / 1024 * 1024;
   // the MMA for tap r reads K rows [r*BW, r*BW + KP): always inside the (BH+2)*BW window
-  p.stage_bytes = p.nsplit * (p.dy_plane_bytes + p.x_plane_bytes);
+  p.stage_bytes = p.nsplit * (p.dy_plane_bytes + p.x_plane_bytes) + (p.ci2 ? p.x_plane_bytes : 0);
   p.dwp = dwp;
   const size_t smem = (size_t)2 * p.stage_bytes + 1024;
   EGAZE_CHECK_ARG(smem <= 224 * 1024, "wgrad3x3_tc: tile does not fit shared memory");
@@ -294,7 +309,7 @@ extern "C" int egaze_wgrad3x3_tc(const void* x_hi, const void* x_lo, const void*
     if (rc) return rc;
   }
   // split-K factor: one CTA per SM is resident (208 KB of smem), so pick the factor that fills whole waves of SMs best
-  const int jobs = p.co_tiles * p.ci_tiles * (p.pairs ? (sub ? 4 : 2) : (sub ? 8 : 3));
+  const int jobs = p.co_tiles * (p.ci2 ? p.ci_tiles / 2 : p.ci_tiles) * (p.pairs ? (sub ? 4 : 2) : (sub ? 8 : 3));
   static int sms = 0;
   if (sms == 0) {
     int dev = 0;
