@@ -551,7 +551,7 @@ extern "C" int egaze_col_sum_split(const void* hi, const void* lo, long long row
   if (by < 1) by = 1;
   dim3 block(bx, by);
   int blocks = (int)((rows + by - 1) / by);
-  if (blocks > 148 * 2) blocks = 148 * 2;
+  if (blocks > 148 * 8) blocks = 148 * 8;   // HBM-bound: 205 MB per launch at the last decoder layer
   const size_t smem = (size_t)by * C * sizeof(float);
   col_sum_split_kernel<<<blocks, block, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)hi, (const __nv_bfloat16*)lo,
                                                                       (size_t)rows, C, out);
